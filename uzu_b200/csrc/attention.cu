@@ -1,0 +1,555 @@
+// Attention kernels: AttentionPrepare (RoPE + Q transpose + KV append), split-KV flash-decode attention
+// behind the AttentionSinglePass / AttentionTwoPass1 / AttentionTwoPass2 entry points, KVCacheUpdate,
+// SigmoidGate.
+//
+// Specs: backends/cpu/kernel/attention/{attention_prepare.rs:7-126, attention_single_pass.rs:49-126,
+// attention_two_pass.rs:55-189, mask.rs:3-62, kv_cache_update.rs:7-28, sigmoid_gate.rs:7-22}.
+//
+// Decode attention design (HBM-bound: 2*ctx*Hkv*D*2 bytes per layer per token):
+//   * one CTA per (kv head, query token, kv split); all G = Hq/Hkv query heads of the group are processed
+//     against each K/V row while it is in registers, so the cache is read from HBM once, not G times;
+//   * a K/V row (D bf16) is read by D/EPL adjacent lanes with 128-bit loads (whole 32 B sectors),
+//     several keys per warp per step; f32 scores, f32 online softmax (expf, not exp2, to stay on the
+//     reference's arithmetic), f32 output accumulators;
+//   * the KV range is split across up to 32 CTAs so a batch-1 decode still fills 148 SMs; partial
+//     (max, sum, o) triples merge either in the caller-visible two-pass buffers (TwoPass1 + TwoPass2
+//     API) or, for the single-pass entry point, through a stream-ordered workspace where the last
+//     CTA of a (kv head, token) merges (one launch).
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace uzu {
+
+// ---------------------------------------------------------------------------------------------------
+// AttentionPrepare
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attention_prepare_kernel(const uzu_attention_prepare_args a) {
+    const uint32_t total_heads = a.has_kv ? a.num_q_heads + 2 * a.num_kv_heads : a.num_q_heads;
+    const uint32_t b = blockIdx.y, h = blockIdx.x;
+    const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(a.qkv);
+    const __nv_bfloat16* head = qkv + ((size_t)b * total_heads + h) * a.head_dim;
+    const bool is_query = !a.has_kv || h < a.num_q_heads;
+    const bool is_key = a.has_kv && h >= a.num_q_heads && h < a.num_q_heads + a.num_kv_heads;
+    const float* cosines = reinterpret_cast<const float*>(a.cosines);
+    const float* sines = reinterpret_cast<const float*>(a.sines);
+    uint32_t kv_token_offset = a.kv_token_offset;
+    if (a.dynamic_position) {
+        kv_token_offset = *reinterpret_cast<const uint32_t*>(a.dynamic_position);
+        if (a.has_rope) {
+            cosines += (size_t)kv_token_offset * a.rope_dim;
+            sines += (size_t)kv_token_offset * a.rope_dim;
+        }
+    }
+    for (uint32_t d = threadIdx.x; d < a.head_dim; d += blockDim.x) {
+        __nv_bfloat16 e = head[d];
+        if (a.has_rope && d < a.rope_dim && (is_query || is_key)) {
+            const uint32_t half = a.rope_dim / 2;
+            const uint32_t paired = d < half ? d + half : d - half;
+            const float input = bf2f(e);
+            const float pv = bf2f(head[paired]);
+            const float signed_p = d < half ? -pv : pv;
+            const float c = cosines[(size_t)b * a.rope_dim + d];
+            const float s = sines[(size_t)b * a.rope_dim + d];
+            e = f2bf(input * c + signed_p * s);
+        }
+        if (is_query) {
+            reinterpret_cast<__nv_bfloat16*>(a.queries)[((size_t)h * a.batch_dim + b) * a.head_dim + d] = e;
+        } else if (is_key) {
+            reinterpret_cast<__nv_bfloat16*>(a.keys)[((size_t)(kv_token_offset + b) * a.num_kv_heads + (h - a.num_q_heads)) * a.head_dim + d] = e;
+        } else {
+            reinterpret_cast<__nv_bfloat16*>(a.values)[((size_t)(kv_token_offset + b) * a.num_kv_heads + (h - a.num_q_heads - a.num_kv_heads)) * a.head_dim + d] = e;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// mask (mask.rs:3-62)
+// ---------------------------------------------------------------------------------------------------
+struct AttnParams {
+    uzu_attention_args a;
+    float* part_o;      // [suffix, heads, nb, D]
+    float* part_sum;    // [suffix, heads, nb]
+    float* part_max;
+    __nv_bfloat16* final_out;  // [suffix, heads, D] when merging in-kernel
+    unsigned int* counters;    // one per (token, head group) when nsplits > 1 and merging in-kernel
+    uint32_t nsplits, keys_per_split, nb, fuse_merge, heads_per_cta_group;
+};
+
+__device__ __forceinline__ bool should_use_key(const uzu_attention_args& a, uint32_t q_seq_idx, uint32_t prefix_length,
+                                               uint32_t suffix_position, uint32_t query_position, uint32_t i) {
+    bool use_key = true;
+    uint32_t key_position;
+    if (i >= prefix_length) {
+        const uint32_t kis = i - prefix_length;
+        if (a.is_trie) {
+            const uzu_trie_node node = reinterpret_cast<const uzu_trie_node*>(a.trie)[kis];
+            key_position = suffix_position + node.height;
+            if (a.is_causal) use_key &= (q_seq_idx >= node.trie_start && q_seq_idx <= node.trie_end);
+        } else {
+            key_position = suffix_position + kis;
+            if (a.is_causal) use_key &= (kis <= q_seq_idx);
+        }
+    } else {
+        if (a.is_kv_cache_ring) {
+            key_position = (prefix_length + i - a.ring_params.ring_offset) % prefix_length;
+            use_key &= key_position < a.ring_params.ring_length;
+        } else {
+            key_position = i;
+        }
+    }
+    if (a.is_sliding_window) {
+        const uint32_t w = a.sliding_window_size;
+        if (a.is_causal) use_key &= (key_position <= query_position && (query_position - key_position) < w);
+        else if (key_position <= query_position) use_key &= ((query_position - key_position) <= w / 2);
+        else use_key &= ((key_position - query_position) <= w / 2);
+    }
+    return use_key;
+}
+
+__device__ __forceinline__ float safe_exp_diff(float m, float gm) { return (m == -INFINITY) ? 0.0f : expf(m - gm); }
+
+constexpr int ATTN_WARPS = 4;
+
+template <int D, int G, int EPL>
+__global__ void __launch_bounds__(ATTN_WARPS * 32) attn_split_kernel(const AttnParams p) {
+    constexpr int LPK = D / EPL;     // lanes per key
+    constexpr int KPW = 32 / LPK;    // keys per warp step
+    static_assert(LPK >= 1 && LPK <= 32 && (EPL % 8) == 0, "bad attention tiling");
+    uzu_attention_args a = p.a;
+    uint32_t keys_per_split = p.keys_per_split;
+    if (a.dynamic_position) {
+        a.sequence_length = *reinterpret_cast<const uint32_t*>(a.dynamic_position) + a.suffix_length;
+        keys_per_split = (a.sequence_length + p.nsplits - 1) / p.nsplits;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / LPK, li = lane % LPK, d0 = li * EPL;
+    const uint32_t head0 = blockIdx.x * G, qs = blockIdx.y, split = blockIdx.z;
+    const uint32_t kvh = head0 / a.gqa_factor;
+
+    const uint32_t prefix_length = a.sequence_length - a.suffix_length;
+    const uint32_t suffix_position = a.is_kv_cache_ring ? a.ring_params.ring_length : prefix_length;
+    const uint32_t query_position = a.is_trie ? suffix_position + reinterpret_cast<const uzu_trie_node*>(a.trie)[qs].height
+                                              : suffix_position + qs;
+
+    const __nv_bfloat16* keys = reinterpret_cast<const __nv_bfloat16*>(a.keys) + (size_t)kvh * a.k_head_stride;
+    const __nv_bfloat16* values = reinterpret_cast<const __nv_bfloat16*>(a.values) + (size_t)kvh * a.v_head_stride;
+
+    float q[G][EPL];
+#pragma unroll
+    for (int h = 0; h < G; ++h) {
+        const __nv_bfloat16* qp = reinterpret_cast<const __nv_bfloat16*>(a.queries) + ((size_t)(head0 + h) * a.suffix_length + qs) * D + d0;
+#pragma unroll
+        for (int v = 0; v < EPL / 8; ++v) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(qp + v * 8);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                q[h][v * 8 + 2 * e] = a.scale * __low2float(h2[e]);
+                q[h][v * 8 + 2 * e + 1] = a.scale * __high2float(h2[e]);
+            }
+        }
+    }
+    float m[G], l[G], o[G][EPL];
+#pragma unroll
+    for (int h = 0; h < G; ++h) {
+        m[h] = -INFINITY;
+        l[h] = 0.0f;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) o[h][e] = 0.0f;
+    }
+    if (a.has_sinks && split == 0 && warp == 0 && sub == 0) {
+#pragma unroll
+        for (int h = 0; h < G; ++h) {
+            m[h] = bf2f(reinterpret_cast<const __nv_bfloat16*>(a.sinks)[head0 + h]);
+            l[h] = 1.0f;  // every lane of the group carries the same (m, l)
+        }
+    }
+
+    const uint32_t begin = min(a.sequence_length, split * keys_per_split);
+    const uint32_t end = min(a.sequence_length, begin + keys_per_split);
+    for (uint32_t base = begin + warp * KPW; base < end; base += ATTN_WARPS * KPW) {
+        const uint32_t i = base + sub;
+        const bool valid = i < end && should_use_key(a, qs, prefix_length, suffix_position, query_position, i);
+        float kf[EPL], vf[EPL];
+        if (valid) {
+            const __nv_bfloat16* kp = keys + (size_t)i * a.k_seq_stride + d0;
+            const __nv_bfloat16* vp = values + (size_t)i * a.v_seq_stride + d0;
+#pragma unroll
+            for (int v = 0; v < EPL / 8; ++v) {
+                const uint4 kr = *reinterpret_cast<const uint4*>(kp + v * 8);
+                const uint4 vr = *reinterpret_cast<const uint4*>(vp + v * 8);
+                const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kr);
+                const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vr);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    kf[v * 8 + 2 * e] = __low2float(k2[e]);
+                    kf[v * 8 + 2 * e + 1] = __high2float(k2[e]);
+                    vf[v * 8 + 2 * e] = __low2float(v2[e]);
+                    vf[v * 8 + 2 * e + 1] = __high2float(v2[e]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) { kf[e] = 0.0f; vf[e] = 0.0f; }
+        }
+#pragma unroll
+        for (int h = 0; h < G; ++h) {
+            float s = 0.0f;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) s += q[h][e] * kf[e];
+#pragma unroll
+            for (int off = LPK / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (valid) {
+                const float new_max = fmaxf(m[h], s);
+                const float factor = expf(m[h] - new_max);   // m = -inf -> 0
+                const float es = expf(s - new_max);
+                m[h] = new_max;
+                l[h] = l[h] * factor + es;
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) o[h][e] = o[h][e] * factor + es * vf[e];
+            }
+        }
+    }
+
+    // ---- merge the KPW key groups of a warp ------------------------------------------------------------
+#pragma unroll
+    for (int off = LPK; off < 32; off <<= 1) {
+#pragma unroll
+        for (int h = 0; h < G; ++h) {
+            const float m2 = __shfl_xor_sync(0xffffffffu, m[h], off);
+            const float l2 = __shfl_xor_sync(0xffffffffu, l[h], off);
+            const float gm = fmaxf(m[h], m2);
+            const float f1 = safe_exp_diff(m[h], gm), f2 = safe_exp_diff(m2, gm);
+            l[h] = l[h] * f1 + l2 * f2;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) {
+                const float o2 = __shfl_xor_sync(0xffffffffu, o[h][e], off);
+                o[h][e] = o[h][e] * f1 + o2 * f2;
+            }
+            m[h] = gm;
+        }
+    }
+
+    // ---- merge the warps of the CTA through shared memory --------------------------------------------------
+    __shared__ float sm_o[ATTN_WARPS][G][D];
+    __shared__ float sm_m[ATTN_WARPS][G], sm_l[ATTN_WARPS][G];
+    __shared__ unsigned int sm_ticket;
+    if (sub == 0) {
+#pragma unroll
+        for (int h = 0; h < G; ++h) {
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) sm_o[warp][h][d0 + e] = o[h][e];
+            if (li == 0) { sm_m[warp][h] = m[h]; sm_l[warp][h] = l[h]; }
+        }
+    }
+    __syncthreads();
+
+    const uint32_t H = a.num_heads;
+    const bool direct = (p.nsplits == 1) && p.fuse_merge;
+    for (int idx = threadIdx.x; idx < G * D; idx += blockDim.x) {
+        const int h = idx / D, d = idx % D;
+        float gm = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < ATTN_WARPS; ++w) gm = fmaxf(gm, sm_m[w][h]);
+        float ov = 0.0f, lv = 0.0f;
+#pragma unroll
+        for (int w = 0; w < ATTN_WARPS; ++w) {
+            const float f = safe_exp_diff(sm_m[w][h], gm);
+            ov += sm_o[w][h][d] * f;
+            lv += sm_l[w][h] * f;
+        }
+        const size_t o_off = (size_t)qs * H + head0 + h;
+        if (direct) {
+            p.final_out[o_off * D + d] = f2bf(ov / lv);
+        } else {
+            p.part_o[(o_off * p.nb + split) * D + d] = ov;
+            if (d == 0) {
+                p.part_sum[o_off * p.nb + split] = lv;
+                p.part_max[o_off * p.nb + split] = (gm == -INFINITY) ? -1e9f : gm;  // two-pass init value (attention_two_pass.rs:95)
+            }
+        }
+    }
+    if (direct) return;
+    if (!p.fuse_merge) {
+        // caller-visible two-pass buffers have 32 blocks; blocks this launch did not produce are empty
+        if (split == 0) {
+            for (uint32_t blk = p.nsplits + warp; blk < p.nb; blk += ATTN_WARPS)
+                for (int h = 0; h < G; ++h) {
+                    const size_t o_off = (size_t)qs * H + head0 + h;
+                    for (int d = lane; d < D; d += 32) p.part_o[(o_off * p.nb + blk) * D + d] = 0.0f;
+                    if (lane == 0) { p.part_sum[o_off * p.nb + blk] = 0.0f; p.part_max[o_off * p.nb + blk] = -1e9f; }
+                }
+        }
+        return;
+    }
+    // ---- in-kernel merge: the last CTA of this (token, head group) combines all splits -----------------------
+    __threadfence();
+    __syncthreads();
+    const uint32_t cidx = qs * gridDim.x + blockIdx.x;
+    if (threadIdx.x == 0) sm_ticket = atomicAdd(&p.counters[cidx], 1u);
+    __syncthreads();
+    if (sm_ticket != p.nsplits - 1) return;
+    __threadfence();
+    for (int idx = threadIdx.x; idx < G * D; idx += blockDim.x) {
+        const int h = idx / D, d = idx % D;
+        const size_t o_off = (size_t)qs * H + head0 + h;
+        float gm = -INFINITY;
+        for (uint32_t s = 0; s < p.nsplits; ++s) gm = fmaxf(gm, __ldcg(&p.part_max[o_off * p.nb + s]));
+        float gs = 0.0f, val = 0.0f;
+        for (uint32_t s = 0; s < p.nsplits; ++s) {
+            const float f = expf(__ldcg(&p.part_max[o_off * p.nb + s]) - gm);
+            gs += __ldcg(&p.part_sum[o_off * p.nb + s]) * f;
+            val += __ldcg(&p.part_o[(o_off * p.nb + s) * D + d]) * f;
+        }
+        p.final_out[o_off * D + d] = f2bf(val / gs);
+    }
+    if (threadIdx.x == 0) p.counters[cidx] = 0;
+}
+
+// AttentionTwoPass2 (attention_two_pass.rs:139-189): merge 32 blocks. One warp per (head, token).
+__global__ void __launch_bounds__(128) attn_two_pass2_kernel(const uzu_attention_two_pass2_args a) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (unit >= a.num_heads * a.suffix_length) return;
+    const float* partials = reinterpret_cast<const float*>(a.partials);
+    const float* sums = reinterpret_cast<const float*>(a.sums);
+    const float* maxs = reinterpret_cast<const float*>(a.maxs);
+    const size_t o_off = unit;  // = q_seq_idx * num_heads + head_idx
+    const float mymax = maxs[o_off * 32 + lane];
+    const float gmax = warp_max(mymax);
+    const float f = expf(mymax - gmax);
+    // global_sum accumulates block 0..31 in order in the reference; a tree sum differs by f32 rounding only
+    const float gsum = warp_sum(sums[o_off * 32 + lane] * f);
+    const uint32_t D = a.head_dim;
+    for (uint32_t j = lane; j < D; j += 32) {
+        float val = 0.0f;
+        for (int b = 0; b < 32; ++b) {
+            const float fb = __shfl_sync(0xffffffffu, f, b);
+            val += partials[(o_off * 32 + b) * D + j] * fb;
+        }
+        reinterpret_cast<__nv_bfloat16*>(a.out)[o_off * D + j] = f2bf(val / gsum);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// KVCacheUpdate / SigmoidGate
+// ---------------------------------------------------------------------------------------------------
+struct KvCopies {
+    uzu_kv_copy c[512];
+};
+__global__ void __launch_bounds__(256) kv_cache_update_kernel(__nv_bfloat16* keys, __nv_bfloat16* values, const __grid_constant__ KvCopies copies,
+                                                             uint32_t copy_count, uint32_t element_dim) {
+    // The reference applies copies sequentially per element (copy i may read a row written by copy j < i);
+    // one thread owns one element and walks the copies in order, which preserves that.
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= element_dim) return;
+    for (uint32_t i = 0; i < copy_count; ++i) {
+        const size_t s = (size_t)copies.c[i].source * element_dim + e, d = (size_t)copies.c[i].destination * element_dim + e;
+        keys[d] = keys[s];
+        values[d] = values[s];
+    }
+}
+
+__global__ void __launch_bounds__(256) sigmoid_gate_kernel(const __nv_bfloat16* gate, __nv_bfloat16* output, uint32_t total) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const float g = bf2f(gate[idx]);
+    const float sg = 1.0f / (1.0f + expf(-g));
+    output[idx] = f2bf(bf2f(output[idx]) * sg);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host dispatch
+// ---------------------------------------------------------------------------------------------------
+template <int D, int G, int EPL>
+static void launch_attn(uzu_command_buffer* cmd, const AttnParams& p, uint32_t head_groups) {
+    dim3 grid(head_groups, p.a.suffix_length, p.nsplits);
+    attn_split_kernel<D, G, EPL><<<grid, ATTN_WARPS * 32, 0, cmd->ctx->stream>>>(p);
+    after_launch(cmd, "attn_split_kernel");
+}
+
+template <int D>
+static void launch_attn_g(uzu_command_buffer* cmd, const AttnParams& p, int g) {
+    const uint32_t H = p.a.num_heads;
+    switch (g) {
+        case 8: launch_attn<D, 8, 8>(cmd, p, H / 8); break;
+        case 4: launch_attn<D, 4, 16>(cmd, p, H / 4); break;
+        case 2: launch_attn<D, 2, 16>(cmd, p, H / 2); break;
+        default: launch_attn<D, 1, 16>(cmd, p, H); break;
+    }
+}
+
+static bool attn_common_checks(uzu_command_buffer* cmd, const uzu_attention_args* a, const char* what) {
+    if (!a->queries || !a->keys || !a->values || !a->out) {
+        cmd->record_error(UZU_ERROR_INVALID_ARGUMENT, std::string(what) + ": null operand");
+        return false;
+    }
+    if (a->head_dim != 64 && a->head_dim != 128 && a->head_dim != 256) {
+        cmd->record_error(UZU_ERROR_UNSUPPORTED, std::string(what) + ": head_dim must be 64, 128 or 256");
+        return false;
+    }
+    if (a->gqa_factor == 0 || a->num_heads % a->gqa_factor != 0 || a->suffix_length == 0 || a->sequence_length < a->suffix_length) {
+        cmd->record_error(UZU_ERROR_INVALID_ARGUMENT, std::string(what) + ": bad head / sequence geometry");
+        return false;
+    }
+    if ((a->k_head_stride | a->k_seq_stride | a->v_head_stride | a->v_seq_stride) % 8 != 0 || ((a->keys | a->values | a->queries) & 15)) {
+        cmd->record_error(UZU_ERROR_UNSUPPORTED, std::string(what) + ": K/V strides must be multiples of 8 elements and 16-byte aligned");
+        return false;
+    }
+    if ((a->is_trie && !a->trie) || (a->has_sinks && !a->sinks)) {
+        cmd->record_error(UZU_ERROR_INVALID_ARGUMENT, std::string(what) + ": missing optional operand");
+        return false;
+    }
+    return true;
+}
+
+static int pick_group(uint32_t gqa) {
+    if (gqa % 8 == 0) return 8;
+    if (gqa % 4 == 0) return 4;
+    if (gqa % 2 == 0) return 2;
+    return 1;
+}
+
+static void dispatch_attn(uzu_command_buffer* cmd, const AttnParams& p, int g) {
+    switch (p.a.head_dim) {
+        case 64: launch_attn_g<64>(cmd, p, g); break;
+        case 128: launch_attn_g<128>(cmd, p, g); break;
+        default: launch_attn_g<256>(cmd, p, g); break;
+    }
+}
+
+}  // namespace uzu
+
+extern "C" {
+
+void uzu_attention_prepare_encode(uzu_command_buffer* cmd, const uzu_attention_prepare_args* a) {
+    if (!uzu::encodable(cmd, "attention_prepare")) return;
+    if (!a->qkv || !a->queries || a->head_dim == 0 || (a->has_kv && (!a->keys || !a->values || a->num_kv_heads == 0)) ||
+        (a->has_rope && (!a->cosines || !a->sines || a->rope_dim == 0 || a->rope_dim > a->head_dim || (a->rope_dim & 1))) ||
+        (a->num_q_heads == 0 && !a->has_kv)) {
+        cmd->record_error(UZU_ERROR_INVALID_ARGUMENT, "attention_prepare: inconsistent arguments");
+        return;
+    }
+    const uint32_t total_heads = a->has_kv ? a->num_q_heads + 2 * a->num_kv_heads : a->num_q_heads;
+    if (a->batch_dim == 0 || total_heads == 0) return;
+    dim3 grid(total_heads, a->batch_dim);
+    uint32_t threads = a->head_dim >= 256 ? 256 : (a->head_dim >= 128 ? 128 : 64);
+    uzu::attention_prepare_kernel<<<grid, threads, 0, cmd->ctx->stream>>>(*a);
+    uzu::after_launch(cmd, "attention_prepare_kernel");
+}
+
+void uzu_attention_single_pass_encode(uzu_command_buffer* cmd, const uzu_attention_args* a) {
+    if (!uzu::encodable(cmd, "attention_single_pass")) return;
+    if (!uzu::attn_common_checks(cmd, a, "attention_single_pass")) return;
+    uzu_context* ctx = cmd->ctx;
+    const int g = uzu::pick_group(a->gqa_factor);
+    const uint32_t head_groups = a->num_heads / g;
+    // enough CTAs for ~2 waves, >= 64 keys per split, <= 32 splits, and only for short suffixes (decode)
+    uint32_t nsplits = 1;
+    if (a->suffix_length <= 16) {
+        const uint32_t ctas = head_groups * a->suffix_length;
+        const uint32_t want = (2u * (uint32_t)ctx->sm_count + ctas - 1) / ctas;
+        const uint32_t cap = (a->sequence_length + 63) / 64;
+        nsplits = std::max(1u, std::min(std::min(want, cap), 32u));
+    }
+    uzu::AttnParams p{};
+    p.a = *a;
+    p.final_out = reinterpret_cast<__nv_bfloat16*>(a->out);
+    p.fuse_merge = 1;
+    p.nsplits = nsplits;
+    p.nb = nsplits;
+    p.keys_per_split = (a->sequence_length + nsplits - 1) / nsplits;
+    if (nsplits > 1) {
+        const size_t units = (size_t)a->suffix_length * a->num_heads * nsplits;
+        const size_t need = units * (a->head_dim + 2) * sizeof(float);
+        if (need > ctx->attn_ws_bytes) {  // grows outside graph capture only (decode needs < 2 MiB)
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(ctx->attn_ws);
+            if (cudaMalloc(&ctx->attn_ws, need) != cudaSuccess) {
+                ctx->attn_ws = nullptr;
+                ctx->attn_ws_bytes = 0;
+                cmd->record_error(UZU_ERROR_OUT_OF_MEMORY, "attention_single_pass: workspace allocation failed");
+                return;
+            }
+            ctx->attn_ws_bytes = need;
+        }
+        if ((size_t)a->suffix_length * head_groups > 65536) {
+            cmd->record_error(UZU_ERROR_UNSUPPORTED, "attention_single_pass: too many (token, head group) pairs for the split path");
+            return;
+        }
+        p.part_o = ctx->attn_ws;
+        p.part_sum = ctx->attn_ws + units * a->head_dim;
+        p.part_max = p.part_sum + units;
+        p.counters = ctx->attn_counters;
+    }
+    uzu::dispatch_attn(cmd, p, g);
+}
+
+void uzu_attention_two_pass1_encode(uzu_command_buffer* cmd, const uzu_attention_args* a) {
+    if (!uzu::encodable(cmd, "attention_two_pass1")) return;
+    if (!uzu::attn_common_checks(cmd, a, "attention_two_pass1")) return;
+    if (!a->sums || !a->maxs) {
+        cmd->record_error(UZU_ERROR_INVALID_ARGUMENT, "attention_two_pass1: missing sums / maxs");
+        return;
+    }
+    uzu_context* ctx = cmd->ctx;
+    const int g = uzu::pick_group(a->gqa_factor);
+    const uint32_t head_groups = a->num_heads / g;
+    const uint32_t ctas = head_groups * a->suffix_length;
+    const uint32_t want = (2u * (uint32_t)ctx->sm_count + ctas - 1) / ctas;
+    const uint32_t cap = (a->sequence_length + 63) / 64;
+    uzu::AttnParams p{};
+    p.a = *a;
+    p.part_o = reinterpret_cast<float*>(a->out);
+    p.part_sum = reinterpret_cast<float*>(a->sums);
+    p.part_max = reinterpret_cast<float*>(a->maxs);
+    p.fuse_merge = 0;
+    p.nsplits = std::max(1u, std::min(std::min(want, cap), 32u));
+    p.nb = 32;  // TOTAL_BLOCKS_COUNT (attention_two_pass.rs:10)
+    p.keys_per_split = (a->sequence_length + p.nsplits - 1) / p.nsplits;
+    uzu::dispatch_attn(cmd, p, g);
+}
+
+void uzu_attention_two_pass2_encode(uzu_command_buffer* cmd, const uzu_attention_two_pass2_args* a) {
+    if (!uzu::encodable(cmd, "attention_two_pass2")) return;
+    if (!a->partials || !a->sums || !a->maxs || !a->out || a->head_dim == 0) {
+        cmd->record_error(UZU_ERROR_INVALID_ARGUMENT, "attention_two_pass2: null operand");
+        return;
+    }
+    const uint32_t units = a->num_heads * a->suffix_length;
+    if (units == 0) return;
+    uzu::attn_two_pass2_kernel<<<(units + 3) / 4, 128, 0, cmd->ctx->stream>>>(*a);
+    uzu::after_launch(cmd, "attn_two_pass2_kernel");
+}
+
+void uzu_kv_cache_update_encode(uzu_command_buffer* cmd, const uzu_kv_cache_update_args* a) {
+    if (!uzu::encodable(cmd, "kv_cache_update")) return;
+    if (a->copy_count == 0 || a->element_dim == 0) return;  // flat decode path: nothing to move (state.rs:185-189)
+    if (!a->in_place_keys || !a->in_place_values || !a->copies) {
+        cmd->record_error(UZU_ERROR_INVALID_ARGUMENT, "kv_cache_update: null operand");
+        return;
+    }
+    for (uint32_t done = 0; done < a->copy_count; done += 512) {
+        uzu::KvCopies c;
+        const uint32_t n = std::min(512u, a->copy_count - done);
+        memcpy(c.c, a->copies + done, n * sizeof(uzu_kv_copy));
+        uzu::kv_cache_update_kernel<<<(a->element_dim + 255) / 256, 256, 0, cmd->ctx->stream>>>(
+            reinterpret_cast<__nv_bfloat16*>(a->in_place_keys), reinterpret_cast<__nv_bfloat16*>(a->in_place_values), c, n, a->element_dim);
+        uzu::after_launch(cmd, "kv_cache_update_kernel");
+    }
+}
+
+void uzu_sigmoid_gate_encode(uzu_command_buffer* cmd, uint64_t gate, uint64_t output, uint32_t total_elements) {
+    if (!uzu::encodable(cmd, "sigmoid_gate")) return;
+    if (total_elements == 0) return;
+    if (!gate || !output) {
+        cmd->record_error(UZU_ERROR_INVALID_ARGUMENT, "sigmoid_gate: null operand");
+        return;
+    }
+    uzu::sigmoid_gate_kernel<<<(total_elements + 255) / 256, 256, 0, cmd->ctx->stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(gate), reinterpret_cast<__nv_bfloat16*>(output), total_elements);
+    uzu::after_launch(cmd, "sigmoid_gate_kernel");
+}
+
+}  // extern "C"

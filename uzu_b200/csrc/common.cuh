@@ -1,0 +1,143 @@
+// Shared device/host helpers for libuzu_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/uzu_b200.h"
+
+namespace uzu {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_last_error(const std::string& msg);
+uzu_status fail(uzu_status st, const std::string& msg);
+
+#define UZU_CUDA_TRY(expr)                                                                         \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return ::uzu::fail(UZU_ERROR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+// ---- runtime objects ------------------------------------------------------------------------
+struct Context;
+
+}  // namespace uzu
+
+struct uzu_context {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    size_t peak_bytes = 0, live_bytes = 0;
+    // split-K workspace shared by the matmul kernels (stream-ordered, so one copy is enough)
+    float* splitk_ws = nullptr;
+    unsigned int* splitk_counters = nullptr;
+    size_t splitk_ws_bytes = 0;
+    size_t splitk_counter_count = 0;
+    // sampling workspace
+    unsigned long long* sampling_ws = nullptr;
+    // split-KV attention workspace (partials + tickets), stream-ordered
+    float* attn_ws = nullptr;
+    size_t attn_ws_bytes = 0;
+    unsigned int* attn_counters = nullptr;
+    bool vmm_supported = false;
+    size_t vmm_granularity = 0;
+};
+
+struct uzu_command_buffer {
+    uzu_context* ctx = nullptr;
+    std::string name;
+    enum State { Initial, Encoding, Executable, Pending, Completed } state = Initial;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    uzu_status sticky = UZU_OK;
+    std::string sticky_msg;
+    uint64_t launches = 0;
+    // Programmatic dependent launch for kernels that opt in (set by the engine)
+    bool use_pdl = false;
+
+    void record_error(uzu_status st, const std::string& msg) {
+        if (sticky == UZU_OK) {
+            sticky = st;
+            sticky_msg = msg;
+        }
+    }
+};
+
+namespace uzu {
+
+// Checks the launch and counts it. Must follow every <<<>>> in an encode function.
+inline void after_launch(uzu_command_buffer* cmd, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) cmd->record_error(UZU_ERROR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    cmd->launches++;
+}
+
+inline bool encodable(uzu_command_buffer* cmd, const char* what) {
+    if (!cmd) return false;
+    if (cmd->state != uzu_command_buffer::Encoding) {
+        cmd->record_error(UZU_ERROR_INVALID_ARGUMENT, std::string(what) + ": command buffer is not in the Encoding state");
+        return false;
+    }
+    return true;
+}
+
+// ---- device helpers -------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float bf16_bits_to_f32(uint16_t h) { return __uint_as_float(((uint32_t)h) << 16); }
+__device__ __forceinline__ float bf2f(__nv_bfloat16 h) { return __bfloat162float(h); }
+// round-to-nearest-even, identical to half::bf16::from_f32
+__device__ __forceinline__ __nv_bfloat16 f2bf(float f) { return __float2bfloat16_rn(f); }
+__device__ __forceinline__ float round_bf16(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024; `red` is >= 32 floats of shared memory. All threads get the result.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = (lane < nw) ? red[lane] : 0.0f;
+    t = warp_sum(t);
+    return t;
+}
+
+__device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// activation math: backends/common/gpu_types/activation_type.rs:16-65 (f32 in, f32 out)
+__device__ __forceinline__ float act_f32(uint32_t act, float x) {
+    switch (act) {
+        case UZU_ACT_SILU: return x / (1.0f + expf(-x));
+        case UZU_ACT_GELU_APPROX: {
+            float t = 0.7978846f * (x + 0.044715f * x * x * x);
+            return 0.5f * x * (1.0f + tanhf(t));
+        }
+        case UZU_ACT_GELU_EXACT: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+        case UZU_ACT_SOFTPLUS: return x > 20.0f ? x : logf(1.0f + expf(x));
+        default: return x;
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace uzu

@@ -1,0 +1,131 @@
+// DeltaNet decode kernels for Qwen3.5 hybrid layers:
+//   DeltaNetConvUpdate  backends/cpu/kernel/gdn/conv_update.rs:8-55   (1-token causal conv + SiLU, f32 rolling state)
+//   DeltaNetUpdate      backends/cpu/kernel/gdn/update.rs:13-144      (gated delta rule over S[Hv, Dv, Dk] + RMSNorm * SiLU(z))
+// Parameter / state dtypes are f32 (what the engine allocates and Metal declares; the reference CPU
+// kernel's `*const T` typing of these buffers is the bug documented in SURVEY.md row a11).
+// State traffic: Hv*Dv*Dk*4 B read + written per layer per token (2 MB for Qwen3.5-0.8B).
+#include "common.cuh"
+
+namespace uzu {
+
+__global__ void __launch_bounds__(256) delta_net_conv_update_kernel(const uzu_delta_net_conv_update_args a) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.conv_dim) return;
+    const float* w = reinterpret_cast<const float*>(a.conv_weight) + (size_t)c * a.kernel_size;
+    float* st = reinterpret_cast<float*>(a.state) + (size_t)c * a.state_stride;
+    __nv_bfloat16* io = reinterpret_cast<__nv_bfloat16*>(a.in_out);
+    const uint32_t taps = a.kernel_size - 1;
+    const float x = bf2f(io[c]);
+    float acc = a.has_bias ? reinterpret_cast<const float*>(a.bias)[c] : 0.0f;
+    for (uint32_t t = 0; t < taps; ++t) acc += st[t] * w[t];
+    acc += x * w[taps];
+    io[c] = f2bf(act_f32(UZU_ACT_SILU, acc));
+    for (uint32_t t = 1; t < taps; ++t) st[t - 1] = st[t];
+    st[taps - 1] = x;
+}
+
+// one CTA per v-head; HEAD_K_DIM = 128 (the only variant the reference instantiates)
+constexpr int DN_WARPS = 8;
+__global__ void __launch_bounds__(DN_WARPS * 32) delta_net_update_kernel(const uzu_delta_net_update_args a) {
+    constexpr int DK = 128;
+    __shared__ float sq[DK], sk[DK];
+    __shared__ float so[256];
+    __shared__ float red[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t hv = blockIdx.x;
+    const uint32_t hk = hv / (a.num_v_heads / a.num_k_heads);
+    const uint32_t conv_dim = 2 * a.key_dim + a.value_dim;
+    const __nv_bfloat16* in_proj = reinterpret_cast<const __nv_bfloat16*>(a.in_proj);
+
+    // L2-normalise q and k, scale q by Dk^-0.5 (update.rs:60-80)
+    float qv = 0.0f, kv = 0.0f;
+    if (threadIdx.x < DK) {
+        qv = bf2f(in_proj[hk * DK + threadIdx.x]);
+        kv = bf2f(in_proj[a.key_dim + hk * DK + threadIdx.x]);
+    }
+    const float qn = block_sum(qv * qv, red);
+    const float kn = block_sum(kv * kv, red);
+    const float qi = 1.0f / sqrtf(qn + 1e-6f), ki = 1.0f / sqrtf(kn + 1e-6f);
+    const float qscale = 1.0f / sqrtf((float)DK);
+    if (threadIdx.x < DK) {
+        float qq = qv * qi;
+        qq = qq * qscale;
+        sq[threadIdx.x] = qq;
+        sk[threadIdx.x] = kv * ki;
+    }
+    __syncthreads();
+    const float kq_part = threadIdx.x < DK ? sk[threadIdx.x] * sq[threadIdx.x] : 0.0f;
+    const float kq = block_sum(kq_part, red);
+
+    const float beta_raw = bf2f(in_proj[conv_dim + a.value_dim + hv]);
+    const float beta = 1.0f / (1.0f + expf(-beta_raw));
+    const float a_raw = bf2f(in_proj[conv_dim + a.value_dim + a.num_v_heads + hv]);
+    const float sp_in = a_raw + reinterpret_cast<const float*>(a.dt_bias)[hv];
+    const float sp = sp_in > 20.0f ? sp_in : logf(1.0f + expf(sp_in));
+    const float gdec = -expf(reinterpret_cast<const float*>(a.a_log)[hv]) * sp;
+    const float decay = expf(gdec);
+
+    float* state = reinterpret_cast<float*>(a.state) + (size_t)hv * a.head_v_dim * DK;
+    const float4 q4 = *reinterpret_cast<const float4*>(&sq[lane * 4]);
+    const float4 k4 = *reinterpret_cast<const float4*>(&sk[lane * 4]);
+    for (uint32_t i = warp; i < a.head_v_dim; i += DN_WARPS) {
+        float4* rowp = reinterpret_cast<float4*>(state + (size_t)i * DK) + lane;
+        const float4 s = *rowp;
+        float sqa = s.x * q4.x + s.y * q4.y + s.z * q4.z + s.w * q4.w;
+        float ska = s.x * k4.x + s.y * k4.y + s.z * k4.z + s.w * k4.w;
+        sqa = warp_sum(sqa);
+        ska = warp_sum(ska);
+        const float v_i = bf2f(in_proj[2 * a.key_dim + hv * a.head_v_dim + i]);
+        const float retrieved = decay * ska;
+        const float delta = beta * (v_i - retrieved);
+        if (lane == 0) so[i] = decay * sqa + delta * kq;
+        float4 ns;
+        ns.x = decay * s.x + k4.x * delta;
+        ns.y = decay * s.y + k4.y * delta;
+        ns.z = decay * s.z + k4.z * delta;
+        ns.w = decay * s.w + k4.w * delta;
+        *rowp = ns;
+    }
+    __syncthreads();
+    const float ov = threadIdx.x < a.head_v_dim ? so[threadIdx.x] : 0.0f;
+    const float ss = block_sum(ov * ov, red);
+    const float inv_rms = 1.0f / sqrtf(ss / (float)a.head_v_dim + a.norm_epsilon);
+    if (threadIdx.x < a.head_v_dim) {
+        const uint32_t i = threadIdx.x;
+        const float nw = reinterpret_cast<const float*>(a.norm_weight)[i];
+        const float z = bf2f(in_proj[conv_dim + hv * a.head_v_dim + i]);
+        const float zs = act_f32(UZU_ACT_SILU, z);
+        reinterpret_cast<__nv_bfloat16*>(a.out)[hv * a.head_v_dim + i] = f2bf(ov * inv_rms * nw * zs);
+    }
+}
+
+}  // namespace uzu
+
+extern "C" {
+
+void uzu_delta_net_conv_update_encode(uzu_command_buffer* cmd, const uzu_delta_net_conv_update_args* a) {
+    if (!uzu::encodable(cmd, "delta_net_conv_update")) return;
+    if (!a->conv_weight || !a->in_out || !a->state || a->kernel_size < 2 || (a->has_bias && !a->bias)) {
+        cmd->record_error(UZU_ERROR_INVALID_ARGUMENT, "delta_net_conv_update: inconsistent arguments");
+        return;
+    }
+    if (a->conv_dim == 0) return;
+    uzu::delta_net_conv_update_kernel<<<(a->conv_dim + 255) / 256, 256, 0, cmd->ctx->stream>>>(*a);
+    uzu::after_launch(cmd, "delta_net_conv_update_kernel");
+}
+
+void uzu_delta_net_update_encode(uzu_command_buffer* cmd, const uzu_delta_net_update_args* a) {
+    if (!uzu::encodable(cmd, "delta_net_update")) return;
+    if (!a->in_proj || !a->a_log || !a->dt_bias || !a->norm_weight || !a->state || !a->out) {
+        cmd->record_error(UZU_ERROR_INVALID_ARGUMENT, "delta_net_update: null operand");
+        return;
+    }
+    if (a->head_k_dim != 128 || a->head_v_dim == 0 || a->head_v_dim > 256 || a->num_k_heads == 0 || a->num_v_heads % a->num_k_heads != 0) {
+        cmd->record_error(UZU_ERROR_UNSUPPORTED, "delta_net_update: HEAD_K_DIM must be 128 and head_v_dim <= 256");
+        return;
+    }
+    uzu::delta_net_update_kernel<<<a->num_v_heads, uzu::DN_WARPS * 32, 0, cmd->ctx->stream>>>(*a);
+    uzu::after_launch(cmd, "delta_net_update_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,1291 @@
+// Host engine: C++ mirror of the reference's backend-agnostic Rust host code, driving the C-ABI kernels of
+// this library in the reference's op order. Mirrors (paths relative to crates/backend-uzu/src/):
+//   Engine::load_language_model          engine/language_model/mod.rs:58-116 (config.json + model.safetensors)
+//   ParameterLoader / leaf.read_allocation parameters/loader.rs:64-250 (pread into DenseBuffer::cpu_ptr)
+//   WeightMatrix::load / matmul_b         encodable_block/weight_matrix.rs:101-215
+//   Decoder::encode                       encodable_block/decoder.rs:138-203
+//   Transformer::encode                   encodable_block/transformer.rs:226-329
+//   TransformerLayer::encode              encodable_block/transformer_layer.rs:194-238
+//   Attention::attend                     encodable_block/mixer/attention/mode.rs:45-144
+//   AttentionState                        encodable_block/mixer/attention/state.rs:62-237
+//   DeltaNet::encode (m == 1 branch)      encodable_block/mixer/delta_net.rs:473-535
+//   DenseMlp::encode                      encodable_block/mlp/dense.rs:32-48
+//   Embedding lookup / readout            encodable_block/embedding.rs:345-456
+//   Sampling::encode                      encodable_block/sampling/mod.rs:83-195
+//   LanguageModelStream::{new,generate}   engine/language_model/stream/stream.rs:131-782
+// Differences that are B200 design, not semantics: scratch is a fixed arena (so a decode step can be a
+// CUDA graph), RoPE tables are the reference's host f32 table evaluated once for every position and kept on
+// the device, per-step scalars (prefix length, seeds) live in a device-side DecodeState so a captured
+// step replays unchanged.
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cmath>
+#include <stdexcept>
+#include <string>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <set>
+#include <sstream>
+#include <vector>
+
+#include "common.cuh"
+
+namespace uzu {
+
+// =====================================================================================================
+// minimal JSON
+// =====================================================================================================
+struct Json {
+    enum Type { Null, Bool, Num, Str, Arr, Obj } type = Null;
+    bool b = false;
+    double num = 0;
+    std::string str;
+    std::vector<Json> arr;
+    std::vector<std::pair<std::string, Json>> obj;
+
+    const Json* get(const std::string& k) const {
+        for (auto& kv : obj)
+            if (kv.first == k) return &kv.second;
+        return nullptr;
+    }
+    const Json& at(const std::string& k) const {
+        const Json* j = get(k);
+        if (!j) throw std::runtime_error("config: missing field '" + k + "'");
+        return *j;
+    }
+    bool is_null() const { return type == Null; }
+    std::string type_tag() const { return at("type").str; }
+    double number() const {
+        if (type != Num) throw std::runtime_error("config: expected a number");
+        return num;
+    }
+    uint32_t u32() const { return (uint32_t)number(); }
+    bool boolean() const {
+        if (type != Bool) throw std::runtime_error("config: expected a bool");
+        return b;
+    }
+};
+
+struct JsonParser {
+    const char* p;
+    const char* end;
+    void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p; }
+    Json parse() {
+        ws();
+        if (p >= end) throw std::runtime_error("json: unexpected end");
+        Json j;
+        if (*p == '{') {
+            j.type = Json::Obj;
+            ++p; ws();
+            if (*p == '}') { ++p; return j; }
+            while (true) {
+                ws();
+                Json k = parse_string();
+                ws();
+                if (*p != ':') throw std::runtime_error("json: expected ':'");
+                ++p;
+                j.obj.emplace_back(k.str, parse());
+                ws();
+                if (*p == ',') { ++p; continue; }
+                if (*p == '}') { ++p; break; }
+                throw std::runtime_error("json: expected ',' or '}'");
+            }
+        } else if (*p == '[') {
+            j.type = Json::Arr;
+            ++p; ws();
+            if (*p == ']') { ++p; return j; }
+            while (true) {
+                j.arr.push_back(parse());
+                ws();
+                if (*p == ',') { ++p; continue; }
+                if (*p == ']') { ++p; break; }
+                throw std::runtime_error("json: expected ',' or ']'");
+            }
+        } else if (*p == '"') {
+            j = parse_string();
+        } else if (!strncmp(p, "true", 4)) { j.type = Json::Bool; j.b = true; p += 4; }
+        else if (!strncmp(p, "false", 5)) { j.type = Json::Bool; j.b = false; p += 5; }
+        else if (!strncmp(p, "null", 4)) { j.type = Json::Null; p += 4; }
+        else {
+            char* e = nullptr;
+            j.type = Json::Num;
+            j.num = strtod(p, &e);
+            if (e == p) throw std::runtime_error("json: bad token");
+            p = e;
+        }
+        return j;
+    }
+    Json parse_string() {
+        if (*p != '"') throw std::runtime_error("json: expected string");
+        ++p;
+        Json j;
+        j.type = Json::Str;
+        while (p < end && *p != '"') {
+            if (*p == '\\' && p + 1 < end) {
+                ++p;
+                switch (*p) {
+                    case 'n': j.str += '\n'; break;
+                    case 't': j.str += '\t'; break;
+                    case 'u': j.str += '?'; p += 4; break;
+                    default: j.str += *p;
+                }
+                ++p;
+            } else {
+                j.str += *p++;
+            }
+        }
+        ++p;
+        return j;
+    }
+};
+
+static Json parse_json(const std::string& text) {
+    JsonParser jp{text.data(), text.data() + text.size()};
+    return jp.parse();
+}
+
+static std::string read_file(const std::string& path) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("cannot open " + path);
+    std::string s;
+    char buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) s.append(buf, n);
+    fclose(f);
+    return s;
+}
+
+// =====================================================================================================
+// parameters (safetensors)
+// =====================================================================================================
+struct TensorInfo {
+    std::string dtype;
+    std::vector<uint64_t> shape;
+    uint64_t begin = 0, end = 0;
+};
+
+struct ParameterLoader {
+    int fd = -1;
+    uint64_t data_offset = 0;
+    std::map<std::string, TensorInfo> tensors;
+    std::map<std::string, std::string> metadata;
+    std::set<std::string> validated;
+
+    explicit ParameterLoader(const std::string& path) {
+        fd = open(path.c_str(), O_RDONLY);
+        if (fd < 0) throw std::runtime_error("cannot open " + path);
+        uint64_t hlen = 0;
+        if (pread(fd, &hlen, 8, 0) != 8) throw std::runtime_error("safetensors: short header");
+        std::string header(hlen, '\0');
+        if ((uint64_t)pread(fd, &header[0], hlen, 8) != hlen) throw std::runtime_error("safetensors: short header");
+        data_offset = 8 + hlen;
+        Json j = parse_json(header);
+        for (auto& kv : j.obj) {
+            if (kv.first == "__metadata__") {
+                for (auto& m : kv.second.obj) metadata[m.first] = m.second.str;
+                continue;
+            }
+            TensorInfo t;
+            t.dtype = kv.second.at("dtype").str;
+            for (auto& d : kv.second.at("shape").arr) t.shape.push_back((uint64_t)d.num);
+            t.begin = (uint64_t)kv.second.at("data_offsets").arr[0].num;
+            t.end = (uint64_t)kv.second.at("data_offsets").arr[1].num;
+            tensors[kv.first] = t;
+        }
+    }
+    ~ParameterLoader() { if (fd >= 0) close(fd); }
+
+    // leaf(name).validate(shape, dtype) (parameters/loader.rs:140-160)
+    const TensorInfo& validate(const std::string& name, const std::vector<uint64_t>& shape, const std::string& dtype) {
+        auto it = tensors.find(name);
+        if (it == tensors.end()) throw std::runtime_error("missing tensor '" + name + "'");
+        if (it->second.shape != shape) {
+            std::ostringstream os;
+            os << "tensor '" << name << "' has shape [";
+            for (auto d : it->second.shape) os << d << ",";
+            os << "], expected [";
+            for (auto d : shape) os << d << ",";
+            os << "]";
+            throw std::runtime_error(os.str());
+        }
+        if (it->second.dtype != dtype) throw std::runtime_error("tensor '" + name + "' has dtype " + it->second.dtype + ", expected " + dtype);
+        validated.insert(name);
+        return it->second;
+    }
+    // read_allocation: pread straight into the buffer's CPU pointer (loader.rs:162-179)
+    void read_into(const TensorInfo& t, void* dst) {
+        uint64_t done = 0, total = t.end - t.begin;
+        while (done < total) {
+            ssize_t n = pread(fd, (char*)dst + done, std::min<uint64_t>(total - done, 1u << 30), data_offset + t.begin + done);
+            if (n <= 0) throw std::runtime_error("safetensors: short read");
+            done += (uint64_t)n;
+        }
+    }
+    void assert_all_validated() {  // loader.rs:230-250
+        for (auto& kv : tensors)
+            if (!validated.count(kv.first)) throw std::runtime_error("tensor '" + kv.first + "' was not consumed by the model");
+    }
+};
+
+// =====================================================================================================
+// model
+// =====================================================================================================
+struct Buf {
+    uzu_buffer* b = nullptr;
+    uint64_t ptr() const { return b ? uzu_buffer_gpu_ptr(b) : 0; }
+};
+
+struct WeightMatrix {
+    Buf values, scales, zero_points, biases;
+    uint32_t prologue = UZU_B_FULL_PRECISION, mode = UZU_QMODE_U4, group_size = 0, bits = 16;
+    uint32_t rows = 0, cols = 0;
+    uint64_t bytes = 0;  // algorithmic bytes streamed by one full pass over the matrix
+};
+
+struct Linear {
+    WeightMatrix w;
+    uint32_t in_dim = 0, out_dim = 0;
+};
+
+struct NormCfg {
+    float epsilon = 1e-5f, scale_offset = 0.0f;
+    bool full_layer = false, subtract_mean = false, has_scale = true, has_biases = false;
+};
+struct Norm {
+    NormCfg cfg;
+    Buf scales;
+    uint32_t n = 0;
+    bool present = false;
+};
+
+struct RopeCfg {
+    int kind = 0;  // 0 unscaled, 1 linear, 2 llama
+    float base = 10000.0f, scaling_factor = 1.0f, low = 1.0f, high = 1.0f;
+    uint32_t head_dim = 0, original_context_length = 0, max_sequence_length = 0;
+    bool operator==(const RopeCfg& o) const {
+        return kind == o.kind && base == o.base && scaling_factor == o.scaling_factor && low == o.low && high == o.high &&
+               head_dim == o.head_dim && original_context_length == o.original_context_length;
+    }
+};
+
+struct AttentionLayer {
+    Linear qkv, out, gate;
+    bool has_gate = false;
+    Norm qnorm, knorm;
+    uint32_t num_heads = 0, num_groups = 0, head_dim = 0;
+    bool is_causal = true;
+    bool has_scale = false;
+    float scale = 0.0f;
+    int rope_index = -1;
+};
+
+struct DeltaNetLayer {
+    Linear in_proj, out_proj;
+    Buf conv_weight, conv_bias, a_log, dt_bias, norm_weight;
+    bool conv_has_bias = false;
+    uint32_t num_heads = 0, num_groups = 0, head_dim = 0, value_head_dim = 0, kernel_size = 0;
+    uint32_t key_dim = 0, value_dim = 0, conv_dim = 0, total_proj_dim = 0;
+    float norm_epsilon = 1e-6f;
+};
+
+struct Layer {
+    bool is_attention = true;
+    Norm pre_mixer, pre_mlp;
+    AttentionLayer attn;
+    DeltaNetLayer dn;
+    Linear up, down;
+    uint32_t hidden_dim = 0;
+    uint32_t act = UZU_ACT_SILU;
+};
+
+struct LayerState {
+    // attention
+    uzu_sparse_buffer* k_sparse = nullptr;
+    uzu_sparse_buffer* v_sparse = nullptr;
+    Buf k_dense, v_dense;
+    uint64_t keys = 0, values = 0;
+    uint32_t length = 0;
+    uint32_t mapped_pages = 0;
+    size_t row_bytes = 0;
+    // delta net
+    Buf conv_state, ssm_state, conv_snapshot, ssm_snapshot;
+    size_t conv_bytes = 0, ssm_bytes = 0;
+};
+
+struct DecodeState {      // device-resident per-stream scalars (one u32-aligned block)
+    uint32_t position;    // prefix length == absolute position of the token being fed
+    uint32_t step;        // decode steps issued so far
+    uint64_t base_seed;
+};
+
+constexpr uint32_t MAX_ROWS = 1024;              // ATTENTION_SUFFIX_CAPACITY (mixer/attention/state.rs:14)
+constexpr uint32_t TOKEN_RING = 256;
+
+__global__ void decode_step_begin_kernel(const DecodeState* st, unsigned long long* seeds) {
+    // PRng::derive(position) (encodable_block/sampling/prng.rs:12-23)
+    unsigned long long h = st->base_seed + (unsigned long long)st->position;
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdULL;
+    h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL;
+    h ^= h >> 33;
+    seeds[0] = h;
+}
+
+__global__ void decode_step_end_kernel(DecodeState* st, const uint32_t* sampled, uint32_t* token_ids, volatile uint32_t* host_ring,
+                                       uint32_t* dev_out, uint32_t dev_out_base_step) {
+    const uint32_t tok = sampled[0];
+    token_ids[0] = tok;                        // device-side chaining of the next input (stream.rs:611-615)
+    host_ring[st->step % TOKEN_RING] = tok;    // pinned host ring read by next()/flush()
+    if (dev_out) dev_out[st->step - dev_out_base_step] = tok;
+    st->position += 1;
+    st->step += 1;
+}
+
+}  // namespace uzu
+
+using namespace uzu;
+
+struct uzu_engine {
+    uzu_context* ctx = nullptr;
+    uzu_engine_options opts{};
+    // model
+    uint32_t model_dim = 0, hidden_dim = 0, vocab = 0;
+    bool tied = false;
+    float input_scale = 1.0f;
+    bool has_logit_scale = false, has_logit_soft_cap = false;
+    float logit_scale = 1.0f, logit_soft_cap = 0.0f;
+    Linear in_emb, out_emb;
+    std::vector<Layer> layers;
+    Norm out_norm;
+    std::vector<RopeCfg> ropes;
+    std::vector<Buf> rope_cos, rope_sin;  // [positions, rope_dim] f32
+    uint32_t rope_positions = 0;
+    std::vector<uzu_buffer*> owned;
+    // state
+    std::vector<LayerState> state;
+    uint32_t context_length = 0, snapshot_context = 0;
+    uint32_t max_context = 0;
+    // scratch arena
+    Buf token_ids, hidden_a, hidden_b, shortcut, qkv, queries, attn_out, gate, fused_up, gated, mixer_out, in_proj, delta_out, normed_out,
+        logits, sampled, seeds, tp_parts, tp_sums, tp_maxs;
+    Buf host_ring;        // pinned u32[TOKEN_RING]
+    Buf host_tokens;      // pinned u32[MAX_ROWS] upload staging
+    Buf decode_state;     // device DecodeState
+    Buf snapshot_token;   // next-input token at snapshot time
+    uint32_t logits_rows = 16;
+    // streaming
+    uzu_sampling_method sampling{};
+    uint32_t steps_issued = 0, steps_returned = 0;
+    cudaEvent_t step_events[2] = {nullptr, nullptr};
+    // CUDA graph of one decode step
+    cudaGraphExec_t graph_exec = nullptr;
+    uint32_t graph_bucket = 0;
+    bool graph_stochastic = false;
+    uint64_t graph_launches_per_step = 0;
+    uint64_t launches = 0;
+    uzu_model_info info{};
+};
+
+namespace uzu {
+
+static void check(uzu_status st) {
+    if (st != UZU_OK) throw std::runtime_error(uzu_last_error());
+}
+
+static Buf make_buf(uzu_engine* e, size_t bytes, uzu_buffer_kind kind) {
+    Buf b;
+    check(uzu_buffer_create(e->ctx, bytes, kind, &b.b));
+    e->owned.push_back(b.b);
+    return b;
+}
+
+static Buf load_tensor(uzu_engine* e, ParameterLoader& pl, const std::string& name, const std::vector<uint64_t>& shape, const std::string& dtype) {
+    const TensorInfo& t = pl.validate(name, shape, dtype);
+    Buf b = make_buf(e, t.end - t.begin, UZU_BUFFER_MANAGED);
+    pl.read_into(t, uzu_buffer_cpu_ptr(b.b));
+    check(uzu_buffer_make_resident(e->ctx, b.b));
+    return b;
+}
+
+// WeightMatrix::load (weight_matrix.rs:101-162). `layout_required`: "output_input" for linears, "input_output" for embeddings.
+static WeightMatrix load_weight_matrix(uzu_engine* e, ParameterLoader& pl, const std::string& prefix, const char* layout_required,
+                                       uint32_t rows, uint32_t cols) {
+    auto it = pl.metadata.find(prefix + ".spec");
+    if (it == pl.metadata.end()) throw std::runtime_error("missing weight spec '" + prefix + ".spec' in safetensors metadata");
+    Json spec = parse_json(it->second);
+    if (spec.at("layout").str != layout_required) throw std::runtime_error(prefix + ": expected " + layout_required + " layout");
+    WeightMatrix w;
+    w.rows = rows;
+    w.cols = cols;
+    const std::string ty = spec.type_tag();
+    if (ty == "FullPrecisionSpec") {
+        w.values = load_tensor(e, pl, prefix + ".weights", {rows, cols}, "BF16");
+        w.bytes = (uint64_t)rows * cols * 2;
+        return w;
+    }
+    if (ty != "MLXSpec" && ty != "IntSpec") throw std::runtime_error(prefix + ": unsupported weight spec " + ty);
+    const uint32_t bits = spec.at("bits").u32();
+    w.group_size = spec.at("group_size").u32();
+    if (bits != 4 && bits != 8) throw std::runtime_error(prefix + ": unsupported bits");
+    if (w.group_size == 0) throw std::runtime_error(prefix + ": group size must be non-zero");
+    w.bits = bits;
+    w.mode = bits == 4 ? UZU_QMODE_U4 : UZU_QMODE_U8;
+    const uint32_t packing = bits == 4 ? 2 : 1;
+    if (cols % packing) throw std::runtime_error(prefix + ": stored columns not divisible by the packing divisor");
+    const uint32_t groups = (cols + w.group_size - 1) / w.group_size;
+    w.values = load_tensor(e, pl, prefix + ".weights", {rows, cols / packing}, "U8");
+    w.scales = load_tensor(e, pl, prefix + ".scales", {rows, groups}, "BF16");
+    w.bytes = (uint64_t)rows * (cols / packing) + (uint64_t)rows * groups * 2;
+    if (ty == "MLXSpec") {
+        w.prologue = UZU_B_SCALE_BIAS_DEQUANT;
+        w.biases = load_tensor(e, pl, prefix + ".biases", {rows, groups}, "BF16");
+        w.bytes += (uint64_t)rows * groups * 2;
+    } else if (spec.at("is_symmetric").boolean()) {
+        w.prologue = UZU_B_SCALE_SYMMETRIC_DEQUANT;
+    } else {
+        w.prologue = UZU_B_SCALE_ZERO_POINT_DEQUANT;
+        const uint32_t zcols = (groups + packing - 1) / packing;
+        w.zero_points = load_tensor(e, pl, prefix + ".zero_points", {rows, zcols}, "U8");
+        w.bytes += (uint64_t)rows * zcols;
+    }
+    return w;
+}
+
+static Linear load_linear(uzu_engine* e, ParameterLoader& pl, const std::string& prefix, uint32_t in_dim, uint32_t out_dim) {
+    Linear l;
+    l.in_dim = in_dim;
+    l.out_dim = out_dim;
+    l.w = load_weight_matrix(e, pl, prefix + ".weights", "output_input", out_dim, in_dim);
+    return l;
+}
+
+static NormCfg parse_norm_cfg(const Json& j) {
+    NormCfg c;
+    c.epsilon = (float)j.at("epsilon").number();
+    c.scale_offset = j.at("scale_offset").is_null() ? 0.0f : (float)j.at("scale_offset").number();
+    c.full_layer = j.at("upcast_mode").str == "full_layer";
+    c.subtract_mean = j.at("subtract_mean").boolean();
+    c.has_scale = j.at("has_scale").boolean();
+    c.has_biases = j.at("has_biases").boolean();
+    if (c.has_biases) throw std::runtime_error("normalization biases are not supported by this engine mirror");
+    return c;
+}
+
+static Norm load_norm(uzu_engine* e, ParameterLoader& pl, const std::string& prefix, const Json& cfg, uint32_t n) {
+    Norm nm;
+    nm.present = true;
+    nm.cfg = parse_norm_cfg(cfg);
+    nm.n = n;
+    if (nm.cfg.has_scale) nm.scales = load_tensor(e, pl, prefix + ".scales", {n}, "F32");
+    return nm;
+}
+
+static RopeCfg parse_rope(const Json& j) {
+    RopeCfg r;
+    const std::string ty = j.type_tag();
+    r.base = (float)j.at("base").number();
+    r.head_dim = j.at("head_dim").u32();
+    r.max_sequence_length = j.at("max_sequence_length").u32();
+    if (ty == "UnscaledRoPEConfig") r.kind = 0;
+    else if (ty == "LinearScalingRoPEConfig") { r.kind = 1; r.scaling_factor = (float)j.at("scaling_factor").number(); }
+    else if (ty == "LlamaRoPEConfig") {
+        r.kind = 2;
+        r.scaling_factor = (float)j.at("scaling_factor").number();
+        r.original_context_length = j.at("original_context_length").u32();
+        r.low = (float)j.at("low_frequency_factor").number();
+        r.high = (float)j.at("high_frequency_factor").number();
+    } else throw std::runtime_error("unsupported RoPE config " + ty + " (YaRN / LongRoPE are outside the BASELINE configs)");
+    return r;
+}
+
+// PrecalculatedRoPE::precalculate (mixer/attention/rope.rs:13-114), evaluated for positions [0, count)
+static void rope_tables(const RopeCfg& c, uint32_t count, float* cosines, float* sines) {
+    const uint32_t head_dim = c.head_dim, half = head_dim / 2;
+    for (uint32_t pair = 0; pair < half; ++pair) {
+        const uint32_t channel = pair * 2;
+        float inv = 1.0f / powf(c.base, (float)channel / (float)head_dim);
+        if (c.kind == 1) inv = inv / c.scaling_factor;
+        else if (c.kind == 2) {
+            const float low_wl = (float)c.original_context_length / c.low;
+            const float high_wl = (float)c.original_context_length / c.high;
+            const float wavelength = 2.0f * 3.14159265358979323846f / inv;
+            const float scaled = inv / c.scaling_factor;
+            if (wavelength < high_wl) {
+            } else if (wavelength > low_wl) inv = scaled;
+            else {
+                float smooth = (float)c.original_context_length / wavelength - c.low;
+                smooth = smooth / (c.high - c.low);
+                inv = smooth * inv + (1.0f - smooth) * scaled;
+            }
+        }
+        for (uint32_t t = 0; t < count; ++t) {
+            const float em = (float)t * inv;
+            const float s = sinf(em) * 1.0f, co = cosf(em) * 1.0f;
+            const size_t po = (size_t)t * head_dim + pair;
+            sines[po] = s; sines[po + half] = s;
+            cosines[po] = co; cosines[po + half] = co;
+        }
+    }
+}
+
+static void load_model(uzu_engine* e, const std::string& dir) {
+    Json cfg = parse_json(read_file(dir + "/config.json"));
+    if (cfg.type_tag() != "LanguageModelConfig") throw std::runtime_error("config.json: not a LanguageModelConfig");
+    const Json& dec = cfg.at("decoder_config");
+    const Json& tr = dec.at("transformer_config");
+    e->model_dim = tr.at("model_dim").u32();
+    e->hidden_dim = tr.at("hidden_dim").u32();
+    e->vocab = dec.at("vocab_size").u32();
+    if (!dec.at("ple_model_config").is_null() || !dec.at("embedding_norm_config").is_null())
+        throw std::runtime_error("PLE / embedding norm are outside this backend's scope (SURVEY 2.1)");
+    ParameterLoader pl(dir + "/model.safetensors");
+    const uint32_t H = e->model_dim, V = e->vocab;
+    const uint32_t tp = e->opts.tp_size ? e->opts.tp_size : 1;
+    if (tp != 1) throw std::runtime_error("tensor parallel loading is not implemented in this build");
+
+    const Json& emb = dec.at("embedding_config");
+    e->tied = emb.type_tag() == "TiedEmbeddingConfig";
+    if (!emb.at("input_scale").is_null()) e->input_scale = (float)emb.at("input_scale").number();
+    if (!emb.at("logit_scale").is_null()) { e->has_logit_scale = true; e->logit_scale = (float)emb.at("logit_scale").number(); }
+    if (!emb.at("logit_soft_cap").is_null()) { e->has_logit_soft_cap = true; e->logit_soft_cap = (float)emb.at("logit_soft_cap").number(); }
+    if (e->tied) {
+        e->in_emb.in_dim = H; e->in_emb.out_dim = V;
+        e->in_emb.w = load_weight_matrix(e, pl, "decoder.embedding.embedding", "input_output", V, H);
+        e->out_emb = e->in_emb;
+    } else {
+        e->in_emb.in_dim = H; e->in_emb.out_dim = V;
+        e->in_emb.w = load_weight_matrix(e, pl, "decoder.embedding.input_embedding", "input_output", V, H);
+        e->out_emb.in_dim = H; e->out_emb.out_dim = V;
+        e->out_emb.w = load_weight_matrix(e, pl, "decoder.embedding.output_embedding", "input_output", V, H);
+    }
+
+    uint64_t wbytes = e->out_emb.w.bytes, kvb = 0, stb = 0;
+    uint32_t n_attn = 0, n_dn = 0;
+    const auto& lcs = tr.at("layer_configs").arr;
+    e->layers.resize(lcs.size());
+    for (size_t i = 0; i < lcs.size(); ++i) {
+        const Json& lc = lcs[i];
+        Layer& L = e->layers[i];
+        const std::string p = "decoder.transformer.layers." + std::to_string(i);
+        if (lc.at("pre_mixer_norm_config").is_null()) throw std::runtime_error("layers without pre_mixer_norm are not supported");
+        if (!lc.at("post_mixer_norm_config").is_null() || !lc.at("post_mlp_norm_config").is_null() || !lc.at("ple_config").is_null() ||
+            lc.at("has_post_layer_scalar").boolean() || !lc.at("kv_source_layer_index").is_null())
+            throw std::runtime_error("post norms / PLE / post-layer scalar / KV sharing are outside this backend's scope");
+        L.pre_mixer = load_norm(e, pl, p + ".pre_mixer_norm", lc.at("pre_mixer_norm_config"), H);
+        L.pre_mlp = load_norm(e, pl, p + ".pre_mlp_norm", lc.at("pre_mlp_norm_config"), H);
+        const Json& mc = lc.at("mixer_config");
+        const std::string mty = mc.type_tag();
+        if (mty == "AttentionConfig") {
+            L.is_attention = true;
+            AttentionLayer& A = L.attn;
+            A.num_heads = mc.at("num_heads").u32();
+            A.num_groups = mc.at("num_groups").u32();
+            A.head_dim = mc.at("head_dim").u32();
+            A.is_causal = mc.at("is_causal").boolean();
+            if (!mc.at("scale").is_null()) { A.has_scale = true; A.scale = (float)mc.at("scale").number(); }
+            if (!mc.at("sliding_window_size").is_null() || mc.at("has_sinks").boolean() || mc.at("has_qkv_biases").boolean() ||
+                mc.at("has_out_biases").boolean() || mc.at("normalize_values").boolean() || mc.at("is_kv_sharing").boolean() ||
+                !mc.at("logit_soft_cap").is_null())
+                throw std::runtime_error("attention variant (sliding window / sinks / biases / value norm / KV sharing) not supported by the engine mirror");
+            const uint32_t qd = A.num_heads * A.head_dim, kvd = A.num_groups * A.head_dim;
+            A.qkv = load_linear(e, pl, p + ".mixer.qkv_projection", H, qd + 2 * kvd);
+            A.out = load_linear(e, pl, p + ".mixer.out_projection", qd, H);
+            if (!mc.at("gate_projection_config").is_null()) {
+                A.has_gate = true;
+                A.gate = load_linear(e, pl, p + ".mixer.gate_projection", H, qd);
+                wbytes += A.gate.w.bytes;
+            }
+            if (!mc.at("query_norm_config").is_null()) A.qnorm = load_norm(e, pl, p + ".mixer.query_norm", mc.at("query_norm_config"), A.head_dim);
+            if (!mc.at("key_norm_config").is_null()) A.knorm = load_norm(e, pl, p + ".mixer.key_norm", mc.at("key_norm_config"), A.head_dim);
+            if (!lc.at("rope_config").is_null()) {
+                RopeCfg rc = parse_rope(lc.at("rope_config"));
+                int idx = -1;
+                for (size_t r = 0; r < e->ropes.size(); ++r)
+                    if (e->ropes[r] == rc) idx = (int)r;
+                if (idx < 0) { e->ropes.push_back(rc); idx = (int)e->ropes.size() - 1; }
+                A.rope_index = idx;
+            }
+            wbytes += A.qkv.w.bytes + A.out.w.bytes;
+            kvb += 2ull * kvd * 2;
+            n_attn++;
+        } else if (mty == "DeltaNetConfig") {
+            L.is_attention = false;
+            DeltaNetLayer& D = L.dn;
+            D.num_heads = mc.at("num_heads").u32();
+            D.num_groups = mc.at("num_groups").u32();
+            D.head_dim = mc.at("head_dim").u32();
+            D.value_head_dim = mc.at("value_head_dim").u32();
+            D.kernel_size = mc.at("kernel_size").u32();
+            if (D.head_dim != 128 || D.value_head_dim != 128 || D.kernel_size < 2)
+                throw std::runtime_error("DeltaNet: head_dim and value_head_dim must be 128, kernel_size >= 2 (delta_net.rs:168-186)");
+            D.key_dim = D.num_groups * D.head_dim;
+            D.value_dim = D.num_heads * D.value_head_dim;
+            D.conv_dim = 2 * D.key_dim + D.value_dim;
+            D.total_proj_dim = D.conv_dim + D.value_dim + 2 * D.num_heads;
+            D.norm_epsilon = (float)mc.at("norm_config").at("epsilon").number();
+            D.conv_has_bias = mc.at("conv_config").at("has_biases").boolean();
+            D.in_proj = load_linear(e, pl, p + ".mixer.in_proj", H, D.total_proj_dim);
+            D.conv_weight = load_tensor(e, pl, p + ".mixer.conv.weights", {D.conv_dim, D.kernel_size}, "F32");
+            if (D.conv_has_bias) D.conv_bias = load_tensor(e, pl, p + ".mixer.conv.biases", {D.conv_dim}, "F32");
+            D.a_log = load_tensor(e, pl, p + ".mixer.a_log", {D.num_heads}, "F32");
+            D.dt_bias = load_tensor(e, pl, p + ".mixer.dt_bias", {D.num_heads}, "F32");
+            D.norm_weight = load_tensor(e, pl, p + ".mixer.norm.scales", {D.value_head_dim}, "F32");
+            D.out_proj = load_linear(e, pl, p + ".mixer.out_proj", D.value_dim, H);
+            wbytes += D.in_proj.w.bytes + D.out_proj.w.bytes;
+            stb += 2ull * D.num_heads * D.value_head_dim * D.head_dim * 4;
+            n_dn++;
+        } else {
+            throw std::runtime_error("mixer " + mty + " is outside this backend's scope (SURVEY 2.1)");
+        }
+        const Json& mlp = lc.at("mlp_config");
+        if (mlp.type_tag() != "DenseMLPConfig") throw std::runtime_error("only DenseMLPConfig is supported");
+        if (mlp.at("has_up_biases").boolean() || mlp.at("has_down_biases").boolean() || !mlp.at("gate_clipping").is_null() ||
+            !mlp.at("up_clipping").is_null())
+            throw std::runtime_error("MLP biases / clipping are not supported by the engine mirror");
+        const std::string act = mlp.at("activation").type_tag();
+        if (act == "SiLU") L.act = UZU_ACT_SILU;
+        else if (act == "GELU") L.act = mlp.at("activation").at("approximate").boolean() ? UZU_ACT_GELU_APPROX : UZU_ACT_GELU_EXACT;
+        else throw std::runtime_error("Identity activation is not supported for kernel (mlp/gate_act_mul.rs:60-62)");
+        L.hidden_dim = lc.at("hidden_dim").is_null() ? e->hidden_dim : lc.at("hidden_dim").u32();
+        L.up = load_linear(e, pl, p + ".mlp.up_projection", H, 2 * L.hidden_dim);
+        L.down = load_linear(e, pl, p + ".mlp.down_projection", L.hidden_dim, H);
+        wbytes += L.up.w.bytes + L.down.w.bytes;
+    }
+    e->out_norm = load_norm(e, pl, "decoder.transformer.output_norm", tr.at("output_norm_config"), H);
+    pl.assert_all_validated();
+
+    e->info.model_dim = H;
+    e->info.hidden_dim = e->hidden_dim;
+    e->info.vocab_size = V;
+    e->info.num_layers = (uint32_t)e->layers.size();
+    e->info.num_attention_layers = n_attn;
+    e->info.num_delta_net_layers = n_dn;
+    e->info.weight_bytes_per_token = wbytes;
+    e->info.kv_bytes_per_token_per_ctx = kvb;
+    e->info.state_bytes_per_token = stb;
+}
+
+static void create_state_and_scratch(uzu_engine* e) {
+    const uint32_t H = e->model_dim, V = e->vocab;
+    uint32_t max_ctx = e->opts.max_context_length ? e->opts.max_context_length : 8192;
+    for (auto& r : e->ropes) max_ctx = std::min(max_ctx, r.max_sequence_length);  // state.rs:80-85
+    e->max_context = max_ctx;
+    const uint32_t rows_total = max_ctx + MAX_ROWS;
+    const bool sparse = (uzu_context_device_capabilities(e->ctx) & UZU_CAP_SPARSE_BUFFERS) != 0;
+    e->state.resize(e->layers.size());
+    uint32_t max_qkv = 0, max_qd = 0, max_f = 0, max_proj = 0, max_vd = 0, max_heads = 0, max_hd = 0;
+    for (size_t i = 0; i < e->layers.size(); ++i) {
+        Layer& L = e->layers[i];
+        LayerState& S = e->state[i];
+        max_f = std::max(max_f, L.hidden_dim);
+        if (L.is_attention) {
+            const AttentionLayer& A = L.attn;
+            S.row_bytes = (size_t)A.num_groups * A.head_dim * 2;
+            const size_t bytes = (size_t)rows_total * S.row_bytes;
+            if (sparse) {
+                check(uzu_sparse_buffer_create(e->ctx, bytes, &S.k_sparse));
+                check(uzu_sparse_buffer_create(e->ctx, bytes, &S.v_sparse));
+                S.keys = uzu_sparse_buffer_gpu_ptr(S.k_sparse);
+                S.values = uzu_sparse_buffer_gpu_ptr(S.v_sparse);
+            } else {
+                S.k_dense = make_buf(e, bytes, UZU_BUFFER_DEVICE);
+                S.v_dense = make_buf(e, bytes, UZU_BUFFER_DEVICE);
+                S.keys = S.k_dense.ptr();
+                S.values = S.v_dense.ptr();
+            }
+            max_qkv = std::max(max_qkv, (A.num_heads + 2 * A.num_groups) * A.head_dim);
+            max_qd = std::max(max_qd, A.num_heads * A.head_dim);
+            max_heads = std::max(max_heads, A.num_heads);
+            max_hd = std::max(max_hd, A.head_dim);
+        } else {
+            const DeltaNetLayer& D = L.dn;
+            S.conv_bytes = (size_t)D.conv_dim * (D.kernel_size - 1) * 4;
+            S.ssm_bytes = (size_t)D.num_heads * D.value_head_dim * D.head_dim * 4;
+            S.conv_state = make_buf(e, S.conv_bytes, UZU_BUFFER_DEVICE);
+            S.ssm_state = make_buf(e, S.ssm_bytes, UZU_BUFFER_DEVICE);
+            S.conv_snapshot = make_buf(e, S.conv_bytes, UZU_BUFFER_DEVICE);
+            S.ssm_snapshot = make_buf(e, S.ssm_bytes, UZU_BUFFER_DEVICE);
+            max_proj = std::max(max_proj, D.total_proj_dim);
+            max_vd = std::max(max_vd, D.value_dim);
+        }
+    }
+    auto dev = [&](size_t bytes) { return make_buf(e, std::max<size_t>(bytes, 256), UZU_BUFFER_DEVICE); };
+    e->token_ids = dev(MAX_ROWS * 4);
+    e->hidden_a = dev((size_t)MAX_ROWS * H * 2);
+    e->hidden_b = dev((size_t)MAX_ROWS * H * 2);
+    e->shortcut = dev((size_t)MAX_ROWS * H * 2);
+    e->mixer_out = dev((size_t)MAX_ROWS * H * 2);
+    e->normed_out = dev((size_t)e->logits_rows * H * 2);
+    e->qkv = dev((size_t)MAX_ROWS * max_qkv * 2);
+    e->queries = dev((size_t)MAX_ROWS * max_qd * 2);
+    e->attn_out = dev((size_t)MAX_ROWS * max_qd * 2);
+    e->gate = dev((size_t)MAX_ROWS * max_qd * 2);
+    e->fused_up = dev((size_t)MAX_ROWS * 2 * max_f * 2);
+    e->gated = dev((size_t)MAX_ROWS * max_f * 2);
+    e->in_proj = dev((size_t)max_proj * 2);
+    e->delta_out = dev((size_t)max_vd * 2);
+    e->logits = dev((size_t)e->logits_rows * V * 2);
+    e->sampled = dev(MAX_ROWS * 4);
+    e->seeds = dev(MAX_ROWS * 8);
+    // two-pass attention scratch (only used for suffix <= 8 and context > 1024, like the reference dispatch)
+    e->tp_parts = dev((size_t)8 * max_heads * 32 * max_hd * 4);
+    e->tp_sums = dev((size_t)8 * max_heads * 32 * 4);
+    e->tp_maxs = dev((size_t)8 * max_heads * 32 * 4);
+    e->host_ring = make_buf(e, TOKEN_RING * 4, UZU_BUFFER_PINNED_HOST);
+    e->host_tokens = make_buf(e, MAX_ROWS * 4, UZU_BUFFER_PINNED_HOST);
+    e->decode_state = dev(sizeof(DecodeState));
+    e->snapshot_token = dev(4);
+    // RoPE tables for every position the state can hold
+    e->rope_positions = rows_total;
+    for (auto& rc : e->ropes) {
+        std::vector<float> cosv((size_t)rows_total * rc.head_dim), sinv((size_t)rows_total * rc.head_dim);
+        rope_tables(rc, rows_total, cosv.data(), sinv.data());
+        Buf c = dev(cosv.size() * 4), s = dev(sinv.size() * 4);
+        cudaMemcpy((void*)c.ptr(), cosv.data(), cosv.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy((void*)s.ptr(), sinv.data(), sinv.size() * 4, cudaMemcpyHostToDevice);
+        e->rope_cos.push_back(c);
+        e->rope_sin.push_back(s);
+    }
+    cudaEventCreateWithFlags(&e->step_events[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->step_events[1], cudaEventDisableTiming);
+}
+
+// TransformerState::prepare (state.rs:141-172): make sure KV pages for rows [0, rows) are mapped
+static void state_prepare(uzu_engine* e, uint32_t rows_needed) {
+    for (auto& S : e->state) {
+        if (!S.k_sparse) continue;
+        const size_t page = uzu_sparse_buffer_page_size_bytes(S.k_sparse);
+        const uint32_t need = (uint32_t)(((size_t)rows_needed * S.row_bytes + page - 1) / page);
+        if (need <= S.mapped_pages) continue;
+        std::vector<uint32_t> pages;
+        for (uint32_t p = S.mapped_pages; p < need; ++p) pages.push_back(p);
+        check(uzu_sparse_buffer_map(S.k_sparse, pages.data(), pages.size()));
+        check(uzu_sparse_buffer_map(S.v_sparse, pages.data(), pages.size()));
+        S.mapped_pages = need;
+    }
+}
+
+static void upload_decode_state(uzu_engine* e);
+
+static void reset_state(uzu_engine* e) {
+    cudaStreamSynchronize(e->ctx->stream);
+    e->context_length = 0;
+    e->snapshot_context = 0;
+    for (auto& S : e->state) {
+        S.length = 0;
+        if (S.conv_state.b) {
+            cudaMemsetAsync((void*)S.conv_state.ptr(), 0, S.conv_bytes, e->ctx->stream);
+            cudaMemsetAsync((void*)S.ssm_state.ptr(), 0, S.ssm_bytes, e->ctx->stream);
+        }
+    }
+    e->steps_issued = e->steps_returned = 0;
+    cudaMemsetAsync((void*)e->token_ids.ptr(), 0, 4, e->ctx->stream);
+    cudaStreamSynchronize(e->ctx->stream);
+    upload_decode_state(e);
+}
+
+// -----------------------------------------------------------------------------------------------------
+// encoding one forward pass (Decoder::encode)
+// -----------------------------------------------------------------------------------------------------
+static void encode_linear(uzu_command_buffer* cmd, const Linear& l, uint64_t a, uint32_t m, uint64_t d) {
+    uzu_matmul_args ma{};
+    ma.a = a;
+    ma.b = l.w.values.ptr();
+    ma.b_scales = l.w.scales.ptr();
+    ma.b_zero_points = l.w.zero_points.ptr();
+    ma.b_biases = l.w.biases.ptr();
+    ma.d = d;
+    ma.b_prologue = l.w.prologue;
+    ma.b_mode = l.w.mode;
+    ma.b_group_size = l.w.group_size;
+    ma.b_transpose = 1;                 // linear/matmul.rs:136
+    ma.ab_scale = 1.0f;
+    ma.m = m; ma.n = l.out_dim; ma.k = l.in_dim;
+    ma.weights_dt = ma.input_dt = ma.output_dt = UZU_DT_BF16;   // language_model/mod.rs:74
+    uzu_matmul_encode(cmd, &ma);
+}
+
+enum ShortcutMode { ShortcutNone, ShortcutCopy, ShortcutAdd };
+
+static void encode_norm(uzu_command_buffer* cmd, const Norm& n, uint64_t input, uint64_t output, uint64_t shortcut, ShortcutMode mode, uint32_t rows) {
+    uzu_normalization_args a{};
+    a.input = input;
+    a.scales = n.scales.ptr();
+    a.output = output;
+    a.shortcut = mode == ShortcutNone ? 0 : shortcut;
+    a.batch_size = rows;
+    a.element_count = n.n;
+    a.epsilon = n.cfg.epsilon;
+    a.scale_offset = n.cfg.scale_offset;
+    a.post_layer_scalar = 1.0f;
+    a.subtract_mean = n.cfg.subtract_mean;
+    a.full_layer = n.cfg.full_layer;
+    a.copy_to_shortcut = mode != ShortcutNone;
+    a.residual_add = mode == ShortcutAdd;
+    a.has_scales = n.cfg.has_scale;
+    uzu_normalization_encode(cmd, &a);
+}
+
+struct PassCtx {
+    uint32_t m = 1;
+    bool dynamic = false;   // decode-graph mode: positions come from the device DecodeState
+};
+
+static uint64_t encode_attention(uzu_engine* e, uzu_command_buffer* cmd, const Layer& L, LayerState& S, uint64_t hidden, const PassCtx& pc) {
+    const AttentionLayer& A = L.attn;
+    const uint32_t m = pc.m, D = A.head_dim, Hq = A.num_heads, Hkv = A.num_groups;
+    const uint64_t dyn = pc.dynamic ? e->decode_state.ptr() : 0;  // &DecodeState::position (first member)
+    // gate projection first (mode.rs:54-61); `hidden` is not modified by our linears, so no copy is needed
+    if (A.has_gate) encode_linear(cmd, A.gate, hidden, m, e->gate.ptr());
+    encode_linear(cmd, A.qkv, hidden, m, e->qkv.ptr());
+    const uint32_t total_heads = Hq + 2 * Hkv;
+    auto qkn = [&](const Norm& n, uint32_t off, uint32_t cnt) {
+        if (!n.present || cnt == 0) return;
+        uzu_qkv_norm_args qa{};
+        qa.scales = n.scales.ptr();
+        qa.qkv_output = e->qkv.ptr();
+        qa.batch_size = m; qa.total_heads = total_heads; qa.head_dim = D;
+        qa.epsilon = n.cfg.epsilon; qa.scale_offset = n.cfg.scale_offset;
+        qa.head_offset = off; qa.head_count = cnt; qa.full_layer = n.cfg.full_layer;
+        qa.in_place = 1; qa.has_scales = n.cfg.has_scale;
+        uzu_qkv_norm_encode(cmd, &qa);
+    };
+    qkn(A.qnorm, 0, Hq);
+    qkn(A.knorm, Hq, Hkv);
+    const uint32_t prefix = S.length;
+    uzu_attention_prepare_args pa{};
+    pa.qkv = e->qkv.ptr(); pa.queries = e->queries.ptr();
+    pa.keys = S.keys; pa.values = S.values;
+    pa.num_q_heads = Hq; pa.num_kv_heads = Hkv; pa.head_dim = D;
+    pa.kv_token_offset = prefix; pa.batch_dim = m; pa.has_kv = 1;
+    if (A.rope_index >= 0) {
+        const RopeCfg& rc = e->ropes[A.rope_index];
+        pa.has_rope = 1; pa.rope_dim = rc.head_dim;
+        const size_t row0 = pc.dynamic ? 0 : (size_t)e->context_length;   // token positions = context_length + i (transformer.rs:246-247)
+        pa.cosines = e->rope_cos[A.rope_index].ptr() + row0 * rc.head_dim * 4;
+        pa.sines = e->rope_sin[A.rope_index].ptr() + row0 * rc.head_dim * 4;
+    }
+    pa.dynamic_position = dyn;
+    uzu_attention_prepare_encode(cmd, &pa);
+
+    uzu_attention_args aa{};
+    aa.queries = e->queries.ptr(); aa.keys = S.keys; aa.values = S.values;
+    aa.gqa_factor = Hq / Hkv;
+    aa.sequence_length = prefix + m;
+    aa.k_head_stride = D; aa.k_seq_stride = Hkv * D; aa.v_head_stride = D; aa.v_seq_stride = Hkv * D;
+    aa.scale = A.has_scale ? A.scale : 1.0f / sqrtf((float)D);
+    aa.num_heads = Hq; aa.suffix_length = m; aa.head_dim = D; aa.is_causal = A.is_causal;
+    aa.dynamic_position = dyn;
+    // AttentionCores::encode (core/mod.rs:81-93). This backend has no "gemm" core yet, so like the CPU backend long
+    // suffixes go through the single/two-pass kernels. For suffix <= 8 with context > 1024 the reference uses the
+    // two-pass core; the fused split-KV single-pass entry point computes the same function in one launch, so the
+    // engine uses it for every decode step unless UZU_TWO_PASS=1 asks for the literal dispatch.
+    static const bool literal_two_pass = getenv("UZU_TWO_PASS") != nullptr;
+    if (literal_two_pass && !pc.dynamic && m <= 8 && prefix + m > 1024) {
+        aa.out = e->tp_parts.ptr(); aa.sums = e->tp_sums.ptr(); aa.maxs = e->tp_maxs.ptr();
+        uzu_attention_two_pass1_encode(cmd, &aa);
+        uzu_attention_two_pass2_args a2{e->tp_parts.ptr(), e->tp_sums.ptr(), e->tp_maxs.ptr(), e->attn_out.ptr(), Hq, m, D};
+        uzu_attention_two_pass2_encode(cmd, &a2);
+    } else {
+        aa.out = e->attn_out.ptr();
+        uzu_attention_single_pass_encode(cmd, &aa);
+    }
+    if (A.has_gate) uzu_sigmoid_gate_encode(cmd, e->gate.ptr(), e->attn_out.ptr(), m * Hq * D);
+    encode_linear(cmd, A.out, e->attn_out.ptr(), m, e->mixer_out.ptr());
+    return e->mixer_out.ptr();
+}
+
+static uint64_t encode_delta_net(uzu_engine* e, uzu_command_buffer* cmd, const Layer& L, LayerState& S, uint64_t hidden, const PassCtx& pc) {
+    const DeltaNetLayer& D = L.dn;
+    if (pc.m != 1) throw std::runtime_error("DeltaNet prefill (m > 1) is stepped token by token by the caller");
+    encode_linear(cmd, D.in_proj, hidden, 1, e->in_proj.ptr());
+    uzu_delta_net_conv_update_args ca{};
+    ca.conv_weight = D.conv_weight.ptr(); ca.bias = D.conv_bias.ptr(); ca.in_out = e->in_proj.ptr(); ca.state = S.conv_state.ptr();
+    ca.kernel_size = D.kernel_size; ca.conv_dim = D.conv_dim; ca.state_stride = D.kernel_size - 1; ca.has_bias = D.conv_has_bias;
+    uzu_delta_net_conv_update_encode(cmd, &ca);
+    uzu_delta_net_update_args ua{};
+    ua.in_proj = e->in_proj.ptr(); ua.a_log = D.a_log.ptr(); ua.dt_bias = D.dt_bias.ptr(); ua.norm_weight = D.norm_weight.ptr();
+    ua.state = S.ssm_state.ptr(); ua.out = e->delta_out.ptr();
+    ua.num_v_heads = D.num_heads; ua.num_k_heads = D.num_groups; ua.head_v_dim = D.value_head_dim; ua.key_dim = D.key_dim;
+    ua.value_dim = D.value_dim; ua.norm_epsilon = D.norm_epsilon; ua.head_k_dim = D.head_dim;
+    uzu_delta_net_update_encode(cmd, &ua);
+    encode_linear(cmd, D.out_proj, e->delta_out.ptr(), 1, e->mixer_out.ptr());
+    return e->mixer_out.ptr();
+}
+
+// Decoder::encode for `m` tokens already in e->token_ids; logits for rows [row_begin, row_end) land in e->logits.
+static void encode_decoder(uzu_engine* e, uzu_command_buffer* cmd, const PassCtx& pc, uint32_t row_begin, uint32_t row_end) {
+    const uint32_t m = pc.m, H = e->model_dim;
+    // embedding lookup (embedding.rs:345-372)
+    if (e->in_emb.w.prologue == UZU_B_FULL_PRECISION) {
+        uzu_full_precision_embedding_lookup_encode(cmd, e->token_ids.ptr(), e->in_emb.w.values.ptr(), e->hidden_a.ptr(), m, e->vocab, H, e->input_scale);
+    } else {
+        uzu_quantized_embedding_lookup_args la{};
+        la.token_ids = e->token_ids.ptr(); la.weights = e->in_emb.w.values.ptr(); la.scales = e->in_emb.w.scales.ptr();
+        la.zero_points = e->in_emb.w.zero_points.ptr(); la.biases = e->in_emb.w.biases.ptr(); la.output = e->hidden_a.ptr();
+        la.batch_size = m; la.vocab_size = e->vocab; la.model_dim = H; la.input_scale = e->input_scale;
+        la.group_size = e->in_emb.w.group_size; la.quantization_mode = e->in_emb.w.mode;
+        la.quantization_method = e->in_emb.w.prologue == UZU_B_SCALE_BIAS_DEQUANT ? UZU_QMETHOD_SCALE_BIAS
+                                 : e->in_emb.w.prologue == UZU_B_SCALE_ZERO_POINT_DEQUANT ? UZU_QMETHOD_SCALE_ZERO_POINT : UZU_QMETHOD_SCALE_SYMMETRIC;
+        uzu_quantized_embedding_lookup_encode(cmd, &la);
+    }
+    uint64_t hidden = e->hidden_a.ptr();
+    for (size_t i = 0; i < e->layers.size(); ++i) {
+        Layer& L = e->layers[i];
+        LayerState& S = e->state[i];
+        // pre_mixer_norm: layer 0 copies the input into the shortcut, later layers add (transformer_layer.rs:95-109)
+        encode_norm(cmd, L.pre_mixer, hidden, e->hidden_b.ptr(), e->shortcut.ptr(), i == 0 ? ShortcutCopy : ShortcutAdd, m);
+        uint64_t mixed = L.is_attention ? encode_attention(e, cmd, L, S, e->hidden_b.ptr(), pc) : encode_delta_net(e, cmd, L, S, e->hidden_b.ptr(), pc);
+        encode_norm(cmd, L.pre_mlp, mixed, e->hidden_b.ptr(), e->shortcut.ptr(), ShortcutAdd, m);
+        // DenseMlp::encode (mlp/dense.rs:32-48)
+        encode_linear(cmd, L.up, e->hidden_b.ptr(), m, e->fused_up.ptr());
+        uzu_gated_act_mul_args ga{};
+        ga.act_operand = e->fused_up.ptr(); ga.fp_out = e->gated.ptr(); ga.gated_dim = L.hidden_dim; ga.batch_dim = m;
+        ga.act_type = L.act; ga.interleaved = 1;
+        uzu_gated_act_mul_encode(cmd, &ga);
+        encode_linear(cmd, L.down, e->gated.ptr(), m, e->hidden_a.ptr());
+        hidden = e->hidden_a.ptr();
+    }
+    if (row_end <= row_begin) return;
+    const uint32_t rows = row_end - row_begin;
+    // output_norm over the requested rows, residual add into the same rows of the shortcut (transformer.rs:317-323)
+    encode_norm(cmd, e->out_norm, hidden + (size_t)row_begin * H * 2, e->normed_out.ptr(), e->shortcut.ptr() + (size_t)row_begin * H * 2, ShortcutAdd, rows);
+    encode_linear(cmd, e->out_emb, e->normed_out.ptr(), rows, e->logits.ptr());  // readout (embedding.rs:374-456)
+    if (e->has_logit_scale || e->has_logit_soft_cap)
+        uzu_logit_transform_encode(cmd, e->logits.ptr(), rows * e->vocab, e->has_logit_scale ? e->logit_scale : 1.0f, e->logit_soft_cap, e->has_logit_soft_cap);
+}
+
+static void encode_sampling(uzu_engine* e, uzu_command_buffer* cmd, uint32_t rows) {
+    const uzu_sampling_method& s = e->sampling;
+    uzu_unified_sampling_args sa{};
+    sa.logits = e->logits.ptr();
+    sa.output = e->sampled.ptr();
+    sa.vocab_size = e->vocab;
+    sa.batch_size = rows;
+    if (s.kind == UZU_SAMPLING_STOCHASTIC) {
+        sa.is_stochastic = 1;
+        sa.seeds = e->seeds.ptr();
+        sa.has_temperature = s.has_temperature; sa.temperature = s.temperature;
+        sa.has_top_k = s.has_top_k; sa.top_k = s.top_k;
+        sa.has_top_p = s.has_top_p; sa.top_p = s.top_p;
+        sa.has_min_p = s.has_min_p; sa.min_p = s.min_p;
+    }
+    uzu_unified_sampling_encode(cmd, &sa);
+}
+
+static bool has_delta(const uzu_engine* e) {
+    for (auto& L : e->layers)
+        if (!L.is_attention) return true;
+    return false;
+}
+
+// advance host-side bookkeeping after a pass over m tokens (TransformerState::encode_accept: flat, no copies)
+static void accept(uzu_engine* e, uint32_t m) {
+    for (size_t i = 0; i < e->layers.size(); ++i)
+        if (e->layers[i].is_attention) e->state[i].length += m;
+    e->context_length += m;
+}
+
+struct CmdGuard {
+    uzu_command_buffer* c = nullptr;
+    explicit CmdGuard(uzu_context* ctx, const char* name) { check(uzu_command_buffer_create(ctx, name, &c)); }
+    ~CmdGuard() { uzu_command_buffer_destroy(c); }
+};
+
+static void run_cmd_to_completion(uzu_engine* e, uzu_command_buffer* c) {
+    check(uzu_command_buffer_end_encoding(c));
+    check(uzu_command_buffer_submit(c));
+    check(uzu_command_buffer_wait_until_completed(c));
+    e->launches += uzu_command_buffer_launch_count(c);
+}
+
+static uint64_t prng_derive(uint64_t seed, uint64_t index) {
+    uint64_t h = seed + index;
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdULL;
+    h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL;
+    h ^= h >> 33;
+    return h;
+}
+
+// one non-graph pass over `count` host tokens; optionally samples the last row
+static void run_pass(uzu_engine* e, const uint32_t* tokens, uint32_t count, uint32_t row_begin, uint32_t row_end, bool sample_last) {
+    if (count == 0 || count > MAX_ROWS) throw std::runtime_error("pass size must be in 1..1024");
+    if (e->context_length + count > e->max_context + MAX_ROWS || e->context_length + count > e->rope_positions)
+        throw std::runtime_error("context overflow: raise max_context_length");
+    state_prepare(e, e->context_length + count);
+    memcpy(uzu_buffer_cpu_ptr(e->host_tokens.b), tokens, count * 4);
+    CmdGuard g(e->ctx, "pass");
+    check(uzu_command_buffer_start_encoding(g.c));
+    uzu_command_buffer_encode_copy(g.c, e->host_tokens.ptr(), e->token_ids.ptr(), count * 4);
+    PassCtx pc;
+    pc.m = count;
+    encode_decoder(e, g.c, pc, row_begin, row_end);
+    if (sample_last) {
+        if (e->sampling.kind == UZU_SAMPLING_STOCHASTIC) {
+            // seed of the sampled row = PRng::derive(absolute index of its input token) (stream.rs:252-254)
+            uint64_t seed = prng_derive(e->sampling.seed, (uint64_t)e->context_length + count - 1);
+            cudaMemcpyAsync((void*)e->seeds.ptr(), &seed, 8, cudaMemcpyHostToDevice, e->ctx->stream);
+            cudaStreamSynchronize(e->ctx->stream);
+        }
+        encode_sampling(e, g.c, 1);
+    }
+    run_cmd_to_completion(e, g.c);
+    accept(e, count);
+}
+
+static uint32_t attention_bucket(uint32_t seq) {
+    uint32_t b = 64;
+    while (b < seq) b <<= 1;
+    return b;
+}
+
+// Capture one decode step (m = 1, positions from DecodeState) into a CUDA graph.
+static void capture_decode_graph(uzu_engine* e) {
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    cudaStream_t s = e->ctx->stream;
+    CmdGuard g(e->ctx, "decode-graph");
+    cudaStreamSynchronize(s);
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) throw std::runtime_error("cudaStreamBeginCapture failed");
+    g.c->state = uzu_command_buffer::Encoding;   // events are not recorded inside a capture
+    if (e->sampling.kind == UZU_SAMPLING_STOCHASTIC) {
+        decode_step_begin_kernel<<<1, 1, 0, s>>>((const DecodeState*)e->decode_state.ptr(), (unsigned long long*)e->seeds.ptr());
+        g.c->launches++;
+    }
+    PassCtx pc;
+    pc.m = 1;
+    pc.dynamic = true;
+    encode_decoder(e, g.c, pc, 0, 1);
+    encode_sampling(e, g.c, 1);
+    decode_step_end_kernel<<<1, 1, 0, s>>>((DecodeState*)e->decode_state.ptr(), (const uint32_t*)e->sampled.ptr(), (uint32_t*)e->token_ids.ptr(),
+                                           (volatile uint32_t*)e->host_ring.ptr(), nullptr, 0);
+    g.c->launches++;
+    cudaGraph_t graph = nullptr;
+    cudaError_t err = cudaStreamEndCapture(s, &graph);
+    if (err != cudaSuccess || g.c->sticky != UZU_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        throw std::runtime_error(std::string("decode graph capture failed: ") + (g.c->sticky != UZU_OK ? g.c->sticky_msg : cudaGetErrorString(err)));
+    }
+    err = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (err != cudaSuccess) throw std::runtime_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(err));
+    e->graph_launches_per_step = g.c->launches;
+    e->graph_bucket = attention_bucket(e->context_length + 1);
+    e->graph_stochastic = e->sampling.kind == UZU_SAMPLING_STOCHASTIC;
+}
+
+// enqueue one decode step (no host wait)
+static void issue_decode_step(uzu_engine* e, uint64_t dev_out, uint32_t dev_out_base_step) {
+    if (e->context_length + 1 > e->max_context + MAX_ROWS || e->context_length + 1 > e->rope_positions)
+        throw std::runtime_error("context overflow: raise max_context_length");
+    state_prepare(e, e->context_length + 1);
+    cudaStream_t s = e->ctx->stream;
+    if (e->opts.use_cuda_graph && !dev_out) {
+        if (!e->graph_exec || e->graph_bucket != attention_bucket(e->context_length + 1) ||
+            e->graph_stochastic != (e->sampling.kind == UZU_SAMPLING_STOCHASTIC))
+            capture_decode_graph(e);
+        cudaError_t err = cudaGraphLaunch(e->graph_exec, s);
+        if (err != cudaSuccess) throw std::runtime_error(std::string("cudaGraphLaunch: ") + cudaGetErrorString(err));
+        e->launches += e->graph_launches_per_step;
+    } else {
+        CmdGuard g(e->ctx, "decode");
+        g.c->state = uzu_command_buffer::Encoding;
+        if (e->sampling.kind == UZU_SAMPLING_STOCHASTIC) {
+            decode_step_begin_kernel<<<1, 1, 0, s>>>((const DecodeState*)e->decode_state.ptr(), (unsigned long long*)e->seeds.ptr());
+            g.c->launches++;
+        }
+        PassCtx pc;
+        pc.m = 1;
+        pc.dynamic = true;
+        encode_decoder(e, g.c, pc, 0, 1);
+        encode_sampling(e, g.c, 1);
+        decode_step_end_kernel<<<1, 1, 0, s>>>((DecodeState*)e->decode_state.ptr(), (const uint32_t*)e->sampled.ptr(), (uint32_t*)e->token_ids.ptr(),
+                                               (volatile uint32_t*)e->host_ring.ptr(), (uint32_t*)dev_out, dev_out_base_step);
+        g.c->launches++;
+        if (g.c->sticky != UZU_OK) throw std::runtime_error(g.c->sticky_msg);
+        e->launches += g.c->launches;
+    }
+    cudaEventRecord(e->step_events[e->steps_issued & 1], s);
+    e->steps_issued++;
+    accept(e, 1);
+}
+
+static void upload_decode_state(uzu_engine* e) {
+    DecodeState st{};
+    st.position = e->context_length;
+    st.step = e->steps_issued;
+    st.base_seed = e->sampling.seed;
+    cudaMemcpyAsync((void*)e->decode_state.ptr(), &st, sizeof st, cudaMemcpyHostToDevice, e->ctx->stream);
+    cudaStreamSynchronize(e->ctx->stream);
+}
+
+}  // namespace uzu
+
+#define UZU_ENGINE_TRY(body)                                           \
+    try {                                                              \
+        cudaSetDevice(e ? e->ctx->device : 0);                         \
+        body;                                                          \
+        return UZU_OK;                                                 \
+    } catch (const std::exception& ex) {                               \
+        return uzu::fail(UZU_ERROR_INVALID_ARGUMENT, ex.what());       \
+    }
+
+extern "C" {
+
+uzu_status uzu_engine_create(uzu_context* ctx, const char* model_dir, const uzu_engine_options* opts, uzu_engine** out) {
+    if (!ctx || !model_dir || !out) return fail(UZU_ERROR_INVALID_ARGUMENT, "uzu_engine_create: null argument");
+    auto* e = new uzu_engine();
+    e->ctx = ctx;
+    if (opts) e->opts = *opts;
+    if (e->opts.tp_size == 0) e->opts.tp_size = 1;
+    try {
+        cudaSetDevice(ctx->device);
+        load_model(e, model_dir);
+        create_state_and_scratch(e);
+        reset_state(e);
+        check(uzu_context_synchronize(ctx));
+    } catch (const std::exception& ex) {
+        std::string msg = ex.what();
+        uzu_engine_destroy(e);
+        return fail(UZU_ERROR_IO, std::string("uzu_engine_create: ") + msg);
+    }
+    *out = e;
+    return UZU_OK;
+}
+
+void uzu_engine_destroy(uzu_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->ctx->device);
+    cudaStreamSynchronize(e->ctx->stream);
+    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    for (auto& S : e->state) {
+        if (S.k_sparse) uzu_sparse_buffer_destroy(S.k_sparse);
+        if (S.v_sparse) uzu_sparse_buffer_destroy(S.v_sparse);
+    }
+    for (auto* b : e->owned) uzu_buffer_destroy(b);
+    if (e->step_events[0]) cudaEventDestroy(e->step_events[0]);
+    if (e->step_events[1]) cudaEventDestroy(e->step_events[1]);
+    delete e;
+}
+
+uzu_status uzu_engine_info(const uzu_engine* e, uzu_model_info* out) {
+    if (!e || !out) return fail(UZU_ERROR_INVALID_ARGUMENT, "uzu_engine_info: null argument");
+    *out = e->info;
+    return UZU_OK;
+}
+
+uzu_status uzu_engine_reset(uzu_engine* e) { UZU_ENGINE_TRY(reset_state(e)); }
+
+uint32_t uzu_engine_context_length(const uzu_engine* e) { return e->context_length; }
+
+uzu_status uzu_engine_snapshot(uzu_engine* e) {
+    UZU_ENGINE_TRY({
+        cudaStream_t s = e->ctx->stream;
+        for (auto& S : e->state)
+            if (S.conv_state.b) {
+                cudaMemcpyAsync((void*)S.conv_snapshot.ptr(), (void*)S.conv_state.ptr(), S.conv_bytes, cudaMemcpyDeviceToDevice, s);
+                cudaMemcpyAsync((void*)S.ssm_snapshot.ptr(), (void*)S.ssm_state.ptr(), S.ssm_bytes, cudaMemcpyDeviceToDevice, s);
+            }
+        cudaMemcpyAsync((void*)e->snapshot_token.ptr(), (void*)e->token_ids.ptr(), 4, cudaMemcpyDeviceToDevice, s);
+        cudaStreamSynchronize(s);
+        e->snapshot_context = e->context_length;
+    });
+}
+
+uzu_status uzu_engine_restore(uzu_engine* e) {
+    UZU_ENGINE_TRY({
+        cudaStream_t s = e->ctx->stream;
+        cudaStreamSynchronize(s);
+        for (size_t i = 0; i < e->state.size(); ++i) {
+            auto& S = e->state[i];
+            if (S.conv_state.b) {
+                cudaMemcpyAsync((void*)S.conv_state.ptr(), (void*)S.conv_snapshot.ptr(), S.conv_bytes, cudaMemcpyDeviceToDevice, s);
+                cudaMemcpyAsync((void*)S.ssm_state.ptr(), (void*)S.ssm_snapshot.ptr(), S.ssm_bytes, cudaMemcpyDeviceToDevice, s);
+            } else {
+                S.length = e->snapshot_context;   // KV rows beyond the snapshot are simply overwritten
+            }
+        }
+        cudaMemcpyAsync((void*)e->token_ids.ptr(), (void*)e->snapshot_token.ptr(), 4, cudaMemcpyDeviceToDevice, s);
+        e->context_length = e->snapshot_context;
+        e->steps_returned = e->steps_issued;
+        cudaStreamSynchronize(s);
+        upload_decode_state(e);
+    });
+}
+
+uzu_status uzu_engine_prefill(uzu_engine* e, const uint32_t* tokens, uint32_t count, const uzu_sampling_method* sampling, uint32_t* out_token) {
+    UZU_ENGINE_TRY({
+        if (!tokens || count == 0) throw std::runtime_error("prefill: empty prompt");
+        if (sampling) e->sampling = *sampling;
+        // chunks of <= 1024 (stream.rs:194-195); only the last chunk's last row is sampled. Hybrid (DeltaNet) models are
+        // stepped token by token: this backend implements the DeltaNet decode branch only.
+        const uint32_t step = has_delta(e) ? 1 : MAX_ROWS;
+        for (uint32_t s0 = 0; s0 < count; s0 += step) {
+            const uint32_t n = std::min(step, count - s0);
+            const bool last = s0 + n == count;
+            run_pass(e, tokens + s0, n, last ? n - 1 : 0, last ? n : 0, last);
+        }
+        uint32_t tok = 0;
+        cudaMemcpy(&tok, (void*)e->sampled.ptr(), 4, cudaMemcpyDeviceToHost);
+        // the sampled token becomes the next input, chained on the device
+        cudaMemcpy((void*)e->token_ids.ptr(), (void*)e->sampled.ptr(), 4, cudaMemcpyDeviceToDevice);
+        e->steps_issued = e->steps_returned = 0;
+        upload_decode_state(e);
+        if (out_token) *out_token = tok;
+    });
+}
+
+uzu_status uzu_engine_next(uzu_engine* e, uint32_t* out_token) {
+    UZU_ENGINE_TRY({
+        // keep one pass in flight: issue step N+1, then wait for step N (ForwardPassChaining::InFlight)
+        issue_decode_step(e, 0, 0);
+        if (e->steps_issued - e->steps_returned >= 2) {
+            const uint32_t idx = e->steps_returned;
+            cudaError_t err = cudaEventSynchronize(e->step_events[idx & 1]);
+            if (err != cudaSuccess) throw std::runtime_error(std::string("decode step failed: ") + cudaGetErrorString(err));
+            if (out_token) *out_token = ((volatile uint32_t*)uzu_buffer_cpu_ptr(e->host_ring.b))[idx % TOKEN_RING];
+            e->steps_returned++;
+        } else if (out_token) {
+            *out_token = 0xFFFFFFFFu;   // nothing resolved yet (first call after prefill)
+        }
+    });
+}
+
+uzu_status uzu_engine_flush(uzu_engine* e, uint32_t* out_token) {
+    UZU_ENGINE_TRY({
+        if (e->steps_returned < e->steps_issued) {
+            const uint32_t idx = e->steps_returned;
+            cudaError_t err = cudaEventSynchronize(e->step_events[idx & 1]);
+            if (err != cudaSuccess) throw std::runtime_error(std::string("decode step failed: ") + cudaGetErrorString(err));
+            if (out_token) *out_token = ((volatile uint32_t*)uzu_buffer_cpu_ptr(e->host_ring.b))[idx % TOKEN_RING];
+            e->steps_returned++;
+        } else if (out_token) {
+            *out_token = 0xFFFFFFFFu;
+        }
+    });
+}
+
+uzu_status uzu_engine_decode_device(uzu_engine* e, uint32_t steps, uint64_t out_tokens_dev) {
+    UZU_ENGINE_TRY({
+        const uint32_t base = e->steps_issued;
+        for (uint32_t i = 0; i < steps; ++i) issue_decode_step(e, out_tokens_dev, base);
+        e->steps_returned = e->steps_issued;   // device-resident run: tokens are not resolved on the host
+    });
+}
+
+uzu_status uzu_engine_forward(uzu_engine* e, const uint32_t* tokens, uint32_t count, uint32_t row_begin, uint32_t row_end, uint16_t* out_logits) {
+    UZU_ENGINE_TRY({
+        if (row_end > count || row_begin > row_end || row_end - row_begin > e->logits_rows) throw std::runtime_error("forward: bad row range (<= 16 rows)");
+        if (has_delta(e) && count != 1) throw std::runtime_error("forward: hybrid models take one token per pass");
+        run_pass(e, tokens, count, row_begin, row_end, false);
+        if (out_logits && row_end > row_begin)
+            cudaMemcpy(out_logits, (void*)e->logits.ptr(), (size_t)(row_end - row_begin) * e->vocab * 2, cudaMemcpyDeviceToHost);
+    });
+}
+
+uint64_t uzu_engine_launch_count(const uzu_engine* e) { return e ? e->launches : 0; }
+
+}  // extern "C"
