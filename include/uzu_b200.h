@@ -388,6 +388,15 @@ UZU_API uzu_status uzu_engine_decode_device(uzu_engine* e, uint32_t steps, uint6
 UZU_API uzu_status uzu_engine_forward(uzu_engine* e, const uint32_t* tokens, uint32_t count, uint32_t row_begin,
                                       uint32_t row_end, uint16_t* out_logits);
 UZU_API uint64_t uzu_engine_launch_count(const uzu_engine* e);   /* kernels launched (incl. graph nodes replayed) */
+/* Measurement helpers (bench.py). All time with CUDA events recorded on the engine's stream.
+ *  decode_timed: `steps` device-chained decode passes between two events; returns seconds.
+ *  step_host:    one decode pass fed from and read back to HOST memory: token_in is copied host->device from pinned
+ *                memory, the pass runs, the sampled token is read back (4 B each way) and the call returns it.
+ *  time_linears: every weight-streaming GEMV of one decode step (all layers + readout, m = 1) replayed back to back
+ *                `iters` times between two events; returns seconds and the number of kernel launches. */
+UZU_API uzu_status uzu_engine_decode_timed(uzu_engine* e, uint32_t steps, double* out_seconds);
+UZU_API uzu_status uzu_engine_step_host(uzu_engine* e, uint32_t token_in, uint32_t* token_out);
+UZU_API uzu_status uzu_engine_time_linears(uzu_engine* e, uint32_t iters, double* out_seconds, uint64_t* out_launches);
 
 #ifdef __cplusplus
 }

@@ -130,7 +130,8 @@ uzu_full_precision_embedding_lookup_encode uzu_logit_transform_encode uzu_tensor
 uzu_tensor_add_bias_encode uzu_tensor_add_swap_encode uzu_unified_sampling_encode uzu_delta_net_conv_update_encode
 uzu_delta_net_update_encode uzu_engine_create uzu_engine_destroy uzu_engine_info uzu_engine_reset uzu_engine_context_length
 uzu_engine_snapshot uzu_engine_restore uzu_engine_prefill uzu_engine_next uzu_engine_flush uzu_engine_decode_device
-uzu_engine_forward uzu_engine_launch_count""".split()
+uzu_engine_forward uzu_engine_launch_count uzu_engine_decode_timed uzu_engine_step_host
+uzu_engine_time_linears""".split()
 
 _lib = None
 
@@ -223,6 +224,9 @@ def load() -> C.CDLL:
         "uzu_engine_decode_device": (C.c_int, [vp, u32, u64]),
         "uzu_engine_forward": (C.c_int, [vp, C.POINTER(u32), u32, u32, u32, C.POINTER(C.c_uint16)]),
         "uzu_engine_launch_count": (u64, [vp]),
+        "uzu_engine_decode_timed": (C.c_int, [vp, u32, C.POINTER(C.c_double)]),
+        "uzu_engine_step_host": (C.c_int, [vp, u32, C.POINTER(u32)]),
+        "uzu_engine_time_linears": (C.c_int, [vp, u32, C.POINTER(C.c_double), C.POINTER(u64)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -441,3 +445,18 @@ class Engine:
     @property
     def launch_count(self):
         return self.lib.uzu_engine_launch_count(self.h)
+
+    def decode_timed(self, steps: int) -> float:
+        t = C.c_double()
+        _check(self.lib.uzu_engine_decode_timed(self.h, steps, C.byref(t)))
+        return t.value
+
+    def step_host(self, token: int) -> int:
+        out = u32()
+        _check(self.lib.uzu_engine_step_host(self.h, int(token), C.byref(out)))
+        return out.value
+
+    def time_linears(self, iters: int):
+        t, n = C.c_double(), u64()
+        _check(self.lib.uzu_engine_time_linears(self.h, iters, C.byref(t), C.byref(n)))
+        return t.value, n.value

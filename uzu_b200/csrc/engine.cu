@@ -1124,10 +1124,10 @@ static void upload_decode_state(uzu_engine* e) {
 
 }  // namespace uzu
 
-#define UZU_ENGINE_TRY(body)                                           \
+#define UZU_ENGINE_TRY(...)                                            \
     try {                                                              \
         cudaSetDevice(e ? e->ctx->device : 0);                         \
-        body;                                                          \
+        __VA_ARGS__;                                                   \
         return UZU_OK;                                                 \
     } catch (const std::exception& ex) {                               \
         return uzu::fail(UZU_ERROR_INVALID_ARGUMENT, ex.what());       \
@@ -1287,5 +1287,83 @@ uzu_status uzu_engine_forward(uzu_engine* e, const uint32_t* tokens, uint32_t co
 }
 
 uint64_t uzu_engine_launch_count(const uzu_engine* e) { return e ? e->launches : 0; }
+
+uzu_status uzu_engine_decode_timed(uzu_engine* e, uint32_t steps, double* out_seconds) {
+    UZU_ENGINE_TRY({
+        cudaStream_t s = e->ctx->stream;
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaStreamSynchronize(s);
+        cudaEventRecord(a, s);
+        for (uint32_t i = 0; i < steps; ++i) issue_decode_step(e, 0, 0);
+        cudaEventRecord(b, s);
+        cudaError_t err = cudaEventSynchronize(b);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, a, b);
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        e->steps_returned = e->steps_issued;
+        if (err != cudaSuccess) throw std::runtime_error(std::string("decode_timed: ") + cudaGetErrorString(err));
+        if (out_seconds) *out_seconds = (double)ms * 1e-3;
+    });
+}
+
+uzu_status uzu_engine_step_host(uzu_engine* e, uint32_t token_in, uint32_t* token_out) {
+    UZU_ENGINE_TRY({
+        cudaStream_t s = e->ctx->stream;
+        uint32_t* staging = (uint32_t*)uzu_buffer_cpu_ptr(e->host_tokens.b);
+        staging[0] = token_in;
+        cudaMemcpyAsync((void*)e->token_ids.ptr(), staging, 4, cudaMemcpyHostToDevice, s);   // H2D: this step's input
+        issue_decode_step(e, 0, 0);
+        uint32_t tok = 0;
+        cudaMemcpyAsync(staging + 1, (void*)e->sampled.ptr(), 4, cudaMemcpyDeviceToHost, s); // D2H: this step's result
+        cudaError_t err = cudaStreamSynchronize(s);
+        if (err != cudaSuccess) throw std::runtime_error(std::string("step_host: ") + cudaGetErrorString(err));
+        tok = staging[1];
+        e->steps_returned = e->steps_issued;
+        if (token_out) *token_out = tok;
+    });
+}
+
+uzu_status uzu_engine_time_linears(uzu_engine* e, uint32_t iters, double* out_seconds, uint64_t* out_launches) {
+    UZU_ENGINE_TRY({
+        cudaStream_t s = e->ctx->stream;
+        CmdGuard g(e->ctx, "linears");
+        g.c->state = uzu_command_buffer::Encoding;
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        auto once = [&]() {
+            for (auto& L : e->layers) {
+                if (L.is_attention) {
+                    if (L.attn.has_gate) encode_linear(g.c, L.attn.gate, e->hidden_b.ptr(), 1, e->gate.ptr());
+                    encode_linear(g.c, L.attn.qkv, e->hidden_b.ptr(), 1, e->qkv.ptr());
+                    encode_linear(g.c, L.attn.out, e->attn_out.ptr(), 1, e->mixer_out.ptr());
+                } else {
+                    encode_linear(g.c, L.dn.in_proj, e->hidden_b.ptr(), 1, e->in_proj.ptr());
+                    encode_linear(g.c, L.dn.out_proj, e->delta_out.ptr(), 1, e->mixer_out.ptr());
+                }
+                encode_linear(g.c, L.up, e->hidden_b.ptr(), 1, e->fused_up.ptr());
+                encode_linear(g.c, L.down, e->gated.ptr(), 1, e->hidden_a.ptr());
+            }
+            encode_linear(g.c, e->out_emb, e->normed_out.ptr(), 1, e->logits.ptr());
+        };
+        once();   // warm-up
+        cudaStreamSynchronize(s);
+        const uint64_t before = g.c->launches;
+        cudaEventRecord(a, s);
+        for (uint32_t i = 0; i < iters; ++i) once();
+        cudaEventRecord(b, s);
+        cudaError_t err = cudaEventSynchronize(b);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, a, b);
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        if (err != cudaSuccess || g.c->sticky != UZU_OK) throw std::runtime_error("time_linears failed: " + g.c->sticky_msg);
+        if (out_seconds) *out_seconds = (double)ms * 1e-3;
+        if (out_launches) *out_launches = g.c->launches - before;
+    });
+}
 
 }  // extern "C"
