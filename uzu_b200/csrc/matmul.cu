@@ -89,54 +89,103 @@ __global__ void __launch_bounds__(QMV_WARPS * 32) qmv_kernel(const QmvParams p) 
     const uint32_t grp_end = min(p.groups_per_row, (ce * 128u + NPG - 1) / NPG);
     const uint32_t ngl = grp_end - grp_begin;
 
-    uint4* xs = reinterpret_cast<uint4*>(smem_raw);                                   // [MROWS][nc][4 t][4 w]
-    float* sx = reinterpret_cast<float*>(smem_raw + (size_t)MROWS * nc * 256);        // [MROWS][ngl]
-    float* red = sx + (size_t)MROWS * ngl;                                            // [QMV_WARPS][MT*4][32]
+    const uint32_t coef_stride = ((ngl + 15u) & ~15u) + 2u;                            // float2 units; rows land on distinct banks
+    const uint32_t row_items = (nc * 16u + 31u) & ~31u;                                // staged words per activation row (warp aligned)
+    uint4* xs = reinterpret_cast<uint4*>(smem_raw);                                   // [m][row_items] = [m][nc][4 t][4 w]
+    float2* coef = reinterpret_cast<float2*>(smem_raw + (size_t)p.m * row_items * 16); // [16 rows][coef_stride] (scale, Sx coefficient)
+    float* sx = reinterpret_cast<float*>(coef + 16 * coef_stride);                    // [m][ngl]
+    float* red = sx + (size_t)p.m * ngl;                                              // [QMV_WARPS][MT*4][32]
 
-    // ---- stage activations: permuted bf16 fragments + per-group sums ---------------------------
-    {
-        const uint32_t items = (uint32_t)MROWS * nc * 16;
-        for (uint32_t it = tid; it < items; it += blockDim.x) {
-            uint32_t w_ = it & 3, t_ = (it >> 2) & 3, c_ = (it >> 4) % nc, r = (it >> 4) / nc;
-            uint32_t pos = (cb + c_) * 128u + t_ * 32u + w_ * 8u;  // nibble position of the word
-            uint4 out = make_uint4(0, 0, 0, 0);
-            if (r < p.m && pos < p.np) {
-                if (p.bits == 4) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(p.x + (size_t)r * p.k + pos);
-                    // v holds x0..x7 as (x0,x1),(x2,x3),(x4,x5),(x6,x7); want (x0,x4),(x1,x5),(x2,x6),(x3,x7)
-                    out.x = __byte_perm(v.x, v.z, 0x5410);
-                    out.y = __byte_perm(v.x, v.z, 0x7632);
-                    out.z = __byte_perm(v.y, v.w, 0x5410);
-                    out.w = __byte_perm(v.y, v.w, 0x7632);
-                } else {
-                    // 8-bit: nibble 2j = lo(code_j) -> x_j, nibble 2j+1 = hi(code_j) -> 16*x_j
-                    const uint2 v = *reinterpret_cast<const uint2*>(p.x + (size_t)r * p.k + pos / 2);
-                    __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v.x);  // x0,x1
-                    __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&v.y);  // x2,x3
-                    float x0 = __low2float(a), x1 = __high2float(a), x2 = __low2float(b), x3 = __high2float(b);
-                    // positions p0..p7 = x0,16x0,x1,16x1,x2,16x2,x3,16x3 ; want (p0,p4),(p1,p5),(p2,p6),(p3,p7)
-                    __nv_bfloat162 o0 = __floats2bfloat162_rn(x0, x2);
-                    __nv_bfloat162 o1 = __floats2bfloat162_rn(16.0f * x0, 16.0f * x2);
-                    __nv_bfloat162 o2 = __floats2bfloat162_rn(x1, x3);
-                    __nv_bfloat162 o3 = __floats2bfloat162_rn(16.0f * x1, 16.0f * x3);
-                    out.x = *reinterpret_cast<uint32_t*>(&o0);
-                    out.y = *reinterpret_cast<uint32_t*>(&o1);
-                    out.z = *reinterpret_cast<uint32_t*>(&o2);
-                    out.w = *reinterpret_cast<uint32_t*>(&o3);
-                }
-            }
-            xs[it] = out;
+    const uint32_t row_a = min(tile * 16u + (uint32_t)g, p.n - 1), row_b = min(tile * 16u + (uint32_t)g + 8u, p.n - 1);
+    const uint8_t* wa_base = p.w + (size_t)row_a * p.row_bytes;
+    const uint8_t* wb_base = p.w + (size_t)row_b * p.row_bytes;
+
+    // first weight chunk is requested before the prologue so its HBM latency overlaps the staging work
+    uint4 wa = make_uint4(0, 0, 0, 0), wb = make_uint4(0, 0, 0, 0);
+    uint32_t c = cb + warp;
+    if (c < ce) {
+        const uint32_t pos = c * 128u + (uint32_t)t * 32u;
+        if (pos < p.np) {
+            wa = ldg_stream_u4(wa_base + pos / 2);
+            wb = ldg_stream_u4(wb_base + pos / 2);
         }
-        const uint32_t sitems = (uint32_t)MROWS * ngl;
-        for (uint32_t it = tid; it < sitems; it += blockDim.x) {
-            uint32_t gl = it % ngl, r = it / ngl;
-            float s = 0.0f;
-            if (r < p.m) {
-                uint32_t k0 = (grp_begin + gl) * p.group_size, k1 = min(p.k, k0 + p.group_size);
-                const __nv_bfloat16* xr = p.x + (size_t)r * p.k;
-                for (uint32_t kk = k0; kk < k1; ++kk) s += __bfloat162float(xr[kk]);
+    }
+
+    // ---- prologue 1: permuted bf16 activation fragments + per-group activation sums -----------------------
+    {
+        constexpr uint32_t IPG = NPG / 8;   // staged 8-nibble words per quantisation group (4..32), lanes of one warp
+        const uint32_t items_padded = p.m * row_items;
+        for (uint32_t it = tid; it < items_padded; it += blockDim.x) {
+            uint4 out = make_uint4(0, 0, 0, 0);
+            float part = 0.0f;
+            const uint32_t r = it / row_items, li = it % row_items;
+            uint32_t gl = 0xffffffffu;
+            const bool in_row = li < nc * 16u;
+            if (in_row) {
+                const uint32_t w_ = li & 3, t_ = (li >> 2) & 3, c_ = li >> 4;
+                const uint32_t pos = (cb + c_) * 128u + t_ * 32u + w_ * 8u;  // nibble position of the word
+                gl = pos / NPG - grp_begin;
+                if (pos < p.np) {
+                    if (p.bits == 4) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(p.x + (size_t)r * p.k + pos);
+                        // v = (x0,x1),(x2,x3),(x4,x5),(x6,x7) -> (x0,x4),(x1,x5),(x2,x6),(x3,x7)
+                        out.x = __byte_perm(v.x, v.z, 0x5410);
+                        out.y = __byte_perm(v.x, v.z, 0x7632);
+                        out.z = __byte_perm(v.y, v.w, 0x5410);
+                        out.w = __byte_perm(v.y, v.w, 0x7632);
+                        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { part += __low2float(h2[e]); part += __high2float(h2[e]); }
+                    } else {
+                        // 8-bit: nibble 2j = lo(code_j) -> x_j, nibble 2j+1 = hi(code_j) -> 16*x_j
+                        const uint2 v = *reinterpret_cast<const uint2*>(p.x + (size_t)r * p.k + pos / 2);
+                        __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v.x);  // x0,x1
+                        __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&v.y);  // x2,x3
+                        const float x0 = __low2float(a), x1 = __high2float(a), x2 = __low2float(b), x3 = __high2float(b);
+                        // positions p0..p7 = x0,16x0,x1,16x1,x2,16x2,x3,16x3 ; want (p0,p4),(p1,p5),(p2,p6),(p3,p7)
+                        __nv_bfloat162 o0 = __floats2bfloat162_rn(x0, x2);
+                        __nv_bfloat162 o1 = __floats2bfloat162_rn(16.0f * x0, 16.0f * x2);
+                        __nv_bfloat162 o2 = __floats2bfloat162_rn(x1, x3);
+                        __nv_bfloat162 o3 = __floats2bfloat162_rn(16.0f * x1, 16.0f * x3);
+                        out.x = *reinterpret_cast<uint32_t*>(&o0);
+                        out.y = *reinterpret_cast<uint32_t*>(&o1);
+                        out.z = *reinterpret_cast<uint32_t*>(&o2);
+                        out.w = *reinterpret_cast<uint32_t*>(&o3);
+                        part = ((x0 + x1) + x2) + x3;
+                    }
+                }
+                xs[it] = out;
             }
-            sx[it] = s;
+            // fixed-shape butterfly over the IPG consecutive lanes that hold one group (deterministic)
+#pragma unroll
+            for (uint32_t o = 1; o < IPG; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (in_row && (li & (IPG - 1)) == 0 && gl < ngl) sx[(size_t)r * ngl + gl] = part;
+        }
+    }
+    // ---- prologue 2: per (row, group) dequantisation coefficients: value = s * dot(128 + code) + z * Sx ----
+    {
+        const float mult128 = p.bits == 4 ? 128.0f : 128.0f * 17.0f;
+        const float sym_mid = p.bits == 4 ? 8.0f : 128.0f;
+        for (uint32_t it = tid; it < 16u * ngl; it += blockDim.x) {
+            const uint32_t gl = it % ngl, rr = it / ngl;
+            const uint32_t row = min(tile * 16u + rr, p.n - 1), gi = grp_begin + gl;
+            const float sc = __bfloat162float(p.scales[(size_t)row * p.groups_per_row + gi]);
+            float z;
+            if (p.method == UZU_QMETHOD_SCALE_ZERO_POINT) {
+                float zp;
+                if (p.bits == 4) {
+                    const uint8_t byte = p.zero_points[(size_t)row * p.zp_stride + (gi >> 1)];
+                    zp = (float)((gi & 1) ? (byte >> 4) : (byte & 15));
+                } else {
+                    zp = (float)p.zero_points[(size_t)row * p.zp_stride + gi];
+                }
+                z = -sc * (zp + mult128);
+            } else if (p.method == UZU_QMETHOD_SCALE_BIAS) {
+                z = __bfloat162float(p.biases[(size_t)row * p.groups_per_row + gi]) - sc * mult128;
+            } else {
+                z = -sc * (sym_mid + mult128);
+            }
+            coef[(size_t)rr * coef_stride + gl] = make_float2(sc, z);
         }
     }
     __syncthreads();
@@ -148,23 +197,22 @@ __global__ void __launch_bounds__(QMV_WARPS * 32) qmv_kernel(const QmvParams p) 
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[mt][i] = 0.0f;
 
-    const uint32_t row_a = min(tile * 16u + (uint32_t)g, p.n - 1), row_b = min(tile * 16u + (uint32_t)g + 8u, p.n - 1);
-    const uint8_t* wa_base = p.w + (size_t)row_a * p.row_bytes;
-    const uint8_t* wb_base = p.w + (size_t)row_b * p.row_bytes;
-    const float mult128 = p.bits == 4 ? 128.0f : 128.0f * 17.0f;
-    const float sym_mid = p.bits == 4 ? 8.0f : 128.0f;
-
     // B-fragment ownership: lane (n = g, t) feeds MMA column n with the k-slots of quad lane t.
     const int col_sub = g % CPM, col_mrow = g / CPM;
     const int lane_sub = CPM == 1 ? 0 : (CPM == 2 ? (t >> 1) : t);
-    const bool b_active = (col_sub == lane_sub);
+    const float2* coef_a = coef + (size_t)g * coef_stride;
+    const float2* coef_b = coef + (size_t)(g + 8) * coef_stride;
 
-    for (uint32_t c = cb + warp; c < ce; c += QMV_WARPS) {
-        const uint32_t pos = c * 128u + (uint32_t)t * 32u;
-        uint4 wa = make_uint4(0, 0, 0, 0), wb = make_uint4(0, 0, 0, 0);
-        if (pos < p.np) {
-            wa = ldg_stream_u4(wa_base + pos / 2);
-            wb = ldg_stream_u4(wb_base + pos / 2);
+    for (; c < ce; c += QMV_WARPS) {
+        // software pipeline: request the next chunk of this warp before working on the current one
+        uint4 wa_n = make_uint4(0, 0, 0, 0), wb_n = make_uint4(0, 0, 0, 0);
+        {
+            const uint32_t cn = c + QMV_WARPS;
+            const uint32_t posn = cn * 128u + (uint32_t)t * 32u;
+            if (cn < ce && posn < p.np) {
+                wa_n = ldg_stream_u4(wa_base + posn / 2);
+                wb_n = ldg_stream_u4(wb_base + posn / 2);
+            }
         }
         float d[MT][4];
 #pragma unroll
@@ -181,74 +229,48 @@ __global__ void __launch_bounds__(QMV_WARPS * 32) qmv_kernel(const QmvParams p) 
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 uint4 xb = make_uint4(0, 0, 0, 0);
-                const int mr = mt * MPM + col_mrow;
-                if (b_active) xb = xs[(((size_t)mr * nc + (c - cb)) * 4 + t) * 4 + w_];
+                const uint32_t mr = mt * MPM + col_mrow;
+                if (col_sub == lane_sub && mr < p.m) xb = xs[(size_t)mr * row_items + ((c - cb) * 4 + t) * 4 + w_];
                 // mma A regs: (row g, k 2t..), (row g+8, k 2t..), (row g, k 2t+8..), (row g+8, k 2t+8..)
                 mma_16816(d[mt], a0, b0, a1, b1, xb.x, xb.y);
                 mma_16816(d[mt], a2, b2, a3, b3, xb.z, xb.w);
             }
         }
 
-        // ---- per-group affine part -----------------------------------------------------------------
-        // D columns of this thread: 2t and 2t+1
+        // ---- per-group affine part: D columns of this thread are 2t and 2t+1 ---------------------------------
         const int c0 = 2 * t, c1 = 2 * t + 1;
-        uint32_t g0, g1;
+        uint32_t gl0, gl1;
+        if (CPM == 1) gl0 = gl1 = (c * 128u) / NPG - grp_begin;
+        else { gl0 = c * CPM + (c0 % CPM) - grp_begin; gl1 = gl0 + 1; }
+        const bool v0 = gl0 < ngl, v1 = gl1 < ngl;
+        float2 ca0 = make_float2(0.f, 0.f), ca1 = ca0, cb0 = ca0, cb1 = ca0;
         if (CPM == 1) {
-            g0 = g1 = (c * 128u) / NPG;
-        } else {
-            g0 = c * CPM + (c0 % CPM);
-            g1 = c * CPM + (c1 % CPM);
+            if (v0) { ca0 = ca1 = coef_a[gl0]; cb0 = cb1 = coef_b[gl0]; }
+        } else if (v1) {   // both groups valid: one 128-bit shared load per row (gl0 is even)
+            const float4 fa = *reinterpret_cast<const float4*>(coef_a + gl0);
+            const float4 fb = *reinterpret_cast<const float4*>(coef_b + gl0);
+            ca0 = make_float2(fa.x, fa.y); ca1 = make_float2(fa.z, fa.w);
+            cb0 = make_float2(fb.x, fb.y); cb1 = make_float2(fb.z, fb.w);
+        } else if (v0) {
+            ca0 = coef_a[gl0]; cb0 = coef_b[gl0];
         }
-        const bool v0 = g0 < p.groups_per_row, v1 = g1 < p.groups_per_row;
-        const uint32_t g0c = v0 ? g0 : 0, g1c = v1 ? g1 : 0;
-        float s_a0 = v0 ? __bfloat162float(p.scales[(size_t)row_a * p.groups_per_row + g0c]) : 0.0f;
-        float s_a1 = v1 ? __bfloat162float(p.scales[(size_t)row_a * p.groups_per_row + g1c]) : 0.0f;
-        float s_b0 = v0 ? __bfloat162float(p.scales[(size_t)row_b * p.groups_per_row + g0c]) : 0.0f;
-        float s_b1 = v1 ? __bfloat162float(p.scales[(size_t)row_b * p.groups_per_row + g1c]) : 0.0f;
-        float z_a0, z_a1, z_b0, z_b1;  // coefficient of Sx
-        if (p.method == UZU_QMETHOD_SCALE_ZERO_POINT) {
-            float zp_a0, zp_a1, zp_b0, zp_b1;
-            if (p.bits == 4) {
-                uint8_t ba0 = p.zero_points[(size_t)row_a * p.zp_stride + (g0c >> 1)];
-                uint8_t ba1 = p.zero_points[(size_t)row_a * p.zp_stride + (g1c >> 1)];
-                uint8_t bb0 = p.zero_points[(size_t)row_b * p.zp_stride + (g0c >> 1)];
-                uint8_t bb1 = p.zero_points[(size_t)row_b * p.zp_stride + (g1c >> 1)];
-                zp_a0 = (float)((g0c & 1) ? (ba0 >> 4) : (ba0 & 15));
-                zp_a1 = (float)((g1c & 1) ? (ba1 >> 4) : (ba1 & 15));
-                zp_b0 = (float)((g0c & 1) ? (bb0 >> 4) : (bb0 & 15));
-                zp_b1 = (float)((g1c & 1) ? (bb1 >> 4) : (bb1 & 15));
-            } else {
-                zp_a0 = (float)p.zero_points[(size_t)row_a * p.zp_stride + g0c];
-                zp_a1 = (float)p.zero_points[(size_t)row_a * p.zp_stride + g1c];
-                zp_b0 = (float)p.zero_points[(size_t)row_b * p.zp_stride + g0c];
-                zp_b1 = (float)p.zero_points[(size_t)row_b * p.zp_stride + g1c];
-            }
-            z_a0 = -s_a0 * (zp_a0 + mult128); z_a1 = -s_a1 * (zp_a1 + mult128);
-            z_b0 = -s_b0 * (zp_b0 + mult128); z_b1 = -s_b1 * (zp_b1 + mult128);
-        } else if (p.method == UZU_QMETHOD_SCALE_BIAS) {
-            z_a0 = (v0 ? __bfloat162float(p.biases[(size_t)row_a * p.groups_per_row + g0c]) : 0.0f) - s_a0 * mult128;
-            z_a1 = (v1 ? __bfloat162float(p.biases[(size_t)row_a * p.groups_per_row + g1c]) : 0.0f) - s_a1 * mult128;
-            z_b0 = (v0 ? __bfloat162float(p.biases[(size_t)row_b * p.groups_per_row + g0c]) : 0.0f) - s_b0 * mult128;
-            z_b1 = (v1 ? __bfloat162float(p.biases[(size_t)row_b * p.groups_per_row + g1c]) : 0.0f) - s_b1 * mult128;
-        } else {
-            z_a0 = -s_a0 * (sym_mid + mult128); z_a1 = -s_a1 * (sym_mid + mult128);
-            z_b0 = -s_b0 * (sym_mid + mult128); z_b1 = -s_b1 * (sym_mid + mult128);
-        }
-        // NPG > 128: a group spans several chunks; its Sx term must be counted once -> on the group's first chunk
-        const bool first_chunk_of_group = (NPG <= 128) || ((c * 128u) % NPG == 0) || (c == cb);
+        // NPG > 128: a group spans several chunks; its Sx term is added once, on the group's first chunk
+        const bool first_chunk_of_group = (NPG <= 128) || ((c * 128u) % NPG == 0);
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-            const int mr0 = mt * MPM + c0 / CPM, mr1 = mt * MPM + c1 / CPM;
+            const uint32_t mr0 = mt * MPM + c0 / CPM, mr1 = mt * MPM + c1 / CPM;
             float sx0 = 0.0f, sx1 = 0.0f;
             if (first_chunk_of_group) {
-                if (v0) sx0 = sx[(size_t)mr0 * ngl + (g0c - grp_begin)];
-                if (v1) sx1 = sx[(size_t)mr1 * ngl + (g1c - grp_begin)];
+                if (v0 && mr0 < p.m) sx0 = sx[(size_t)mr0 * ngl + gl0];
+                if (v1 && mr1 < p.m) sx1 = sx[(size_t)mr1 * ngl + gl1];
             }
-            acc[mt][0] += s_a0 * d[mt][0] + z_a0 * sx0;
-            acc[mt][1] += s_a1 * d[mt][1] + z_a1 * sx1;
-            acc[mt][2] += s_b0 * d[mt][2] + z_b0 * sx0;
-            acc[mt][3] += s_b1 * d[mt][3] + z_b1 * sx1;
+            acc[mt][0] += ca0.x * d[mt][0] + ca0.y * sx0;
+            acc[mt][1] += ca1.x * d[mt][1] + ca1.y * sx1;
+            acc[mt][2] += cb0.x * d[mt][2] + cb0.y * sx0;
+            acc[mt][3] += cb1.x * d[mt][3] + cb1.y * sx1;
         }
+        wa = wa_n;
+        wb = wb_n;
     }
 
     // ---- reduce across the CTA's warps (fixed order) ---------------------------------------------------
@@ -448,13 +470,19 @@ static const char* validate(const uzu_matmul_args* a) {
     return nullptr;
 }
 
+static size_t qmv_smem_bytes(uint32_t m, uint32_t nc, uint32_t ngl, int mt) {
+    const uint32_t coef_stride = ((ngl + 15u) & ~15u) + 2u;
+    return (size_t)m * (((size_t)nc * 16 + 31) & ~(size_t)31) * 16 + (size_t)16 * coef_stride * 8 + (size_t)m * ngl * 4 + (size_t)QMV_WARPS * mt * 4 * 32 * 4 + 64;
+}
+
 template <int NPG, int MT>
 static void launch_qmv(uzu_command_buffer* cmd, const QmvParams& p, uint32_t tiles) {
     constexpr int CPM = NPG >= 128 ? 1 : 128 / NPG;
     constexpr int MROWS = MT * (8 / CPM);
     const uint32_t nc = p.chunks_per_slice;
     const uint32_t ngl = (nc * 128u + NPG - 1) / NPG + 1;
-    size_t smem = (size_t)MROWS * nc * 256 + (size_t)MROWS * ngl * 4 + (size_t)QMV_WARPS * MT * 4 * 32 * 4;
+    (void)MROWS;
+    size_t smem = qmv_smem_bytes(p.m, nc, ngl, MT);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(qmv_kernel<NPG, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -512,7 +540,7 @@ static void encode_matmul(uzu_command_buffer* cmd, const uzu_matmul_args& a) {
         uint32_t max_ks = std::max(1u, chunks_total / QMV_WARPS);
         ks = std::min(ks, max_ks);
         uint32_t cps = (chunks_total + ks - 1) / ks;
-        const uint32_t smem_cap_chunks = std::max(1u, (160u * 1024u) / (mrows * 256u + mrows * 16u));
+        const uint32_t smem_cap_chunks = std::max(1u, (150u * 1024u) / (mb * 256u + mb * 16u + 64u));
         cps = std::min(cps, smem_cap_chunks);
         cps = (cps + chunk_align - 1) / chunk_align * chunk_align;
         ks = (chunks_total + cps - 1) / cps;
@@ -521,8 +549,7 @@ static void encode_matmul(uzu_command_buffer* cmd, const uzu_matmul_args& a) {
             cps *= 2;
             ks = (chunks_total + cps - 1) / cps;
         }
-        const size_t smem_need = (size_t)mrows * cps * 256 + (size_t)mrows * ((cps * 128u + npg - 1) / npg + 1) * 4 +
-                                 (size_t)QMV_WARPS * mt * 4 * 32 * 4;
+        const size_t smem_need = qmv_smem_bytes(mb, cps, (cps * 128u + npg - 1) / npg + 1, mt);
         if (smem_need > 200u * 1024u) {  // cannot satisfy both limits: generic fallback
             uzu_matmul_args b = a;
             b.a = a.a + (size_t)m0 * a.k * 2;
