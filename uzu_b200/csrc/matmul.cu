@@ -68,6 +68,16 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a
 // (code_i, code_{i+4}) of a packed word -> bf16x2 holding (128+code_i, 128+code_{i+4}); exact.
 __device__ __forceinline__ uint32_t nib_pair(uint32_t w, int shift) { return ((w >> shift) & 0x000f000fu) | 0x43004300u; }
 
+// Same, tuned for the decode kernel where the integer ALU pipe is the limiter: the shift is a multiply-high
+// (IMAD.HI runs on the FMA pipe, which is otherwise idle) and (x & mask) | magic is forced into ONE LOP3 by keeping
+// the magic constant in a register (ptxas emits two LOP3 when both constants are immediates).
+__device__ __forceinline__ uint32_t nib_pair_fast(uint32_t w, int shift, uint32_t magic_reg) {
+    const uint32_t sh = shift == 0 ? w : __umulhi(w, 1u << (32 - shift));
+    uint32_t d;
+    asm("lop3.b32 %0, %1, 0x000f000f, %2, 0xEA;" : "=r"(d) : "r"(sh), "r"(magic_reg));
+    return d;
+}
+
 constexpr int QMV_WARPS = 8;
 
 // NPG: nibbles per quantisation group (32, 64, 128, 256); MT: MMA column tiles (activation rows = MT * 8 / CPM)
@@ -371,6 +381,597 @@ __global__ void __launch_bounds__(QMV_WARPS * 32) qmv_kernel(const QmvParams p) 
 }
 
 // -------------------------------------------------------------------------------------------------
+// Streaming variant (the decode fast path): persistent warps, no CTA-level synchronisation after the
+// one-time activation staging. A work item is (16-row tile, k-slice); items are dealt round-robin to
+// all resident warps (item id interleaved across CTAs so every SM gets the same share). A warp streams
+// its item in "super-chunks" of 4 x 128 nibbles per row: per lane 8 x 16 B of packed weights plus the
+// matching scale / zero-point vectors, double-buffered in registers, so ~8 KB per warp are in flight
+// while the previous super-chunk is being multiplied. Dequantisation coefficients are derived in
+// registers from the vector-loaded scales (no shared-memory round trip, no per-item prologue).
+// -------------------------------------------------------------------------------------------------
+constexpr int QS_WARPS = 4;
+constexpr int QS_SC = 4;   // chunks per super-chunk
+
+template <int NPG>
+struct SuperChunk {
+    static constexpr int GPS = (QS_SC * 128) / NPG;          // groups per super-chunk: 16, 8, 4, 2
+    static constexpr int SW = GPS >= 2 ? GPS / 2 : 1;        // 32-bit words of bf16 scales (and MLX biases)
+    uint4 wa[QS_SC], wb[QS_SC];
+    uint32_t sa[SW], sb[SW];
+    uint32_t ca[SW], cb[SW];                                 // zero points (packed) or biases
+};
+
+template <int WORDS>
+__device__ __forceinline__ void ldg_words(const void* ptr, uint32_t (&out)[WORDS]) {
+    if constexpr (WORDS == 8) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(ptr)), b = __ldg(reinterpret_cast<const uint4*>(ptr) + 1);
+        out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+    } else if constexpr (WORDS == 4) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(ptr));
+        out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
+    } else if constexpr (WORDS == 2) {
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(ptr));
+        out[0] = a.x; out[1] = a.y;
+    } else {
+        out[0] = __ldg(reinterpret_cast<const uint32_t*>(ptr));
+    }
+}
+
+template <int NPG, int MT>
+__global__ void __launch_bounds__(QS_WARPS * 32) qmv_stream_kernel(const QmvParams p) {
+    constexpr int CPM = NPG >= 128 ? 1 : 128 / NPG;
+    constexpr int MPM = 8 / CPM;
+    constexpr int MROWS = MT * MPM;
+    using SCk = SuperChunk<NPG>;
+    constexpr int GPS = SCk::GPS, SW = SCk::SW;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t nc_all = p.chunks_total;
+    const uint32_t row_items = (nc_all * 16u + 31u) & ~31u;
+    const uint32_t ngroups = p.groups_per_row;
+    uint4* xs = reinterpret_cast<uint4*>(smem_raw);                                     // [m][row_items]
+    float* sx = reinterpret_cast<float*>(smem_raw + (size_t)p.m * row_items * 16);     // [m][ngroups]
+
+    // ---- one-time staging of the activations (whole k range) -------------------------------------------------
+    {
+        constexpr uint32_t IPG = NPG / 8;
+        const uint32_t items_padded = p.m * row_items;
+        for (uint32_t it = tid; it < items_padded; it += blockDim.x) {
+            uint4 out = make_uint4(0, 0, 0, 0);
+            float part = 0.0f;
+            const uint32_t r = it / row_items, li = it % row_items;
+            const bool in_row = li < nc_all * 16u;
+            uint32_t gl = 0xffffffffu;
+            if (in_row) {
+                const uint32_t pos = li * 8u;   // li = (chunk*4 + t)*4 + w  ->  nibble position = li * 8
+                gl = pos / NPG;
+                if (pos < p.np) {
+                    if (p.bits == 4) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(p.x + (size_t)r * p.k + pos);
+                        out.x = __byte_perm(v.x, v.z, 0x5410);
+                        out.y = __byte_perm(v.x, v.z, 0x7632);
+                        out.z = __byte_perm(v.y, v.w, 0x5410);
+                        out.w = __byte_perm(v.y, v.w, 0x7632);
+                        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { part += __low2float(h2[e]); part += __high2float(h2[e]); }
+                    } else {
+                        const uint2 v = *reinterpret_cast<const uint2*>(p.x + (size_t)r * p.k + pos / 2);
+                        __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+                        __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+                        const float x0 = __low2float(a), x1 = __high2float(a), x2 = __low2float(b), x3 = __high2float(b);
+                        __nv_bfloat162 o0 = __floats2bfloat162_rn(x0, x2);
+                        __nv_bfloat162 o1 = __floats2bfloat162_rn(16.0f * x0, 16.0f * x2);
+                        __nv_bfloat162 o2 = __floats2bfloat162_rn(x1, x3);
+                        __nv_bfloat162 o3 = __floats2bfloat162_rn(16.0f * x1, 16.0f * x3);
+                        out.x = *reinterpret_cast<uint32_t*>(&o0);
+                        out.y = *reinterpret_cast<uint32_t*>(&o1);
+                        out.z = *reinterpret_cast<uint32_t*>(&o2);
+                        out.w = *reinterpret_cast<uint32_t*>(&o3);
+                        part = ((x0 + x1) + x2) + x3;
+                    }
+                }
+                xs[it] = out;
+            }
+#pragma unroll
+            for (uint32_t o = 1; o < IPG; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (in_row && (li & (IPG - 1)) == 0 && gl < ngroups) sx[(size_t)r * ngroups + gl] = part;
+        }
+    }
+    __syncthreads();
+
+    const float mult128 = p.bits == 4 ? 128.0f : 128.0f * 17.0f;
+    const float sym_mid = p.bits == 4 ? 8.0f : 128.0f;
+    const int col_sub = g % CPM, col_mrow = g / CPM;
+    const int lane_sub = CPM == 1 ? 0 : (CPM == 2 ? (t >> 1) : t);
+    const uint32_t total_warps = gridDim.x * QS_WARPS;
+    const uint32_t items_total = ((p.n + 15u) / 16u) * p.kslices;
+
+    for (uint32_t item = blockIdx.x + gridDim.x * warp; item < items_total; item += total_warps) {
+        const uint32_t tile = item / p.kslices, slice = item % p.kslices;
+        const uint32_t cb = slice * p.chunks_per_slice;
+        const uint32_t ce = min(p.chunks_total, cb + p.chunks_per_slice);
+        const uint32_t row_a = min(tile * 16u + (uint32_t)g, p.n - 1), row_b = min(tile * 16u + (uint32_t)g + 8u, p.n - 1);
+        const uint8_t* wa_base = p.w + (size_t)row_a * p.row_bytes + (size_t)t * 16;
+        const uint8_t* wb_base = p.w + (size_t)row_b * p.row_bytes + (size_t)t * 16;
+
+        auto load_super = [&](SCk& sc, uint32_t c0) {
+#pragma unroll
+            for (int j = 0; j < QS_SC; ++j) {
+                const uint32_t c = c0 + j;
+                if (c < ce) {
+                    sc.wa[j] = ldg_stream_u4(wa_base + (size_t)c * 64);
+                    sc.wb[j] = ldg_stream_u4(wb_base + (size_t)c * 64);
+                } else {
+                    sc.wa[j] = make_uint4(0, 0, 0, 0);
+                    sc.wb[j] = make_uint4(0, 0, 0, 0);
+                }
+            }
+            const uint32_t gi = (c0 * 128u) / NPG;   // first group of the super-chunk (multiple of GPS)
+            if constexpr (GPS >= 2) {
+                ldg_words<SW>(p.scales + (size_t)row_a * ngroups + gi, sc.sa);
+                ldg_words<SW>(p.scales + (size_t)row_b * ngroups + gi, sc.sb);
+            } else {
+                sc.sa[0] = *reinterpret_cast<const uint16_t*>(p.scales + (size_t)row_a * ngroups + gi);
+                sc.sb[0] = *reinterpret_cast<const uint16_t*>(p.scales + (size_t)row_b * ngroups + gi);
+            }
+            if (p.method == UZU_QMETHOD_SCALE_BIAS) {
+                if constexpr (GPS >= 2) {
+                    ldg_words<SW>(p.biases + (size_t)row_a * ngroups + gi, sc.ca);
+                    ldg_words<SW>(p.biases + (size_t)row_b * ngroups + gi, sc.cb);
+                } else {
+                    sc.ca[0] = *reinterpret_cast<const uint16_t*>(p.biases + (size_t)row_a * ngroups + gi);
+                    sc.cb[0] = *reinterpret_cast<const uint16_t*>(p.biases + (size_t)row_b * ngroups + gi);
+                }
+            } else if (p.method == UZU_QMETHOD_SCALE_ZERO_POINT) {
+                // packed zero points of GPS groups: 4-bit -> GPS/2 bytes, 8-bit -> GPS bytes (<= 16 B)
+                const uint32_t zbytes = p.bits == 4 ? (GPS + 1) / 2 : GPS;
+                const uint8_t* za = p.zero_points + (size_t)row_a * p.zp_stride + (p.bits == 4 ? gi / 2 : gi);
+                const uint8_t* zb = p.zero_points + (size_t)row_b * p.zp_stride + (p.bits == 4 ? gi / 2 : gi);
+#pragma unroll
+                for (int w_ = 0; w_ < SW; ++w_) {
+                    if ((uint32_t)w_ * 4u < zbytes) {
+                        if (zbytes >= 4) {
+                            sc.ca[w_] = __ldg(reinterpret_cast<const uint32_t*>(za) + w_);
+                            sc.cb[w_] = __ldg(reinterpret_cast<const uint32_t*>(zb) + w_);
+                        } else if (zbytes == 2) {
+                            sc.ca[w_] = __ldg(reinterpret_cast<const uint16_t*>(za));
+                            sc.cb[w_] = __ldg(reinterpret_cast<const uint16_t*>(zb));
+                        } else {
+                            sc.ca[w_] = __ldg(za);
+                            sc.cb[w_] = __ldg(zb);
+                        }
+                    } else {
+                        sc.ca[w_] = 0; sc.cb[w_] = 0;
+                    }
+                }
+            }
+        };
+
+        float acc[MT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][i] = 0.0f;
+
+        // (scale, Sx coefficient) of local group `lg` (compile-time constant) for rows a and b
+        auto coef_of = [&](const SCk& sc, int lg, float& s_a, float& z_a, float& s_b, float& z_b) {
+            const uint32_t wa_ = sc.sa[lg >> 1], wb_ = sc.sb[lg >> 1];
+            s_a = __uint_as_float((lg & 1) ? (wa_ & 0xffff0000u) : (wa_ << 16));
+            s_b = __uint_as_float((lg & 1) ? (wb_ & 0xffff0000u) : (wb_ << 16));
+            if (p.method == UZU_QMETHOD_SCALE_ZERO_POINT) {
+                float zpa, zpb;
+                if (p.bits == 4) {
+                    zpa = (float)((sc.ca[lg >> 3] >> ((lg & 7) * 4)) & 15u);
+                    zpb = (float)((sc.cb[lg >> 3] >> ((lg & 7) * 4)) & 15u);
+                } else {
+                    zpa = (float)((sc.ca[lg >> 2] >> ((lg & 3) * 8)) & 255u);
+                    zpb = (float)((sc.cb[lg >> 2] >> ((lg & 3) * 8)) & 255u);
+                }
+                z_a = -s_a * (zpa + mult128);
+                z_b = -s_b * (zpb + mult128);
+            } else if (p.method == UZU_QMETHOD_SCALE_BIAS) {
+                const uint32_t ba_ = sc.ca[lg >> 1], bb_ = sc.cb[lg >> 1];
+                z_a = __uint_as_float((lg & 1) ? (ba_ & 0xffff0000u) : (ba_ << 16)) - s_a * mult128;
+                z_b = __uint_as_float((lg & 1) ? (bb_ & 0xffff0000u) : (bb_ << 16)) - s_b * mult128;
+            } else {
+                z_a = -s_a * (sym_mid + mult128);
+                z_b = -s_b * (sym_mid + mult128);
+            }
+        };
+
+        auto compute_super = [&](const SCk& sc, uint32_t c0) {
+#pragma unroll
+            for (int j = 0; j < QS_SC; ++j) {
+                const uint32_t c = c0 + j;
+                if (c >= ce) break;
+                float d[MT][4];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) d[mt][i] = 0.0f;
+                const uint32_t wav[4] = {sc.wa[j].x ^ p.xor_mask, sc.wa[j].y ^ p.xor_mask, sc.wa[j].z ^ p.xor_mask, sc.wa[j].w ^ p.xor_mask};
+                const uint32_t wbv[4] = {sc.wb[j].x ^ p.xor_mask, sc.wb[j].y ^ p.xor_mask, sc.wb[j].z ^ p.xor_mask, sc.wb[j].w ^ p.xor_mask};
+#pragma unroll
+                for (int w_ = 0; w_ < 4; ++w_) {
+                    const uint32_t a0 = nib_pair(wav[w_], 0), a1 = nib_pair(wav[w_], 4), a2 = nib_pair(wav[w_], 8), a3 = nib_pair(wav[w_], 12);
+                    const uint32_t b0 = nib_pair(wbv[w_], 0), b1 = nib_pair(wbv[w_], 4), b2 = nib_pair(wbv[w_], 8), b3 = nib_pair(wbv[w_], 12);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        uint4 xb = make_uint4(0, 0, 0, 0);
+                        const uint32_t mr = mt * MPM + col_mrow;
+                        if (col_sub == lane_sub && mr < p.m) xb = xs[(size_t)mr * row_items + (c * 4 + t) * 4 + w_];
+                        mma_16816(d[mt], a0, b0, a1, b1, xb.x, xb.y);
+                        mma_16816(d[mt], a2, b2, a3, b3, xb.z, xb.w);
+                    }
+                }
+                // affine part. Local group indices of this thread's two D columns (2t, 2t+1):
+                float sa0, za0, sb0, zb0, sa1, za1, sb1, zb1;
+                uint32_t gi0, gi1;
+                if constexpr (CPM == 1) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const int lg = (j * 128) / NPG;
+                    coef_of(sc, lg, sa0, za0, sb0, zb0);
+                    sa1 = sa0; za1 = za0; sb1 = sb0; zb1 = zb0;
+                    gi0 = gi1 = (c * 128u) / NPG;
+                } else if constexpr (CPM == 2) {
+                    coef_of(sc, 2 * j, sa0, za0, sb0, zb0);
+                    coef_of(sc, 2 * j + 1, sa1, za1, sb1, zb1);
+                    gi0 = c * 2u; gi1 = gi0 + 1u;
+                } else {
+                    float e0, f0, g0_, h0, e1, f1, g1_, h1;
+                    coef_of(sc, 4 * j, sa0, za0, sb0, zb0);
+                    coef_of(sc, 4 * j + 1, sa1, za1, sb1, zb1);
+                    coef_of(sc, 4 * j + 2, e0, f0, g0_, h0);
+                    coef_of(sc, 4 * j + 3, e1, f1, g1_, h1);
+                    if (t & 1) { sa0 = e0; za0 = f0; sb0 = g0_; zb0 = h0; sa1 = e1; za1 = f1; sb1 = g1_; zb1 = h1; }
+                    gi0 = c * 4u + 2u * (t & 1); gi1 = gi0 + 1u;
+                }
+                const bool first_chunk_of_group = (NPG <= 128) || ((j & 1) == 0);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const uint32_t mr0 = mt * MPM + (2 * t) / CPM, mr1 = mt * MPM + (2 * t + 1) / CPM;
+                    float sx0 = 0.0f, sx1 = 0.0f;
+                    if (first_chunk_of_group) {
+                        if (mr0 < p.m) sx0 = sx[(size_t)mr0 * ngroups + gi0];
+                        if (mr1 < p.m) sx1 = sx[(size_t)mr1 * ngroups + gi1];
+                    }
+                    acc[mt][0] += sa0 * d[mt][0] + za0 * sx0;
+                    acc[mt][1] += sa1 * d[mt][1] + za1 * sx1;
+                    acc[mt][2] += sb0 * d[mt][2] + zb0 * sx0;
+                    acc[mt][3] += sb1 * d[mt][3] + zb1 * sx1;
+                }
+            }
+        };
+
+        SCk cur, nxt;
+        load_super(cur, cb);
+        for (uint32_t c0 = cb; c0 < ce; c0 += QS_SC) {
+            const bool more = c0 + QS_SC < ce;
+            if (more) load_super(nxt, c0 + QS_SC);
+            compute_super(cur, c0);
+            if (more) cur = nxt;
+        }
+
+        // ---- epilogue of the item (warp-local) ---------------------------------------------------------------------
+        float outv[MT][2][2];
+        int out_mrow[MT][2];
+        int nslots;
+        if (CPM == 1) {
+            nslots = 2;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                outv[mt][0][0] = acc[mt][0]; outv[mt][0][1] = acc[mt][1];
+                outv[mt][1][0] = acc[mt][2]; outv[mt][1][1] = acc[mt][3];
+                out_mrow[mt][0] = mt * MPM + 2 * t; out_mrow[mt][1] = mt * MPM + 2 * t + 1;
+            }
+        } else if (CPM == 2) {
+            nslots = 1;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                outv[mt][0][0] = acc[mt][0] + acc[mt][1];
+                outv[mt][1][0] = acc[mt][2] + acc[mt][3];
+                outv[mt][0][1] = outv[mt][1][1] = 0.0f;
+                out_mrow[mt][0] = mt * MPM + t; out_mrow[mt][1] = -1;
+            }
+        } else {
+            nslots = 1;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                float a = acc[mt][0] + acc[mt][1], b = acc[mt][2] + acc[mt][3];
+                float a2 = __shfl_xor_sync(0xffffffffu, a, 1), b2 = __shfl_xor_sync(0xffffffffu, b, 1);
+                outv[mt][0][0] = (t & 1) ? (a2 + a) : (a + a2);
+                outv[mt][1][0] = (t & 1) ? (b2 + b) : (b + b2);
+                outv[mt][0][1] = outv[mt][1][1] = 0.0f;
+                out_mrow[mt][0] = (t & 1) ? -1 : mt * MPM + t / 2; out_mrow[mt][1] = -1;
+            }
+        }
+        auto epilogue_store = [&](uint32_t row, uint32_t mrow, float v) {
+            if (row >= p.n || mrow >= p.m) return;
+            const size_t oi = (size_t)mrow * p.n + row;
+            float value = p.ab_scale * v;
+            if (p.accumulate) value += p.d_is_f32 ? reinterpret_cast<float*>(p.d)[oi] : __bfloat162float(reinterpret_cast<__nv_bfloat16*>(p.d)[oi]);
+            if (p.bias) value += __bfloat162float(p.bias[row]);
+            if (p.has_soft_cap) value = p.soft_cap * tanhf(value / p.soft_cap);
+            if (p.d_is_f32) reinterpret_cast<float*>(p.d)[oi] = value;
+            else reinterpret_cast<__nv_bfloat16*>(p.d)[oi] = __float2bfloat16_rn(value);
+        };
+        if (p.kslices == 1) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+                for (int s_ = 0; s_ < nslots; ++s_) {
+                    if (out_mrow[mt][s_] < 0) continue;
+                    epilogue_store(tile * 16u + g, (uint32_t)out_mrow[mt][s_], outv[mt][0][s_]);
+                    epilogue_store(tile * 16u + g + 8, (uint32_t)out_mrow[mt][s_], outv[mt][1][s_]);
+                }
+            continue;
+        }
+        float* wst = p.ws + ((size_t)tile * p.kslices + slice) * (16 * MROWS);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+            for (int s_ = 0; s_ < nslots; ++s_) {
+                if (out_mrow[mt][s_] < 0) continue;
+                wst[out_mrow[mt][s_] * 16 + g] = outv[mt][0][s_];
+                wst[out_mrow[mt][s_] * 16 + g + 8] = outv[mt][1][s_];
+            }
+        __threadfence();
+        __syncwarp();
+        unsigned int ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&p.counters[tile], 1u);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket != p.kslices - 1) continue;
+        __threadfence();
+        const float* wt = p.ws + (size_t)tile * p.kslices * (16 * MROWS);
+        for (int e = lane; e < 16 * MROWS; e += 32) {
+            float sum = 0.0f;
+            for (uint32_t sl = 0; sl < p.kslices; ++sl) sum += __ldcg(wt + (size_t)sl * (16 * MROWS) + e);
+            epilogue_store(tile * 16u + (e & 15), (uint32_t)(e >> 4), sum);
+        }
+        __syncwarp();
+        if (lane == 0) p.counters[tile] = 0;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Decode kernel: the m == 1 specialisation of the streaming variant (the per-token hot path).
+// Profiling the generic streaming kernel showed the integer ALU pipe (shift + LOP3 of the nibble
+// extraction, coefficient unpacking, register moves), not HBM, as the limiter. For one activation row
+// the 8 columns of the MMA tile are free, so the 4 chunks of a super-chunk are steered into *different*
+// column pairs (chunk j -> columns 2j, 2j+1 for group size 64; column j for 128): all 32 MMAs of a
+// super-chunk accumulate into one 4-register fragment, lane t of a quad ends up owning chunk t, and each
+// lane unpacks only the two (scale, zero-point) pairs of its own chunk: the affine work drops 4x, the
+// accumulator is zeroed once per 4 KB, and the two register buffers ping-pong without copies.
+// -------------------------------------------------------------------------------------------------
+template <int NPG>
+__global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_kernel(const QmvParams p) {
+    static_assert(NPG == 64 || NPG == 128, "decode kernel covers int4 gs64 / gs128 and int8 gs64");
+    constexpr int CPM = NPG >= 128 ? 1 : 2;
+    constexpr int GPS = 512 / NPG;    // groups per super-chunk: 8 or 4
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t nc_all = p.chunks_total;
+    const uint32_t row_items = (nc_all * 16u + 31u) & ~31u;
+    const uint32_t ngroups = p.groups_per_row;
+    uint4* xs = reinterpret_cast<uint4*>(smem_raw);                            // [row_items] + one zero block of 4 x uint4
+    float* sx = reinterpret_cast<float*>(smem_raw + (size_t)(row_items + 4) * 16);   // [ngroups]
+    uint32_t magic;
+    asm volatile("mov.b32 %0, 0x43004300;" : "=r"(magic));
+    if (tid < 4) xs[row_items + tid] = make_uint4(0, 0, 0, 0);
+
+    {   // one-time staging of the activation row (same layout as the streaming kernel)
+        constexpr uint32_t IPG = NPG / 8;
+        for (uint32_t it = tid; it < row_items; it += blockDim.x) {
+            uint4 out = make_uint4(0, 0, 0, 0);
+            float part = 0.0f;
+            const bool in_row = it < nc_all * 16u;
+            const uint32_t pos = it * 8u;
+            if (in_row && pos < p.np) {
+                if (p.bits == 4) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(p.x + pos);
+                    out.x = __byte_perm(v.x, v.z, 0x5410);
+                    out.y = __byte_perm(v.x, v.z, 0x7632);
+                    out.z = __byte_perm(v.y, v.w, 0x5410);
+                    out.w = __byte_perm(v.y, v.w, 0x7632);
+                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { part += __low2float(h2[e]); part += __high2float(h2[e]); }
+                } else {
+                    const uint2 v = *reinterpret_cast<const uint2*>(p.x + pos / 2);
+                    __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+                    __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+                    const float x0 = __low2float(a), x1 = __high2float(a), x2 = __low2float(b), x3 = __high2float(b);
+                    __nv_bfloat162 o0 = __floats2bfloat162_rn(x0, x2);
+                    __nv_bfloat162 o1 = __floats2bfloat162_rn(16.0f * x0, 16.0f * x2);
+                    __nv_bfloat162 o2 = __floats2bfloat162_rn(x1, x3);
+                    __nv_bfloat162 o3 = __floats2bfloat162_rn(16.0f * x1, 16.0f * x3);
+                    out.x = *reinterpret_cast<uint32_t*>(&o0);
+                    out.y = *reinterpret_cast<uint32_t*>(&o1);
+                    out.z = *reinterpret_cast<uint32_t*>(&o2);
+                    out.w = *reinterpret_cast<uint32_t*>(&o3);
+                    part = ((x0 + x1) + x2) + x3;
+                }
+            }
+            if (in_row) xs[it] = out;
+#pragma unroll
+            for (uint32_t o = 1; o < IPG; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            const uint32_t gl = pos / NPG;
+            if (in_row && (it & (IPG - 1)) == 0 && gl < ngroups) sx[gl] = part;
+        }
+    }
+    __syncthreads();
+
+    struct Buf {
+        uint4 wa[4], wb[4];
+        uint32_t sa, sb, ca, cb;
+    };
+    const float mult128 = p.bits == 4 ? 128.0f : 128.0f * 17.0f;
+    const float sym_mid = p.bits == 4 ? 8.0f : 128.0f;
+    const bool lane_has_groups = 2 * t < GPS;       // NPG = 128: only lanes t = 0, 1 own columns
+    const uint32_t total_warps = gridDim.x * QS_WARPS;
+    const uint32_t items_total = ((p.n + 15u) / 16u) * p.kslices;
+    // which chunk of a super-chunk this lane feeds into the MMA B operand (column n = g)
+    const int b_chunk = CPM == 2 ? (g >> 1) : g;
+    const bool b_lane = CPM == 2 ? ((g & 1) == (t >> 1)) : true;
+
+    for (uint32_t item = blockIdx.x + gridDim.x * warp; item < items_total; item += total_warps) {
+        const uint32_t tile = item / p.kslices, slice = item % p.kslices;
+        const uint32_t cb = slice * p.chunks_per_slice;
+        const uint32_t ce = min(p.chunks_total, cb + p.chunks_per_slice);
+        const uint32_t row_a = min(tile * 16u + (uint32_t)g, p.n - 1), row_b = min(tile * 16u + (uint32_t)g + 8u, p.n - 1);
+        const uint8_t* wa_base = p.w + (size_t)row_a * p.row_bytes + (size_t)t * 16;
+        const uint8_t* wb_base = p.w + (size_t)row_b * p.row_bytes + (size_t)t * 16;
+        const __nv_bfloat16* sa_base = p.scales + (size_t)row_a * ngroups + 2 * t;
+        const __nv_bfloat16* sb_base = p.scales + (size_t)row_b * ngroups + 2 * t;
+
+        auto load = [&](Buf& b, uint32_t c0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                b.wa[j] = ldg_stream_u4(wa_base + (size_t)(c0 + j) * 64);
+                b.wb[j] = ldg_stream_u4(wb_base + (size_t)(c0 + j) * 64);
+            }
+            b.sa = b.sb = b.ca = b.cb = 0;
+            if (lane_has_groups) {
+                const uint32_t gi = (c0 * 128u) / NPG;   // groups gi + 2t, gi + 2t + 1 belong to this lane
+                b.sa = __ldg(reinterpret_cast<const uint32_t*>(sa_base + gi));
+                b.sb = __ldg(reinterpret_cast<const uint32_t*>(sb_base + gi));
+                if (p.method == UZU_QMETHOD_SCALE_ZERO_POINT) {
+                    if (p.bits == 4) {
+                        b.ca = __ldg(p.zero_points + (size_t)row_a * p.zp_stride + gi / 2 + t);
+                        b.cb = __ldg(p.zero_points + (size_t)row_b * p.zp_stride + gi / 2 + t);
+                    } else {
+                        b.ca = __ldg(reinterpret_cast<const uint16_t*>(p.zero_points + (size_t)row_a * p.zp_stride + gi + 2 * t));
+                        b.cb = __ldg(reinterpret_cast<const uint16_t*>(p.zero_points + (size_t)row_b * p.zp_stride + gi + 2 * t));
+                    }
+                } else if (p.method == UZU_QMETHOD_SCALE_BIAS) {
+                    b.ca = __ldg(reinterpret_cast<const uint32_t*>(p.biases + (size_t)row_a * ngroups + gi + 2 * t));
+                    b.cb = __ldg(reinterpret_cast<const uint32_t*>(p.biases + (size_t)row_b * ngroups + gi + 2 * t));
+                }
+            }
+            if (p.xor_mask) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    b.wa[j].x ^= p.xor_mask; b.wa[j].y ^= p.xor_mask; b.wa[j].z ^= p.xor_mask; b.wa[j].w ^= p.xor_mask;
+                    b.wb[j].x ^= p.xor_mask; b.wb[j].y ^= p.xor_mask; b.wb[j].z ^= p.xor_mask; b.wb[j].w ^= p.xor_mask;
+                }
+            }
+        };
+
+        float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+
+        auto compute = [&](const Buf& b, uint32_t c0) {
+            float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t wav[4] = {b.wa[j].x, b.wa[j].y, b.wa[j].z, b.wa[j].w};
+                const uint32_t wbv[4] = {b.wb[j].x, b.wb[j].y, b.wb[j].z, b.wb[j].w};
+                const bool feeds = b_lane && b_chunk == j;
+                // lanes that do not feed this chunk's column read a shared zero block (no predication, no register zeroing)
+                const uint4* xrow = feeds ? xs + ((size_t)(c0 + j) * 4 + t) * 4 : xs + row_items;
+#pragma unroll
+                for (int w_ = 0; w_ < 4; ++w_) {
+                    const uint4 xb = xrow[w_];
+                    const uint32_t a0 = nib_pair_fast(wav[w_], 0, magic), a1 = nib_pair_fast(wav[w_], 4, magic), a2 = nib_pair_fast(wav[w_], 8, magic), a3 = nib_pair_fast(wav[w_], 12, magic);
+                    const uint32_t b0 = nib_pair_fast(wbv[w_], 0, magic), b1 = nib_pair_fast(wbv[w_], 4, magic), b2 = nib_pair_fast(wbv[w_], 8, magic), b3 = nib_pair_fast(wbv[w_], 12, magic);
+                    mma_16816(d, a0, b0, a1, b1, xb.x, xb.y);
+                    mma_16816(d, a2, b2, a3, b3, xb.z, xb.w);
+                }
+            }
+            // this lane's two D columns (2t, 2t+1) hold groups gi + 2t and gi + 2t + 1 of rows g (d0, d1) and g+8 (d2, d3)
+            if (lane_has_groups) {
+                const uint32_t gi = (c0 * 128u) / NPG + 2 * t;
+                const float2 sxv = *reinterpret_cast<const float2*>(sx + gi);
+                const float sa0 = __uint_as_float(b.sa << 16), sa1 = __uint_as_float(b.sa & 0xffff0000u);
+                const float sb0 = __uint_as_float(b.sb << 16), sb1 = __uint_as_float(b.sb & 0xffff0000u);
+                float ka0, ka1, kb0, kb1;   // Sx coefficient / scale:  value = s * (d + k * Sx)
+                if (p.method == UZU_QMETHOD_SCALE_ZERO_POINT) {
+                    if (p.bits == 4) {
+                        ka0 = -((float)(b.ca & 15u) + mult128); ka1 = -((float)((b.ca >> 4) & 15u) + mult128);
+                        kb0 = -((float)(b.cb & 15u) + mult128); kb1 = -((float)((b.cb >> 4) & 15u) + mult128);
+                    } else {
+                        ka0 = -((float)(b.ca & 255u) + mult128); ka1 = -((float)((b.ca >> 8) & 255u) + mult128);
+                        kb0 = -((float)(b.cb & 255u) + mult128); kb1 = -((float)((b.cb >> 8) & 255u) + mult128);
+                    }
+                    acc0 += sa0 * (d[0] + ka0 * sxv.x);
+                    acc1 += sa1 * (d[1] + ka1 * sxv.y);
+                    acc2 += sb0 * (d[2] + kb0 * sxv.x);
+                    acc3 += sb1 * (d[3] + kb1 * sxv.y);
+                } else if (p.method == UZU_QMETHOD_SCALE_BIAS) {
+                    const float ba0 = __uint_as_float(b.ca << 16), ba1 = __uint_as_float(b.ca & 0xffff0000u);
+                    const float bb0 = __uint_as_float(b.cb << 16), bb1 = __uint_as_float(b.cb & 0xffff0000u);
+                    acc0 += sa0 * (d[0] - mult128 * sxv.x) + ba0 * sxv.x;
+                    acc1 += sa1 * (d[1] - mult128 * sxv.y) + ba1 * sxv.y;
+                    acc2 += sb0 * (d[2] - mult128 * sxv.x) + bb0 * sxv.x;
+                    acc3 += sb1 * (d[3] - mult128 * sxv.y) + bb1 * sxv.y;
+                } else {
+                    const float k = -(sym_mid + mult128);
+                    acc0 += sa0 * (d[0] + k * sxv.x);
+                    acc1 += sa1 * (d[1] + k * sxv.y);
+                    acc2 += sb0 * (d[2] + k * sxv.x);
+                    acc3 += sb1 * (d[3] + k * sxv.y);
+                }
+            }
+        };
+
+        Buf A, B;
+        load(A, cb);
+        for (uint32_t c0 = cb; c0 < ce; c0 += 8) {
+            const bool has_b = c0 + 4 < ce;
+            if (has_b) load(B, c0 + 4);
+            compute(A, c0);
+            if (!has_b) break;
+            if (c0 + 8 < ce) load(A, c0 + 8);
+            compute(B, c0 + 4);
+        }
+
+        // ---- quad reduction (fixed order) and epilogue --------------------------------------------------------------
+        float ra = acc0 + acc1, rb = acc2 + acc3;
+        ra += __shfl_xor_sync(0xffffffffu, ra, 1);
+        rb += __shfl_xor_sync(0xffffffffu, rb, 1);
+        ra += __shfl_xor_sync(0xffffffffu, ra, 2);
+        rb += __shfl_xor_sync(0xffffffffu, rb, 2);
+        auto epilogue_store = [&](uint32_t row, float v) {
+            if (row >= p.n) return;
+            float value = p.ab_scale * v;
+            if (p.accumulate) value += p.d_is_f32 ? reinterpret_cast<float*>(p.d)[row] : __bfloat162float(reinterpret_cast<__nv_bfloat16*>(p.d)[row]);
+            if (p.bias) value += __bfloat162float(p.bias[row]);
+            if (p.has_soft_cap) value = p.soft_cap * tanhf(value / p.soft_cap);
+            if (p.d_is_f32) reinterpret_cast<float*>(p.d)[row] = value;
+            else reinterpret_cast<__nv_bfloat16*>(p.d)[row] = __float2bfloat16_rn(value);
+        };
+        if (p.kslices == 1) {
+            if (t == 0) {
+                epilogue_store(tile * 16u + g, ra);
+                epilogue_store(tile * 16u + g + 8, rb);
+            }
+            continue;
+        }
+        float* wst = p.ws + ((size_t)tile * p.kslices + slice) * 16;
+        if (t == 0) {
+            wst[g] = ra;
+            wst[g + 8] = rb;
+        }
+        __threadfence();
+        __syncwarp();
+        unsigned int ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&p.counters[tile], 1u);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket != p.kslices - 1) continue;
+        __threadfence();
+        if (lane < 16) {
+            const float* wt = p.ws + (size_t)tile * p.kslices * 16;
+            float sum = 0.0f;
+            for (uint32_t sl = 0; sl < p.kslices; ++sl) sum += __ldcg(wt + (size_t)sl * 16 + lane);
+            epilogue_store(tile * 16u + lane, sum);
+        }
+        __syncwarp();
+        if (lane == 0) p.counters[tile] = 0;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // Generic kernel: one warp per output element, the reference loop verbatim (any dtype / layout / gather).
 // -------------------------------------------------------------------------------------------------
 struct GenericParams {
@@ -493,6 +1094,37 @@ static void launch_qmv(uzu_command_buffer* cmd, const QmvParams& p, uint32_t til
 }
 
 template <int NPG>
+static void launch_qmv_decode(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(qmv_decode_kernel<NPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    qmv_decode_kernel<NPG><<<grid, QS_WARPS * 32, smem, cmd->ctx->stream>>>(p);
+    after_launch(cmd, "qmv_decode_kernel");
+}
+
+template <int NPG, int MT>
+static void launch_qmv_stream(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(qmv_stream_kernel<NPG, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    qmv_stream_kernel<NPG, MT><<<grid, QS_WARPS * 32, smem, cmd->ctx->stream>>>(p);
+    after_launch(cmd, "qmv_stream_kernel");
+}
+
+template <int NPG>
+static void launch_qmv_stream_mt(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem, int mt) {
+    switch (mt) {
+        case 1: launch_qmv_stream<NPG, 1>(cmd, p, grid, smem); break;
+        case 2: launch_qmv_stream<NPG, 2>(cmd, p, grid, smem); break;
+        default: launch_qmv_stream<NPG, 4>(cmd, p, grid, smem); break;
+    }
+}
+
+template <int NPG>
 static void launch_qmv_mt(uzu_command_buffer* cmd, const QmvParams& p, uint32_t tiles, int mt) {
     switch (mt) {
         case 1: launch_qmv<NPG, 1>(cmd, p, tiles); break;
@@ -533,6 +1165,69 @@ static void encode_matmul(uzu_command_buffer* cmd, const uzu_matmul_args& a) {
         int mt = (int)((mb + mpm - 1) / mpm);
         mt = mt <= 1 ? 1 : (mt == 2 ? 2 : 4);
         const uint32_t mrows = mt * mpm;
+        // ---- streaming kernel (decode fast path) when the whole activation row set fits shared memory ----------
+        static const bool force_tile = getenv("UZU_QMV_TILE") != nullptr;
+        const uint32_t gps = 512u / npg;
+        const size_t stream_smem = (size_t)mb * (((size_t)chunks_total * 16 + 31) & ~(size_t)31) * 16 +
+                                   (size_t)mb * ((a.k + a.b_group_size - 1) / a.b_group_size) * 4 + 64 + 64;
+        if (!force_tile && np % 512 == 0 && a.k % a.b_group_size == 0 && (a.k / a.b_group_size) % gps == 0 && stream_smem <= 150u * 1024u &&
+            ((a.b_scales & 15) == 0) && ((a.b_zero_points & 15) == 0) && ((a.b_biases & 15) == 0)) {
+            // items = (tile, k-slice); aim for >= 2 items per resident warp, slices of >= 2 super-chunks
+            const uint32_t ctas_per_sm = stream_smem <= 40u * 1024u ? 4u : (stream_smem <= 70u * 1024u ? 3u : (stream_smem <= 100u * 1024u ? 2u : 1u));
+            const uint32_t grid = (uint32_t)ctx->sm_count * ctas_per_sm;
+            const uint32_t warps = grid * QS_WARPS;
+            const uint32_t scs = chunks_total / QS_SC;            // super-chunks per row
+            uint32_t want_slices = (2u * warps + tiles - 1) / tiles;
+            uint32_t max_slices = std::max(1u, scs / 2u);
+            uint32_t ks = std::max(1u, std::min(want_slices, max_slices));
+            uint32_t sc_per_slice = (scs + ks - 1) / ks;
+            ks = (scs + sc_per_slice - 1) / sc_per_slice;
+            while (ks > 1 && ((size_t)tiles * ks * 16 * mrows * 4 > ctx->splitk_ws_bytes || tiles > ctx->splitk_counter_count)) {
+                sc_per_slice *= 2;
+                ks = (scs + sc_per_slice - 1) / sc_per_slice;
+            }
+            QmvParams p{};
+            p.w = (const uint8_t*)a.b;
+            p.scales = (const __nv_bfloat16*)a.b_scales;
+            p.zero_points = (const uint8_t*)a.b_zero_points;
+            p.biases = (const __nv_bfloat16*)a.b_biases;
+            p.x = (const __nv_bfloat16*)a.a + (size_t)m0 * a.k;
+            p.d = (void*)(a.d + (size_t)m0 * a.n * (a.output_dt == UZU_DT_F32 ? 4 : 2));
+            p.bias = (a.d_transform & UZU_D_BIAS) ? (const __nv_bfloat16*)a.bias : nullptr;
+            p.ws = ctx->splitk_ws;
+            p.counters = ctx->splitk_counters;
+            p.m = mb; p.n = a.n; p.k = a.k;
+            p.np = np;
+            p.row_bytes = np / 2;
+            p.groups_per_row = a.k / a.b_group_size;
+            p.zp_stride = bits == 4 ? (p.groups_per_row + 1) / 2 : p.groups_per_row;
+            p.group_size = a.b_group_size;
+            p.chunks_total = chunks_total; p.chunks_per_slice = sc_per_slice * QS_SC; p.kslices = ks;
+            p.method = a.b_prologue == UZU_B_SCALE_BIAS_DEQUANT ? UZU_QMETHOD_SCALE_BIAS
+                       : a.b_prologue == UZU_B_SCALE_ZERO_POINT_DEQUANT ? UZU_QMETHOD_SCALE_ZERO_POINT : UZU_QMETHOD_SCALE_SYMMETRIC;
+            p.bits = bits;
+            p.xor_mask = a.b_signed_codes ? (bits == 4 ? 0x88888888u : 0x80808080u) : 0u;
+            p.d_is_f32 = a.output_dt == UZU_DT_F32;
+            p.accumulate = (a.d_transform & UZU_D_ACCUMULATE) != 0;
+            p.has_soft_cap = (a.d_transform & UZU_D_SOFT_CAP) != 0;
+            p.ab_scale = (a.d_transform & UZU_D_SCALE) ? a.ab_scale : 1.0f;
+            p.soft_cap = a.soft_cap;
+            const uint32_t items = tiles * ks;
+            const uint32_t use_grid = std::min(grid, std::max(1u, (items + QS_WARPS - 1) / QS_WARPS));
+            static const bool no_decode_kernel = getenv("UZU_QMV_NO_DECODE") != nullptr;
+            if (mb == 1 && (npg == 64 || npg == 128) && !no_decode_kernel) {
+                if (npg == 64) launch_qmv_decode<64>(cmd, p, use_grid, stream_smem);
+                else launch_qmv_decode<128>(cmd, p, use_grid, stream_smem);
+                continue;
+            }
+            switch (npg) {
+                case 32: launch_qmv_stream_mt<32>(cmd, p, use_grid, stream_smem, mt); break;
+                case 64: launch_qmv_stream_mt<64>(cmd, p, use_grid, stream_smem, mt); break;
+                case 128: launch_qmv_stream_mt<128>(cmd, p, use_grid, stream_smem, mt); break;
+                default: launch_qmv_stream_mt<256>(cmd, p, use_grid, stream_smem, mt); break;
+            }
+            continue;
+        }
         // k slicing: enough CTAs to fill the machine, >= 1 chunk per warp, activations must fit shared memory
         uint32_t ks = 1;
         const uint32_t target = 4u * (uint32_t)ctx->sm_count;
