@@ -25,6 +25,8 @@ namespace uzu {
 // AttentionPrepare
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) attention_prepare_kernel(const uzu_attention_prepare_args a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t total_heads = a.has_kv ? a.num_q_heads + 2 * a.num_kv_heads : a.num_q_heads;
     const uint32_t b = blockIdx.y, h = blockIdx.x;
     const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(a.qkv);
@@ -116,6 +118,8 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attn_split_kernel(const AttnP
     constexpr int LPK = D / EPL;     // lanes per key
     constexpr int KPW = 32 / LPK;    // keys per warp step
     static_assert(LPK >= 1 && LPK <= 32 && (EPL % 8) == 0, "bad attention tiling");
+    pdl_launch_dependents();
+    pdl_wait();
     uzu_attention_args a = p.a;
     uint32_t keys_per_split = p.keys_per_split;
     if (a.dynamic_position) {
@@ -309,6 +313,8 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attn_split_kernel(const AttnP
 
 // AttentionTwoPass2 (attention_two_pass.rs:139-189): merge 32 blocks. One warp per (head, token).
 __global__ void __launch_bounds__(128) attn_two_pass2_kernel(const uzu_attention_two_pass2_args a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const uint32_t unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (unit >= a.num_heads * a.suffix_length) return;
@@ -352,6 +358,8 @@ __global__ void __launch_bounds__(256) kv_cache_update_kernel(__nv_bfloat16* key
 }
 
 __global__ void __launch_bounds__(256) sigmoid_gate_kernel(const __nv_bfloat16* gate, __nv_bfloat16* output, uint32_t total) {
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const float g = bf2f(gate[idx]);
@@ -365,8 +373,7 @@ __global__ void __launch_bounds__(256) sigmoid_gate_kernel(const __nv_bfloat16* 
 template <int D, int G, int EPL>
 static void launch_attn(uzu_command_buffer* cmd, const AttnParams& p, uint32_t head_groups) {
     dim3 grid(head_groups, p.a.suffix_length, p.nsplits);
-    attn_split_kernel<D, G, EPL><<<grid, ATTN_WARPS * 32, 0, cmd->ctx->stream>>>(p);
-    after_launch(cmd, "attn_split_kernel");
+    launch(cmd, "attn_split_kernel", attn_split_kernel<D, G, EPL>, grid, dim3(ATTN_WARPS * 32), 0, p);
 }
 
 template <int D>
@@ -435,8 +442,7 @@ void uzu_attention_prepare_encode(uzu_command_buffer* cmd, const uzu_attention_p
     if (a->batch_dim == 0 || total_heads == 0) return;
     dim3 grid(total_heads, a->batch_dim);
     uint32_t threads = a->head_dim >= 256 ? 256 : (a->head_dim >= 128 ? 128 : 64);
-    uzu::attention_prepare_kernel<<<grid, threads, 0, cmd->ctx->stream>>>(*a);
-    uzu::after_launch(cmd, "attention_prepare_kernel");
+    uzu::launch(cmd, "attention_prepare_kernel", uzu::attention_prepare_kernel, grid, dim3(threads), 0, *a);
 }
 
 void uzu_attention_single_pass_encode(uzu_command_buffer* cmd, const uzu_attention_args* a) {
@@ -519,8 +525,7 @@ void uzu_attention_two_pass2_encode(uzu_command_buffer* cmd, const uzu_attention
     }
     const uint32_t units = a->num_heads * a->suffix_length;
     if (units == 0) return;
-    uzu::attn_two_pass2_kernel<<<(units + 3) / 4, 128, 0, cmd->ctx->stream>>>(*a);
-    uzu::after_launch(cmd, "attn_two_pass2_kernel");
+    uzu::launch(cmd, "attn_two_pass2_kernel", uzu::attn_two_pass2_kernel, dim3((units + 3) / 4), dim3(128), 0, *a);
 }
 
 void uzu_kv_cache_update_encode(uzu_command_buffer* cmd, const uzu_kv_cache_update_args* a) {
@@ -547,9 +552,8 @@ void uzu_sigmoid_gate_encode(uzu_command_buffer* cmd, uint64_t gate, uint64_t ou
         cmd->record_error(UZU_ERROR_INVALID_ARGUMENT, "sigmoid_gate: null operand");
         return;
     }
-    uzu::sigmoid_gate_kernel<<<(total_elements + 255) / 256, 256, 0, cmd->ctx->stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(gate), reinterpret_cast<__nv_bfloat16*>(output), total_elements);
-    uzu::after_launch(cmd, "sigmoid_gate_kernel");
+    uzu::launch(cmd, "sigmoid_gate_kernel", uzu::sigmoid_gate_kernel, dim3((total_elements + 255) / 256), dim3(256), 0,
+                reinterpret_cast<const __nv_bfloat16*>(gate), reinterpret_cast<__nv_bfloat16*>(output), total_elements);
 }
 
 }  // extern "C"

@@ -75,6 +75,28 @@ inline void after_launch(uzu_command_buffer* cmd, const char* what) {
     cmd->launches++;
 }
 
+#ifdef __CUDACC__
+// Launch through cudaLaunchKernelEx so the command buffer can opt kernels into programmatic dependent launch.
+template <typename... KArgs, typename... Args>
+inline void launch(uzu_command_buffer* cmd, const char* what, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = cmd->ctx->stream;
+    cudaLaunchAttribute attr[1];
+    if (cmd->use_pdl) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    if (e != cudaSuccess) cmd->record_error(UZU_ERROR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    cmd->launches++;
+}
+#endif
+
 inline bool encodable(uzu_command_buffer* cmd, const char* what) {
     if (!cmd) return false;
     if (cmd->state != uzu_command_buffer::Encoding) {
@@ -115,6 +137,12 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     t = warp_sum(t);
     return t;
 }
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may start
+// while its predecessor is still running; it must not touch the predecessor's outputs (or write anything the predecessor
+// reads) before pdl_wait(). Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
     uint4 r;

@@ -9,6 +9,8 @@
 namespace uzu {
 
 __global__ void __launch_bounds__(256) delta_net_conv_update_kernel(const uzu_delta_net_conv_update_args a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.conv_dim) return;
     const float* w = reinterpret_cast<const float*>(a.conv_weight) + (size_t)c * a.kernel_size;
@@ -31,6 +33,8 @@ __global__ void __launch_bounds__(DN_WARPS * 32) delta_net_update_kernel(const u
     __shared__ float sq[DK], sk[DK];
     __shared__ float so[256];
     __shared__ float red[32];
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t hv = blockIdx.x;
     const uint32_t hk = hv / (a.num_v_heads / a.num_k_heads);
@@ -110,8 +114,7 @@ void uzu_delta_net_conv_update_encode(uzu_command_buffer* cmd, const uzu_delta_n
         return;
     }
     if (a->conv_dim == 0) return;
-    uzu::delta_net_conv_update_kernel<<<(a->conv_dim + 255) / 256, 256, 0, cmd->ctx->stream>>>(*a);
-    uzu::after_launch(cmd, "delta_net_conv_update_kernel");
+    uzu::launch(cmd, "delta_net_conv_update_kernel", uzu::delta_net_conv_update_kernel, dim3((a->conv_dim + 255) / 256), dim3(256), 0, *a);
 }
 
 void uzu_delta_net_update_encode(uzu_command_buffer* cmd, const uzu_delta_net_update_args* a) {
@@ -124,8 +127,7 @@ void uzu_delta_net_update_encode(uzu_command_buffer* cmd, const uzu_delta_net_up
         cmd->record_error(UZU_ERROR_UNSUPPORTED, "delta_net_update: HEAD_K_DIM must be 128 and head_v_dim <= 256");
         return;
     }
-    uzu::delta_net_update_kernel<<<a->num_v_heads, uzu::DN_WARPS * 32, 0, cmd->ctx->stream>>>(*a);
-    uzu::after_launch(cmd, "delta_net_update_kernel");
+    uzu::launch(cmd, "delta_net_update_kernel", uzu::delta_net_update_kernel, dim3(a->num_v_heads), dim3(uzu::DN_WARPS * 32), 0, *a);
 }
 
 }  // extern "C"

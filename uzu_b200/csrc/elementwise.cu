@@ -8,6 +8,8 @@ namespace uzu {
 
 // out[t,j] = bf16( value * bf16(act(gate)) ): two bf16 roundings (gated_act_mul/mod.rs:5-12)
 __global__ void __launch_bounds__(256) gated_act_mul_kernel(const uzu_gated_act_mul_args a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     if (j >= a.gated_dim) return;
     const __nv_bfloat16* act_operand = reinterpret_cast<const __nv_bfloat16*>(a.act_operand);
@@ -28,6 +30,8 @@ __global__ void __launch_bounds__(256) gated_act_mul_kernel(const uzu_gated_act_
 }
 
 __global__ void __launch_bounds__(256) quant_embedding_lookup_kernel(const uzu_quantized_embedding_lookup_args a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     if (d >= a.model_dim) return;
     const uint32_t tok = reinterpret_cast<const uint32_t*>(a.token_ids)[b];
@@ -138,8 +142,7 @@ void uzu_gated_act_mul_encode(uzu_command_buffer* cmd, const uzu_gated_act_mul_a
     }
     if (a->gated_dim == 0 || a->batch_dim == 0) return;
     dim3 grid(blocks_for(a->gated_dim), a->batch_dim);
-    gated_act_mul_kernel<<<grid, 256, 0, cmd->ctx->stream>>>(*a);
-    after_launch(cmd, "gated_act_mul_kernel");
+    launch(cmd, "gated_act_mul_kernel", gated_act_mul_kernel, grid, dim3(256), 0, *a);
 }
 
 void uzu_quantized_embedding_lookup_encode(uzu_command_buffer* cmd, const uzu_quantized_embedding_lookup_args* a) {
@@ -152,8 +155,7 @@ void uzu_quantized_embedding_lookup_encode(uzu_command_buffer* cmd, const uzu_qu
     }
     if (a->batch_size == 0 || a->model_dim == 0) return;
     dim3 grid(blocks_for(a->model_dim), a->batch_size);
-    quant_embedding_lookup_kernel<<<grid, 256, 0, cmd->ctx->stream>>>(*a);
-    after_launch(cmd, "quant_embedding_lookup_kernel");
+    launch(cmd, "quant_embedding_lookup_kernel", quant_embedding_lookup_kernel, grid, dim3(256), 0, *a);
 }
 
 void uzu_full_precision_embedding_lookup_encode(uzu_command_buffer* cmd, uint64_t token_ids, uint64_t weights, uint64_t output,

@@ -386,6 +386,7 @@ struct uzu_engine {
     uint32_t graph_bucket = 0;
     bool graph_stochastic = false;
     uint64_t graph_launches_per_step = 0;
+    bool use_pdl = true;   // programmatic dependent launch between the kernels of a decode step (UZU_NO_PDL=1 disables)
     uint64_t launches = 0;
     uzu_model_info info{};
 };
@@ -1051,6 +1052,7 @@ static void capture_decode_graph(uzu_engine* e) {
     cudaStreamSynchronize(s);
     if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) throw std::runtime_error("cudaStreamBeginCapture failed");
     g.c->state = uzu_command_buffer::Encoding;   // events are not recorded inside a capture
+    g.c->use_pdl = e->use_pdl;
     if (e->sampling.kind == UZU_SAMPLING_STOCHASTIC) {
         decode_step_begin_kernel<<<1, 1, 0, s>>>((const DecodeState*)e->decode_state.ptr(), (unsigned long long*)e->seeds.ptr());
         g.c->launches++;
@@ -1093,6 +1095,7 @@ static void issue_decode_step(uzu_engine* e, uint64_t dev_out, uint32_t dev_out_
     } else {
         CmdGuard g(e->ctx, "decode");
         g.c->state = uzu_command_buffer::Encoding;
+        g.c->use_pdl = e->use_pdl;
         if (e->sampling.kind == UZU_SAMPLING_STOCHASTIC) {
             decode_step_begin_kernel<<<1, 1, 0, s>>>((const DecodeState*)e->decode_state.ptr(), (unsigned long long*)e->seeds.ptr());
             g.c->launches++;
@@ -1141,6 +1144,7 @@ uzu_status uzu_engine_create(uzu_context* ctx, const char* model_dir, const uzu_
     e->ctx = ctx;
     if (opts) e->opts = *opts;
     if (e->opts.tp_size == 0) e->opts.tp_size = 1;
+    e->use_pdl = getenv("UZU_NO_PDL") == nullptr;
     try {
         cudaSetDevice(ctx->device);
         load_model(e, model_dir);

@@ -11,6 +11,8 @@ namespace uzu {
 
 __global__ void __launch_bounds__(1024) normalization_kernel(const uzu_normalization_args a) {
     __shared__ float red[32];
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t row = blockIdx.x;
     const uint32_t n = a.element_count;
     const size_t off = (size_t)row * n;
@@ -62,6 +64,8 @@ __global__ void __launch_bounds__(1024) normalization_kernel(const uzu_normaliza
 // one warp per (row, head)
 __global__ void __launch_bounds__(128) qkv_norm_kernel(const uzu_qkv_norm_args a) {
     const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (unit >= a.batch_size * a.head_count) return;
     const uint32_t b = unit / a.head_count, h = unit % a.head_count;
@@ -105,8 +109,7 @@ void uzu_normalization_encode(uzu_command_buffer* cmd, const uzu_normalization_a
     }
     if (a->batch_size == 0 || a->element_count == 0) return;
     uint32_t threads = a->element_count >= 4096 ? 1024 : (a->element_count >= 1024 ? 512 : 256);
-    uzu::normalization_kernel<<<a->batch_size, threads, 0, cmd->ctx->stream>>>(*a);
-    uzu::after_launch(cmd, "normalization_kernel");
+    uzu::launch(cmd, "normalization_kernel", uzu::normalization_kernel, dim3(a->batch_size), dim3(threads), 0, *a);
 }
 
 void uzu_qkv_norm_encode(uzu_command_buffer* cmd, const uzu_qkv_norm_args* a) {
@@ -117,8 +120,7 @@ void uzu_qkv_norm_encode(uzu_command_buffer* cmd, const uzu_qkv_norm_args* a) {
     }
     uint32_t units = a->batch_size * a->head_count;
     if (units == 0) return;
-    uzu::qkv_norm_kernel<<<(units + 3) / 4, 128, 0, cmd->ctx->stream>>>(*a);
-    uzu::after_launch(cmd, "qkv_norm_kernel");
+    uzu::launch(cmd, "qkv_norm_kernel", uzu::qkv_norm_kernel, dim3((units + 3) / 4), dim3(128), 0, *a);
 }
 
 }  // extern "C"

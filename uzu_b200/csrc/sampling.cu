@@ -76,6 +76,8 @@ __global__ void __launch_bounds__(1024) sampling_argmax_kernel(const uzu_unified
                                                                unsigned int* tickets) {
     __shared__ unsigned long long red[32];
     __shared__ unsigned int sm_ticket;
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t row = row0 + blockIdx.y, V = a.vocab_size;
     const __nv_bfloat16* logits = reinterpret_cast<const __nv_bfloat16*>(a.logits) + (size_t)row * V;
     const uint32_t* bitmask = a.has_bitmask ? reinterpret_cast<const uint32_t*>(a.bitmask) + (size_t)row * ((V + 31) / 32) : nullptr;
@@ -248,8 +250,7 @@ void uzu_unified_sampling_encode(uzu_command_buffer* cmd, const uzu_unified_samp
     for (uint32_t row0 = 0; row0 < a->batch_size; row0 += uzu::SAMPLING_ROWS_PER_LAUNCH) {
         const uint32_t rows = std::min(uzu::SAMPLING_ROWS_PER_LAUNCH, a->batch_size - row0);
         dim3 grid(nblocks, rows);
-        uzu::sampling_argmax_kernel<<<grid, 1024, 0, ctx->stream>>>(*a, row0, ctx->sampling_ws, tickets);
-        uzu::after_launch(cmd, "sampling_argmax_kernel");
+        uzu::launch(cmd, "sampling_argmax_kernel", uzu::sampling_argmax_kernel, grid, dim3(1024), 0, *a, row0, ctx->sampling_ws, tickets);
     }
 }
 
