@@ -121,6 +121,21 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def max_over_ranks(dist, seconds: float, device: str) -> float:
+    """Timing contract: every number reported is the MAX over ranks of the device-timed region."""
+    if dist is None:
+        return seconds
+    import torch
+    t = torch.tensor([seconds], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def whole_job_value(world: int, steps: int, seconds_max: float) -> float:
+    """Replicas (weak scaling): every rank decodes `steps` tokens; whole-job throughput = all tokens / slowest rank."""
+    return world * steps / seconds_max
+
+
 def hbm_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -209,7 +224,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     max_ctx = max(1024, prefill + K + W + 64)
 
     ctx = B.Context(local_rank)
-    eng = B.Engine(ctx, mdir, max_context_length=max_ctx, use_cuda_graph=not args.no_graph)
+    eng = B.Engine(ctx, mdir, max_context_length=max_ctx, use_cuda_graph=not args.no_graph, fused_decode=args.fused)
     info = eng.info
     rng = np.random.default_rng(0)
     prompt = rng.integers(0, info.vocab_size, prefill).astype(np.uint32)
@@ -234,12 +249,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if dist:
         import torch
         torch.cuda.synchronize()
-        t = torch.tensor([seconds], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        seconds = float(t.item())
+        seconds = max_over_ranks(dist, seconds, "cuda")
         dist.barrier()
     clocks = sampler.stop()
-    value = world * K / seconds
+    value = whole_job_value(world, K, seconds)
 
     # ---- end to end through host buffers ----
     eng.restore()
@@ -254,12 +267,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     for _ in range(K):
         tok = eng.step_host(tok)
     e2e_s = time.perf_counter() - t0
-    if dist:
-        import torch
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * K / e2e_s
+    e2e_s = max_over_ranks(dist, e2e_s, "cuda")
+    e2e_value = whole_job_value(world, K, e2e_s)
 
     # ---- roofline of the dominant kernel (fused dequant + GEMV) ----
     iters = 10
@@ -289,7 +298,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "model_dim": info.model_dim, "vocab": info.vocab_size, "weight_bytes_per_token": info.weight_bytes_per_token,
             "kv_bytes_per_token_at_mid_ctx": int(info.kv_bytes_per_token_per_ctx * ctx_mid), "state_bytes_per_token": info.state_bytes_per_token,
             "cache_policy": f"inputs larger than L2: {info.weight_bytes_per_token / 1e6:.0f} MB of weights streamed every step vs 126 MB L2",
-            "cuda_graph": not args.no_graph, "prefill_tokens_per_s": prefill / prefill_s,
+            "cuda_graph": not args.no_graph, "fused_decode": bool(args.fused), "prefill_tokens_per_s": prefill / prefill_s,
             "whole_step_hbm_frac": bytes_per_token * (K / seconds) / 1e9 / peak,
             "gemv_launches_per_token": lin_launches // iters, "gemv_ms_per_token": 1000.0 * gemv_s_per_token,
         },
@@ -322,6 +331,7 @@ def main():
     ap.add_argument("--workload", default="qwen3.5-0.8b-int4", choices=sorted(WORKLOADS))
     ap.add_argument("--prefill", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--fused", action="store_true", help="fold norm / gated-act / sigmoid-gate launches into the consuming GEMV (experimental: slower in round 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -176,6 +176,25 @@ typedef struct uzu_matmul_args {
 UZU_API void uzu_matmul_encode(uzu_command_buffer* cmd, const uzu_matmul_args* args);
 UZU_API uzu_status uzu_matmul_validate(const uzu_matmul_args* args);   /* MatmulKernel::new + encode error paths */
 
+/* Fused decode linear (extension; m = 1): Matmul whose activation row is produced inside the GEMV, replacing a separate launch of
+ *   prologue 1: NormalizationKernel (RMS norm, optional residual add; the updated residual goes to `shortcut_out`, which must differ
+ *               from `norm_shortcut_in`; 0 = do not write, for a second linear sharing the same norm),
+ *   prologue 2: GatedActMulKernel (interleaved [value | gate] row of length 2k in `act_operand`),
+ *   prologue 3: SigmoidGateKernel (x = attn * sigmoid(gate)).
+ * Same arithmetic and rounding points as the standalone kernels. uzu_fused_linear_supported() tells whether the fast path applies;
+ * if not, the caller encodes the unfused sequence. `matmul.a` is ignored for prologue != 0. */
+typedef struct uzu_fused_linear_args {
+    uzu_matmul_args matmul;
+    uint32_t prologue;
+    uint64_t norm_input, norm_shortcut_in, norm_scales, shortcut_out;
+    float norm_epsilon, norm_scale_offset;
+    uint32_t norm_residual_add, norm_full_layer;
+    uint64_t act_operand; uint32_t act_type;
+    uint64_t sg_attn, sg_gate;
+} uzu_fused_linear_args;
+UZU_API int uzu_fused_linear_supported(uzu_context* ctx, const uzu_fused_linear_args* args);
+UZU_API void uzu_fused_linear_encode(uzu_command_buffer* cmd, const uzu_fused_linear_args* args);
+
 /* NormalizationKernel: backends/cpu/kernel/normalization/normalization.rs:7-49 */
 typedef struct uzu_normalization_args {
     uint64_t input;                /* optional(!in_place) */

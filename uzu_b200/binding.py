@@ -109,7 +109,12 @@ ModelInfo = _struct("uzu_model_info", [
     ("num_delta_net_layers", u32), ("weight_bytes_per_token", u64), ("kv_bytes_per_token_per_ctx", u64),
     ("state_bytes_per_token", u64)])
 
-ABI_STRUCTS = [RingParams, TrieNode, KvCopy, MatmulArgs, NormalizationArgs, QkvNormArgs, AttentionPrepareArgs, AttentionArgs,
+FusedLinearArgs = _struct("uzu_fused_linear_args", [
+    ("matmul", MatmulArgs), ("prologue", u32), ("norm_input", u64), ("norm_shortcut_in", u64), ("norm_scales", u64), ("shortcut_out", u64),
+    ("norm_epsilon", f32), ("norm_scale_offset", f32), ("norm_residual_add", u32), ("norm_full_layer", u32), ("act_operand", u64),
+    ("act_type", u32), ("sg_attn", u64), ("sg_gate", u64)])
+
+ABI_STRUCTS = [FusedLinearArgs, RingParams, TrieNode, KvCopy, MatmulArgs, NormalizationArgs, QkvNormArgs, AttentionPrepareArgs, AttentionArgs,
                AttentionTwoPass2Args, KvCacheUpdateArgs, GatedActMulArgs, QuantizedEmbeddingLookupArgs, UnifiedSamplingArgs,
                DeltaNetConvUpdateArgs, DeltaNetUpdateArgs, EngineOptions, SamplingMethod, ModelInfo]
 
@@ -131,7 +136,7 @@ uzu_tensor_add_bias_encode uzu_tensor_add_swap_encode uzu_unified_sampling_encod
 uzu_delta_net_update_encode uzu_engine_create uzu_engine_destroy uzu_engine_info uzu_engine_reset uzu_engine_context_length
 uzu_engine_snapshot uzu_engine_restore uzu_engine_prefill uzu_engine_next uzu_engine_flush uzu_engine_decode_device
 uzu_engine_forward uzu_engine_launch_count uzu_engine_decode_timed uzu_engine_step_host
-uzu_engine_time_linears""".split()
+uzu_engine_time_linears uzu_fused_linear_supported uzu_fused_linear_encode""".split()
 
 _lib = None
 
@@ -227,6 +232,8 @@ def load() -> C.CDLL:
         "uzu_engine_decode_timed": (C.c_int, [vp, u32, C.POINTER(C.c_double)]),
         "uzu_engine_step_host": (C.c_int, [vp, u32, C.POINTER(u32)]),
         "uzu_engine_time_linears": (C.c_int, [vp, u32, C.POINTER(C.c_double), C.POINTER(u64)]),
+        "uzu_fused_linear_supported": (C.c_int, [vp, C.POINTER(FusedLinearArgs)]),
+        "uzu_fused_linear_encode": (None, [vp, C.POINTER(FusedLinearArgs)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

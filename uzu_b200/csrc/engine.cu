@@ -370,6 +370,8 @@ struct uzu_engine {
     uint32_t context_length = 0, snapshot_context = 0;
     uint32_t max_context = 0;
     // scratch arena
+    Buf shortcut2;   // fused decode path: the residual ping-pongs between `shortcut` and `shortcut2`
+    bool fused_ok = false;
     Buf token_ids, hidden_a, hidden_b, shortcut, qkv, queries, attn_out, gate, fused_up, gated, mixer_out, in_proj, delta_out, normed_out,
         logits, sampled, seeds, tp_parts, tp_sums, tp_maxs;
     Buf host_ring;        // pinned u32[TOKEN_RING]
@@ -719,6 +721,7 @@ static void create_state_and_scratch(uzu_engine* e) {
     e->hidden_a = dev((size_t)MAX_ROWS * H * 2);
     e->hidden_b = dev((size_t)MAX_ROWS * H * 2);
     e->shortcut = dev((size_t)MAX_ROWS * H * 2);
+    e->shortcut2 = dev((size_t)H * 2);
     e->mixer_out = dev((size_t)MAX_ROWS * H * 2);
     e->normed_out = dev((size_t)e->logits_rows * H * 2);
     e->qkv = dev((size_t)MAX_ROWS * max_qkv * 2);
@@ -960,6 +963,167 @@ static void encode_decoder(uzu_engine* e, uzu_command_buffer* cmd, const PassCtx
         uzu_logit_transform_encode(cmd, e->logits.ptr(), rows * e->vocab, e->has_logit_scale ? e->logit_scale : 1.0f, e->logit_soft_cap, e->has_logit_soft_cap);
 }
 
+// ---- fused decode step (m = 1): norm / gated-act / sigmoid-gate launches folded into the consuming GEMV ---------------------
+static uzu_matmul_args linear_args(const Linear& l, uint64_t a, uint32_t m, uint64_t d) {
+    uzu_matmul_args ma{};
+    ma.a = a;
+    ma.b = l.w.values.ptr();
+    ma.b_scales = l.w.scales.ptr();
+    ma.b_zero_points = l.w.zero_points.ptr();
+    ma.b_biases = l.w.biases.ptr();
+    ma.d = d;
+    ma.b_prologue = l.w.prologue;
+    ma.b_mode = l.w.mode;
+    ma.b_group_size = l.w.group_size;
+    ma.b_transpose = 1;
+    ma.ab_scale = 1.0f;
+    ma.m = m; ma.n = l.out_dim; ma.k = l.in_dim;
+    ma.weights_dt = ma.input_dt = ma.output_dt = UZU_DT_BF16;
+    return ma;
+}
+
+static uzu_fused_linear_args fused_norm_args(const Linear& l, const Norm& n, uint64_t input, uint64_t sc_in, uint64_t sc_out, bool add, uint64_t d) {
+    uzu_fused_linear_args f{};
+    f.matmul = linear_args(l, 0, 1, d);
+    f.prologue = 1;
+    f.norm_input = input; f.norm_shortcut_in = add ? sc_in : 0; f.norm_scales = n.scales.ptr(); f.shortcut_out = sc_out;
+    f.norm_epsilon = n.cfg.epsilon; f.norm_scale_offset = n.cfg.scale_offset;
+    f.norm_residual_add = add; f.norm_full_layer = n.cfg.full_layer;
+    return f;
+}
+
+static bool fused_decode_supported(uzu_engine* e) {
+    for (auto& L : e->layers) {
+        if (L.pre_mixer.cfg.subtract_mean || L.pre_mlp.cfg.subtract_mean || !L.pre_mixer.cfg.has_scale || !L.pre_mlp.cfg.has_scale) return false;
+        std::vector<uzu_fused_linear_args> fs;
+        const uint64_t x = e->hidden_a.ptr(), s0 = e->shortcut.ptr(), s1 = e->shortcut2.ptr();
+        if (L.is_attention) {
+            if (L.attn.has_gate) {
+                fs.push_back(fused_norm_args(L.attn.gate, L.pre_mixer, x, s0, s1, true, e->gate.ptr()));
+                uzu_fused_linear_args g{};
+                g.matmul = linear_args(L.attn.out, 0, 1, e->mixer_out.ptr());
+                g.prologue = 3; g.sg_attn = e->attn_out.ptr(); g.sg_gate = e->gate.ptr();
+                fs.push_back(g);
+            }
+            fs.push_back(fused_norm_args(L.attn.qkv, L.pre_mixer, x, s0, s1, true, e->qkv.ptr()));
+        } else {
+            fs.push_back(fused_norm_args(L.dn.in_proj, L.pre_mixer, x, s0, s1, true, e->in_proj.ptr()));
+        }
+        fs.push_back(fused_norm_args(L.up, L.pre_mlp, e->mixer_out.ptr(), s0, s1, true, e->fused_up.ptr()));
+        uzu_fused_linear_args d{};
+        d.matmul = linear_args(L.down, 0, 1, e->hidden_a.ptr());
+        d.prologue = 2; d.act_operand = e->fused_up.ptr(); d.act_type = L.act;
+        fs.push_back(d);
+        for (auto& f : fs)
+            if (!uzu_fused_linear_supported(e->ctx, &f)) return false;
+    }
+    return true;
+}
+
+static void encode_decoder_fused(uzu_engine* e, uzu_command_buffer* cmd, const PassCtx& pc) {
+    const uint32_t H = e->model_dim;
+    // embedding lookup (embedding.rs:345-372)
+    if (e->in_emb.w.prologue == UZU_B_FULL_PRECISION) {
+        uzu_full_precision_embedding_lookup_encode(cmd, e->token_ids.ptr(), e->in_emb.w.values.ptr(), e->hidden_a.ptr(), 1, e->vocab, H, e->input_scale);
+    } else {
+        uzu_quantized_embedding_lookup_args la{};
+        la.token_ids = e->token_ids.ptr(); la.weights = e->in_emb.w.values.ptr(); la.scales = e->in_emb.w.scales.ptr();
+        la.zero_points = e->in_emb.w.zero_points.ptr(); la.biases = e->in_emb.w.biases.ptr(); la.output = e->hidden_a.ptr();
+        la.batch_size = 1; la.vocab_size = e->vocab; la.model_dim = H; la.input_scale = e->input_scale;
+        la.group_size = e->in_emb.w.group_size; la.quantization_mode = e->in_emb.w.mode;
+        la.quantization_method = e->in_emb.w.prologue == UZU_B_SCALE_BIAS_DEQUANT ? UZU_QMETHOD_SCALE_BIAS
+                                 : e->in_emb.w.prologue == UZU_B_SCALE_ZERO_POINT_DEQUANT ? UZU_QMETHOD_SCALE_ZERO_POINT : UZU_QMETHOD_SCALE_SYMMETRIC;
+        uzu_quantized_embedding_lookup_encode(cmd, &la);
+    }
+    uint64_t S[2] = {e->shortcut.ptr(), e->shortcut2.ptr()};
+    int cur = 0;
+    const uint64_t dyn = e->decode_state.ptr();
+    for (size_t i = 0; i < e->layers.size(); ++i) {
+        Layer& L = e->layers[i];
+        LayerState& St = e->state[i];
+        const bool add = i > 0;   // layer 0: Copy mode (transformer_layer.rs:95-109)
+        if (L.is_attention) {
+            const AttentionLayer& A = L.attn;
+            const uint32_t D = A.head_dim, Hq = A.num_heads, Hkv = A.num_groups;
+            bool wrote = false;
+            if (A.has_gate) {
+                auto f = fused_norm_args(A.gate, L.pre_mixer, e->hidden_a.ptr(), S[cur], S[cur ^ 1], add, e->gate.ptr());
+                uzu_fused_linear_encode(cmd, &f);
+                wrote = true;
+            }
+            auto fq = fused_norm_args(A.qkv, L.pre_mixer, e->hidden_a.ptr(), S[cur], wrote ? 0 : S[cur ^ 1], add, e->qkv.ptr());
+            uzu_fused_linear_encode(cmd, &fq);
+            const uint32_t total_heads = Hq + 2 * Hkv;
+            auto qkn = [&](const Norm& n, uint32_t off, uint32_t cnt) {
+                if (!n.present || cnt == 0) return;
+                uzu_qkv_norm_args qa{};
+                qa.scales = n.scales.ptr(); qa.qkv_output = e->qkv.ptr();
+                qa.batch_size = 1; qa.total_heads = total_heads; qa.head_dim = D;
+                qa.epsilon = n.cfg.epsilon; qa.scale_offset = n.cfg.scale_offset;
+                qa.head_offset = off; qa.head_count = cnt; qa.full_layer = n.cfg.full_layer;
+                qa.in_place = 1; qa.has_scales = n.cfg.has_scale;
+                uzu_qkv_norm_encode(cmd, &qa);
+            };
+            qkn(A.qnorm, 0, Hq);
+            qkn(A.knorm, Hq, Hkv);
+            uzu_attention_prepare_args pa{};
+            pa.qkv = e->qkv.ptr(); pa.queries = e->queries.ptr(); pa.keys = St.keys; pa.values = St.values;
+            pa.num_q_heads = Hq; pa.num_kv_heads = Hkv; pa.head_dim = D; pa.kv_token_offset = St.length; pa.batch_dim = 1; pa.has_kv = 1;
+            if (A.rope_index >= 0) {
+                const RopeCfg& rc = e->ropes[A.rope_index];
+                pa.has_rope = 1; pa.rope_dim = rc.head_dim;
+                pa.cosines = e->rope_cos[A.rope_index].ptr(); pa.sines = e->rope_sin[A.rope_index].ptr();
+            }
+            pa.dynamic_position = dyn;
+            uzu_attention_prepare_encode(cmd, &pa);
+            uzu_attention_args aa{};
+            aa.queries = e->queries.ptr(); aa.keys = St.keys; aa.values = St.values; aa.out = e->attn_out.ptr();
+            aa.gqa_factor = Hq / Hkv; aa.sequence_length = St.length + 1;
+            aa.k_head_stride = D; aa.k_seq_stride = Hkv * D; aa.v_head_stride = D; aa.v_seq_stride = Hkv * D;
+            aa.scale = A.has_scale ? A.scale : 1.0f / sqrtf((float)D);
+            aa.num_heads = Hq; aa.suffix_length = 1; aa.head_dim = D; aa.is_causal = A.is_causal; aa.dynamic_position = dyn;
+            uzu_attention_single_pass_encode(cmd, &aa);
+            if (A.has_gate) {
+                uzu_fused_linear_args g{};
+                g.matmul = linear_args(A.out, 0, 1, e->mixer_out.ptr());
+                g.prologue = 3; g.sg_attn = e->attn_out.ptr(); g.sg_gate = e->gate.ptr();
+                uzu_fused_linear_encode(cmd, &g);
+            } else {
+                encode_linear(cmd, A.out, e->attn_out.ptr(), 1, e->mixer_out.ptr());
+            }
+        } else {
+            const DeltaNetLayer& Dn = L.dn;
+            auto f = fused_norm_args(Dn.in_proj, L.pre_mixer, e->hidden_a.ptr(), S[cur], S[cur ^ 1], add, e->in_proj.ptr());
+            uzu_fused_linear_encode(cmd, &f);
+            uzu_delta_net_conv_update_args ca{};
+            ca.conv_weight = Dn.conv_weight.ptr(); ca.bias = Dn.conv_bias.ptr(); ca.in_out = e->in_proj.ptr(); ca.state = St.conv_state.ptr();
+            ca.kernel_size = Dn.kernel_size; ca.conv_dim = Dn.conv_dim; ca.state_stride = Dn.kernel_size - 1; ca.has_bias = Dn.conv_has_bias;
+            uzu_delta_net_conv_update_encode(cmd, &ca);
+            uzu_delta_net_update_args ua{};
+            ua.in_proj = e->in_proj.ptr(); ua.a_log = Dn.a_log.ptr(); ua.dt_bias = Dn.dt_bias.ptr(); ua.norm_weight = Dn.norm_weight.ptr();
+            ua.state = St.ssm_state.ptr(); ua.out = e->delta_out.ptr();
+            ua.num_v_heads = Dn.num_heads; ua.num_k_heads = Dn.num_groups; ua.head_v_dim = Dn.value_head_dim; ua.key_dim = Dn.key_dim;
+            ua.value_dim = Dn.value_dim; ua.norm_epsilon = Dn.norm_epsilon; ua.head_k_dim = Dn.head_dim;
+            uzu_delta_net_update_encode(cmd, &ua);
+            encode_linear(cmd, Dn.out_proj, e->delta_out.ptr(), 1, e->mixer_out.ptr());
+        }
+        cur ^= 1;
+        auto fu = fused_norm_args(L.up, L.pre_mlp, e->mixer_out.ptr(), S[cur], S[cur ^ 1], true, e->fused_up.ptr());
+        uzu_fused_linear_encode(cmd, &fu);
+        cur ^= 1;
+        uzu_fused_linear_args fd{};
+        fd.matmul = linear_args(L.down, 0, 1, e->hidden_a.ptr());
+        fd.prologue = 2; fd.act_operand = e->fused_up.ptr(); fd.act_type = L.act;
+        uzu_fused_linear_encode(cmd, &fd);
+    }
+    // output norm with the residual add in place on the current residual buffer (transformer.rs:317-323), readout, logit transform
+    encode_norm(cmd, e->out_norm, e->hidden_a.ptr(), e->normed_out.ptr(), S[cur], ShortcutAdd, 1);
+    encode_linear(cmd, e->out_emb, e->normed_out.ptr(), 1, e->logits.ptr());
+    if (e->has_logit_scale || e->has_logit_soft_cap)
+        uzu_logit_transform_encode(cmd, e->logits.ptr(), e->vocab, e->has_logit_scale ? e->logit_scale : 1.0f, e->logit_soft_cap, e->has_logit_soft_cap);
+    (void)pc;
+}
+
 static void encode_sampling(uzu_engine* e, uzu_command_buffer* cmd, uint32_t rows) {
     const uzu_sampling_method& s = e->sampling;
     uzu_unified_sampling_args sa{};
@@ -1060,7 +1224,8 @@ static void capture_decode_graph(uzu_engine* e) {
     PassCtx pc;
     pc.m = 1;
     pc.dynamic = true;
-    encode_decoder(e, g.c, pc, 0, 1);
+    if (e->fused_ok) encode_decoder_fused(e, g.c, pc);
+    else encode_decoder(e, g.c, pc, 0, 1);
     encode_sampling(e, g.c, 1);
     decode_step_end_kernel<<<1, 1, 0, s>>>((DecodeState*)e->decode_state.ptr(), (const uint32_t*)e->sampled.ptr(), (uint32_t*)e->token_ids.ptr(),
                                            (volatile uint32_t*)e->host_ring.ptr(), nullptr, 0);
@@ -1103,7 +1268,8 @@ static void issue_decode_step(uzu_engine* e, uint64_t dev_out, uint32_t dev_out_
         PassCtx pc;
         pc.m = 1;
         pc.dynamic = true;
-        encode_decoder(e, g.c, pc, 0, 1);
+        if (e->fused_ok) encode_decoder_fused(e, g.c, pc);
+        else encode_decoder(e, g.c, pc, 0, 1);
         encode_sampling(e, g.c, 1);
         decode_step_end_kernel<<<1, 1, 0, s>>>((DecodeState*)e->decode_state.ptr(), (const uint32_t*)e->sampled.ptr(), (uint32_t*)e->token_ids.ptr(),
                                                (volatile uint32_t*)e->host_ring.ptr(), (uint32_t*)dev_out, dev_out_base_step);
@@ -1150,6 +1316,7 @@ uzu_status uzu_engine_create(uzu_context* ctx, const char* model_dir, const uzu_
         load_model(e, model_dir);
         create_state_and_scratch(e);
         reset_state(e);
+        e->fused_ok = e->opts.fused_decode && getenv("UZU_NO_FUSED") == nullptr && fused_decode_supported(e);
         check(uzu_context_synchronize(ctx));
     } catch (const std::exception& ex) {
         std::string msg = ex.what();

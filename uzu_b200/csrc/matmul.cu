@@ -50,6 +50,15 @@ struct QmvParams {
     uint32_t group_size;       // in k elements
     uint32_t chunks_total, chunks_per_slice, kslices;
     uint32_t warps_per_tile;   // decode kernel: warps of a CTA sharing one 16-row tile (1, 2 or 4)
+    // fused activation prologue (decode kernel only): the activation row is produced inside the GEMV instead of by a
+    // separate Normalization / GatedActMul / SigmoidGate launch. 0 = plain (x), 1 = RMS norm, 2 = gated act, 3 = sigmoid gate
+    uint32_t prologue;
+    const __nv_bfloat16* pro_a;      // norm: input row; gated: fused up row [2F]; sigmoid: attention output row
+    const __nv_bfloat16* pro_b;      // norm: shortcut in (or null); sigmoid: gate row
+    __nv_bfloat16* pro_shortcut_out; // norm: updated residual, written by CTA 0 only (null = do not write)
+    const float* pro_scales;         // norm scales f32 [k]
+    float pro_eps, pro_scale_offset;
+    uint32_t pro_residual_add, pro_full_layer, pro_act;
     uint32_t method;           // uzu_quantization_method
     uint32_t bits;
     uint32_t xor_mask;         // signed_codes
@@ -1117,6 +1126,8 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
     // per-warp cp.async ring: QA_STAGES x ([8 vectors][32 lanes] uint4 weights + [4 words][32 lanes] u32 scale / zero-point words)
     uint8_t* ring_base = reinterpret_cast<uint8_t*>(red + 2 * QS_WARPS * 16) + (size_t)warp * QA_STAGES * QA_STAGE_BYTES;
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring_base);
+    // fused prologue: the produced activation row (bf16 [k]) lives after the rings
+    __nv_bfloat16* xrow = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(red + 2 * QS_WARPS * 16) + (size_t)QS_WARPS * QA_STAGES * QA_STAGE_BYTES);
     uint32_t magic;
     asm volatile("mov.b32 %0, 0x43004300;" : "=r"(magic));
 
@@ -1229,6 +1240,127 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
     pdl_wait();
     if (tid < 4) xs[row_items + tid] = make_uint4(0, 0, 0, 0);
 
+    const __nv_bfloat16* xsrc = p.x;
+    if (p.prologue != 0) {
+        // ---- fused prologue: every CTA recomputes the (tiny) activation row; same arithmetic and rounding points as the
+        // standalone kernels (normalization.rs:50-125, gated_act_mul/mod.rs:5-12, sigmoid_gate.rs:7-22) -------------------------
+        const uint32_t K = p.k;
+        constexpr int PB = 4;   // items (8 elements each) per thread per batch: all global loads of a batch are issued before use
+        const uint32_t stride = blockDim.x * 8u;
+        if (p.prologue == 1) {
+            float ssq = 0.0f;
+            for (uint32_t base = tid * 8u; base < K; base += stride * PB) {
+                uint4 va[PB], vb[PB];
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    const uint32_t i = base + u * stride;
+                    va[u] = make_uint4(0, 0, 0, 0); vb[u] = make_uint4(0, 0, 0, 0);
+                    if (i < K) {
+                        va[u] = *reinterpret_cast<const uint4*>(p.pro_a + i);
+                        if (p.pro_residual_add) vb[u] = *reinterpret_cast<const uint4*>(p.pro_b + i);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    const uint32_t i = base + u * stride;
+                    if (i >= K) break;
+                    __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&va[u]);
+                    if (p.pro_residual_add) {
+                        const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&vb[u]);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            a2[e] = __floats2bfloat162_rn(__fadd_rn(__low2float(a2[e]), __low2float(b2[e])), __fadd_rn(__high2float(a2[e]), __high2float(b2[e])));
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float lo = __low2float(a2[e]), hi = __high2float(a2[e]);
+                        ssq = __fadd_rn(ssq, __fmul_rn(lo, lo));
+                        ssq = __fadd_rn(ssq, __fmul_rn(hi, hi));
+                    }
+                    *reinterpret_cast<uint4*>(xrow + i) = va[u];
+                    if (p.pro_shortcut_out && blockIdx.x == 0) *reinterpret_cast<uint4*>(p.pro_shortcut_out + i) = va[u];
+                }
+            }
+            ssq = warp_sum(ssq);
+            if (lane == 0) red[warp] = ssq;
+            __syncthreads();
+            float tot = 0.0f;
+#pragma unroll
+            for (int w_ = 0; w_ < QS_WARPS; ++w_) tot = __fadd_rn(tot, red[w_]);
+            const float rms_inv = __frcp_rn(__fsqrt_rn(__fadd_rn(__fdiv_rn(tot, (float)K), p.pro_eps)));
+            for (uint32_t base = tid * 8u; base < K; base += stride * PB) {
+                float4 s0[PB], s1[PB];
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    const uint32_t i = base + u * stride;
+                    if (i < K) {
+                        s0[u] = __ldg(reinterpret_cast<const float4*>(p.pro_scales + i));
+                        s1[u] = __ldg(reinterpret_cast<const float4*>(p.pro_scales + i + 4));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    const uint32_t i = base + u * stride;
+                    if (i >= K) break;
+                    uint4 va = *reinterpret_cast<const uint4*>(xrow + i);
+                    __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&va);
+                    const float sc[8] = {s0[u].x, s0[u].y, s0[u].z, s0[u].w, s1[u].x, s1[u].y, s1[u].z, s1[u].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float v[2] = {__low2float(a2[e]), __high2float(a2[e])};
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const float normalized = __fmul_rn(v[h], rms_inv);
+                            const float so = __fadd_rn(sc[2 * e + h], p.pro_scale_offset);
+                            if (p.pro_full_layer) v[h] = __fmul_rn(normalized, so);
+                            else v[h] = __fmul_rn(__bfloat162float(__float2bfloat16_rn(normalized)), __bfloat162float(__float2bfloat16_rn(so)));
+                        }
+                        a2[e] = __floats2bfloat162_rn(v[0], v[1]);
+                    }
+                    *reinterpret_cast<uint4*>(xrow + i) = va;
+                }
+            }
+        } else {
+            // prologue 2: x = value * act(gate) from [value | gate]; prologue 3: x = attn * sigmoid(gate)
+            const __nv_bfloat16* pv = p.pro_a;
+            const __nv_bfloat16* pg = p.prologue == 2 ? p.pro_a + K : p.pro_b;
+            for (uint32_t base = tid * 8u; base < K; base += stride * PB) {
+                uint4 vv[PB], vg[PB];
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    const uint32_t i = base + u * stride;
+                    vv[u] = make_uint4(0, 0, 0, 0); vg[u] = make_uint4(0, 0, 0, 0);
+                    if (i < K) {
+                        vv[u] = *reinterpret_cast<const uint4*>(pv + i);
+                        vg[u] = *reinterpret_cast<const uint4*>(pg + i);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    const uint32_t i = base + u * stride;
+                    if (i >= K) break;
+                    __nv_bfloat162* v2 = reinterpret_cast<__nv_bfloat162*>(&vv[u]);
+                    const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&vg[u]);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float m0, m1;
+                        if (p.prologue == 2) {
+                            m0 = __bfloat162float(__float2bfloat16_rn(act_f32(p.pro_act, __low2float(g2[e]))));
+                            m1 = __bfloat162float(__float2bfloat16_rn(act_f32(p.pro_act, __high2float(g2[e]))));
+                        } else {
+                            m0 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-__low2float(g2[e]))));
+                            m1 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-__high2float(g2[e]))));
+                        }
+                        v2[e] = __floats2bfloat162_rn(__fmul_rn(__low2float(v2[e]), m0), __fmul_rn(__high2float(v2[e]), m1));
+                    }
+                    *reinterpret_cast<uint4*>(xrow + i) = vv[u];
+                }
+            }
+        }
+        __syncthreads();
+        xsrc = xrow;
+    }
+
     {   // one-time staging of the activation row: all global loads of a batch are issued before any is consumed
         constexpr uint32_t IPG = NPG / 8;
         constexpr int BATCH = 4;
@@ -1240,9 +1372,9 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
                 const uint32_t pos = it * 8u;
                 v[u] = make_uint4(0, 0, 0, 0);
                 if (it < nc_all * 16u && pos < p.np) {
-                    if (p.bits == 4) v[u] = *reinterpret_cast<const uint4*>(p.x + pos);
+                    if (p.bits == 4) v[u] = *reinterpret_cast<const uint4*>(xsrc + pos);
                     else {
-                        const uint2 h = *reinterpret_cast<const uint2*>(p.x + pos / 2);
+                        const uint2 h = *reinterpret_cast<const uint2*>(xsrc + pos / 2);
                         v[u].x = h.x; v[u].y = h.y;
                     }
                 }
@@ -1638,7 +1770,8 @@ static void launch_generic(uzu_command_buffer* cmd, const uzu_matmul_args& a) {
     after_launch(cmd, "matmul generic_kernel");
 }
 
-static void encode_matmul(uzu_command_buffer* cmd, const uzu_matmul_args& a) {
+// returns true when the fused fast path (decode kernel) handled the call; with `fused` set and `dry_run`, only reports applicability
+static bool encode_matmul(uzu_command_buffer* cmd, uzu_context* ctx_for_query, const uzu_matmul_args& a, const uzu_fused_linear_args* fused = nullptr, bool dry_run = false) {
     const bool quant = a.b_prologue != UZU_B_FULL_PRECISION;
     const uint32_t bits = a.b_mode == UZU_QMODE_U4 ? 4 : 8;
     const uint32_t np = quant ? a.k * bits / 4 : 0;          // nibbles per row
@@ -1647,10 +1780,12 @@ static void encode_matmul(uzu_command_buffer* cmd, const uzu_matmul_args& a) {
                       (np % 32 == 0) && (npg == 32 || npg == 64 || npg == 128 || npg == 256) &&
                       (a.k % a.b_group_size == 0 || true) && ((a.a & 15) == 0) && ((a.b & 15) == 0) && ((a.k * 2) % 16 == 0);
     if (!fast) {
+        if (fused) return false;
         launch_generic(cmd, a);
-        return;
+        return true;
     }
-    uzu_context* ctx = cmd->ctx;
+    uzu_context* ctx = cmd ? cmd->ctx : ctx_for_query;
+    if (fused && (a.m != 1 || (npg != 64 && npg != 128) || a.output_dt != UZU_DT_BF16 && a.output_dt != UZU_DT_F32)) return false;
     const int cpm = npg >= 128 ? 1 : 128 / npg;
     const int mpm = 8 / cpm;
     const uint32_t max_rows = 4 * mpm;  // MT = 4
@@ -1740,6 +1875,33 @@ static void encode_matmul(uzu_command_buffer* cmd, const uzu_matmul_args& a) {
                 const size_t dsmem = stream_smem + 2 * QS_WARPS * 16 * 4 + 64;
                 static const bool use_regs = getenv("UZU_QMV_REGS") != nullptr;
                 const size_t asmem = dsmem + (size_t)QS_WARPS * QA_STAGES * QA_STAGE_BYTES;
+                const size_t fsmem = asmem + (fused ? (size_t)a.k * 2 + 64 : 0);
+                if (fused) {
+                    if (fsmem > 200u * 1024u || (a.k % 8) != 0) return false;
+                    if (dry_run) return true;
+                    p.prologue = fused->prologue;
+                    if (fused->prologue == 1) {
+                        p.pro_a = (const __nv_bfloat16*)fused->norm_input;
+                        p.pro_b = (const __nv_bfloat16*)fused->norm_shortcut_in;
+                        p.pro_shortcut_out = (__nv_bfloat16*)fused->shortcut_out;
+                        p.pro_scales = (const float*)fused->norm_scales;
+                        p.pro_eps = fused->norm_epsilon; p.pro_scale_offset = fused->norm_scale_offset;
+                        p.pro_residual_add = fused->norm_residual_add; p.pro_full_layer = fused->norm_full_layer;
+                    } else if (fused->prologue == 2) {
+                        p.pro_a = (const __nv_bfloat16*)fused->act_operand;
+                        p.pro_act = fused->act_type;
+                    } else {
+                        p.pro_a = (const __nv_bfloat16*)fused->sg_attn;
+                        p.pro_b = (const __nv_bfloat16*)fused->sg_gate;
+                    }
+                    const uint32_t per_sm = std::max(1u, std::min(4u, (uint32_t)((220u * 1024u) / (fsmem + 1024u))));
+                    const uint32_t aitems = std::max(1u, tgroups * dks), amax = per_sm * (uint32_t)ctx->sm_count;
+                    const uint32_t rounds = (aitems + amax - 1) / amax;
+                    const uint32_t agrid = (aitems + rounds - 1) / rounds;
+                    if (npg == 64) launch_qmv_decode_async<64>(cmd, p, agrid, fsmem);
+                    else launch_qmv_decode_async<128>(cmd, p, agrid, fsmem);
+                    return true;
+                }
                 if (!use_regs && asmem <= 200u * 1024u) {
                     const uint32_t per_sm = std::max(1u, std::min(4u, (uint32_t)((220u * 1024u) / (asmem + 1024u))));
                     const uint32_t aitems = std::max(1u, tgroups * dks), amax = per_sm * (uint32_t)ctx->sm_count;
@@ -1754,6 +1916,7 @@ static void encode_matmul(uzu_command_buffer* cmd, const uzu_matmul_args& a) {
                 else launch_qmv_decode<128>(cmd, p, dgrid, dsmem);
                 continue;
             }
+            if (fused) return false;
             switch (npg) {
                 case 32: launch_qmv_stream_mt<32>(cmd, p, use_grid, stream_smem, mt); break;
                 case 64: launch_qmv_stream_mt<64>(cmd, p, use_grid, stream_smem, mt); break;
@@ -1762,6 +1925,7 @@ static void encode_matmul(uzu_command_buffer* cmd, const uzu_matmul_args& a) {
             }
             continue;
         }
+        if (fused) return false;
         // k slicing: enough CTAs to fill the machine, >= 1 chunk per warp, activations must fit shared memory
         uint32_t ks = 1;
         const uint32_t target = 4u * (uint32_t)ctx->sm_count;
@@ -1820,6 +1984,7 @@ static void encode_matmul(uzu_command_buffer* cmd, const uzu_matmul_args& a) {
             default: launch_qmv_mt<256>(cmd, p, tiles, mt); break;
         }
     }
+    return true;
 }
 
 }  // namespace uzu
@@ -1839,7 +2004,36 @@ void uzu_matmul_encode(uzu_command_buffer* cmd, const uzu_matmul_args* args) {
         cmd->record_error(UZU_ERROR_INVALID_ARGUMENT, std::string("matmul: ") + err);
         return;
     }
-    uzu::encode_matmul(cmd, *args);
+    uzu::encode_matmul(cmd, cmd->ctx, *args);
+}
+
+int uzu_fused_linear_supported(uzu_context* ctx, const uzu_fused_linear_args* args) {
+    if (!ctx || !args || uzu::validate(&args->matmul)) {
+        // validate() wants matmul.a non-null; the fused path ignores it, so tolerate a == 0 here
+        if (!ctx || !args) return 0;
+        uzu_matmul_args m = args->matmul;
+        if (!m.a) m.a = m.d;
+        if (uzu::validate(&m)) return 0;
+    }
+    if (args->prologue < 1 || args->prologue > 3) return 0;
+    if (args->prologue == 1 && (!args->norm_input || !args->norm_scales || (args->norm_residual_add && !args->norm_shortcut_in) ||
+                                (args->shortcut_out && args->shortcut_out == args->norm_shortcut_in))) return 0;
+    if (args->prologue == 2 && !args->act_operand) return 0;
+    if (args->prologue == 3 && (!args->sg_attn || !args->sg_gate)) return 0;
+    uzu_matmul_args m = args->matmul;
+    m.a = 0;
+    return uzu::encode_matmul(nullptr, ctx, m, args, true) ? 1 : 0;
+}
+
+void uzu_fused_linear_encode(uzu_command_buffer* cmd, const uzu_fused_linear_args* args) {
+    if (!uzu::encodable(cmd, "fused_linear")) return;
+    if (!uzu_fused_linear_supported(cmd->ctx, args)) {
+        cmd->record_error(UZU_ERROR_UNSUPPORTED, "fused_linear: shape / format not covered by the fused decode kernel (encode the unfused sequence)");
+        return;
+    }
+    uzu_matmul_args m = args->matmul;
+    m.a = 0;
+    uzu::encode_matmul(cmd, cmd->ctx, m, args, false);
 }
 
 }  // extern "C"

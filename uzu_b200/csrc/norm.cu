@@ -9,10 +9,99 @@
 
 namespace uzu {
 
+// One CTA per row. Fast path (element_count % 8 == 0, <= 8 vectors per thread): every thread issues all its 128-bit loads first,
+// keeps the (residual-added) bf16 values in registers across the block reduction, and writes shortcut / output once. The
+// generic path below handles every other shape. Arithmetic and rounding points are identical in both.
+template <int MAXV>
+__device__ __forceinline__ void normalization_fast(const uzu_normalization_args& a, float* red) {
+    const uint32_t row = blockIdx.x, n = a.element_count;
+    const size_t off = (size_t)row * n;
+    const __nv_bfloat16* input = (a.in_place ? reinterpret_cast<const __nv_bfloat16*>(a.output) : reinterpret_cast<const __nv_bfloat16*>(a.input)) + off;
+    __nv_bfloat16* shortcut = reinterpret_cast<__nv_bfloat16*>(a.shortcut) + off;
+    __nv_bfloat16* output = reinterpret_cast<__nv_bfloat16*>(a.output) + off;
+    const float* scales = reinterpret_cast<const float*>(a.scales);
+    const float* biases = reinterpret_cast<const float*>(a.biases);
+    const uint32_t stride = blockDim.x * 8u;
+    uint4 v[MAXV], sv[MAXV];
+#pragma unroll
+    for (int u = 0; u < MAXV; ++u) {
+        const uint32_t i = threadIdx.x * 8u + u * stride;
+        v[u] = make_uint4(0, 0, 0, 0); sv[u] = make_uint4(0, 0, 0, 0);
+        if (i < n) {
+            v[u] = *reinterpret_cast<const uint4*>(input + i);
+            if (a.copy_to_shortcut && a.residual_add) sv[u] = *reinterpret_cast<const uint4*>(shortcut + i);
+        }
+    }
+    float sum = 0.0f, sum_sq = 0.0f;
+#pragma unroll
+    for (int u = 0; u < MAXV; ++u) {
+        const uint32_t i = threadIdx.x * 8u + u * stride;
+        if (i >= n) break;
+        __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(&v[u]);
+        const __nv_bfloat16* se = reinterpret_cast<const __nv_bfloat16*>(&sv[u]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            __nv_bfloat16 val = e[j];
+            if (a.copy_to_shortcut && a.residual_add) {
+                val = f2bf(bf2f(val) + bf2f(se[j]));
+                if (a.scale_residual_sum) val = f2bf(bf2f(val) * a.post_layer_scalar);
+            }
+            e[j] = val;
+            const float av = bf2f(val);
+            if (a.subtract_mean) sum += av;
+            sum_sq += av * av;
+        }
+        if (a.copy_to_shortcut) *reinterpret_cast<uint4*>(shortcut + i) = v[u];
+    }
+    const float nf = (float)n;
+    float mean = 0.0f;
+    if (a.subtract_mean) mean = block_sum(sum, red) / nf;
+    sum_sq = block_sum(sum_sq, red);
+    const float variance = sum_sq / nf - mean * mean;
+    const float rms_inv = 1.0f / sqrtf(variance + a.epsilon);
+#pragma unroll
+    for (int u = 0; u < MAXV; ++u) {
+        const uint32_t i = threadIdx.x * 8u + u * stride;
+        if (i >= n) break;
+        float sc[8], bs[8];
+        if (a.has_scales) {
+            const float4 s0 = *reinterpret_cast<const float4*>(scales + i), s1 = *reinterpret_cast<const float4*>(scales + i + 4);
+            sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+        }
+        if (a.has_biases) {
+            const float4 b0 = *reinterpret_cast<const float4*>(biases + i), b1 = *reinterpret_cast<const float4*>(biases + i + 4);
+            bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w; bs[4] = b1.x; bs[5] = b1.y; bs[6] = b1.z; bs[7] = b1.w;
+        }
+        __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(&v[u]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float normalized = (bf2f(e[j]) - mean) * rms_inv;
+            __nv_bfloat16 result;
+            if (a.has_scales) {
+                if (a.full_layer) result = f2bf(normalized * (sc[j] + a.scale_offset));
+                else result = f2bf(bf2f(f2bf(normalized)) * bf2f(f2bf(sc[j] + a.scale_offset)));
+            } else {
+                result = f2bf(normalized);
+            }
+            if (a.has_biases) result = f2bf(bf2f(result) + bs[j]);
+            if (a.scale_output) result = f2bf(bf2f(result) * bf2f(f2bf(a.post_layer_scalar)));
+            e[j] = result;
+        }
+        *reinterpret_cast<uint4*>(output + i) = v[u];
+    }
+}
+
 __global__ void __launch_bounds__(1024) normalization_kernel(const uzu_normalization_args a) {
     __shared__ float red[32];
     pdl_launch_dependents();
     pdl_wait();
+    {
+        const bool aligned = (a.element_count % 8 == 0) && (((a.in_place ? a.output : a.input) | a.output | a.shortcut | a.scales | a.biases) % 16 == 0);
+        if (aligned && a.element_count <= blockDim.x * 8u * 4u) {
+            normalization_fast<4>(a, red);
+            return;
+        }
+    }
     const uint32_t row = blockIdx.x;
     const uint32_t n = a.element_count;
     const size_t off = (size_t)row * n;
@@ -108,7 +197,9 @@ void uzu_normalization_encode(uzu_command_buffer* cmd, const uzu_normalization_a
         return;
     }
     if (a->batch_size == 0 || a->element_count == 0) return;
-    uint32_t threads = a->element_count >= 4096 ? 1024 : (a->element_count >= 1024 ? 512 : 256);
+    // 128-bit loads: 8 elements per thread per vector, up to 4 vectors per thread on the fast path
+    uint32_t threads = a->element_count >= 8192 ? 512 : (a->element_count >= 2048 ? 256 : 128);
+    if (a->element_count % 8 != 0) threads = a->element_count >= 4096 ? 1024 : (a->element_count >= 1024 ? 512 : 256);
     uzu::launch(cmd, "normalization_kernel", uzu::normalization_kernel, dim3(a->batch_size), dim3(threads), 0, *a);
 }
 

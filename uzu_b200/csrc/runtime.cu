@@ -88,7 +88,7 @@ const char* uzu_version(void) { return "uzu_b200 0.1 (sm_100a)"; }
 
 size_t uzu_abi_struct_size(const char* name) {
 #define UZU_SZ(T) if (!strcmp(name, #T)) return sizeof(T);
-    UZU_SZ(uzu_matmul_args) UZU_SZ(uzu_normalization_args) UZU_SZ(uzu_qkv_norm_args) UZU_SZ(uzu_attention_prepare_args)
+    UZU_SZ(uzu_fused_linear_args) UZU_SZ(uzu_matmul_args) UZU_SZ(uzu_normalization_args) UZU_SZ(uzu_qkv_norm_args) UZU_SZ(uzu_attention_prepare_args)
     UZU_SZ(uzu_attention_args) UZU_SZ(uzu_attention_two_pass2_args) UZU_SZ(uzu_kv_cache_update_args) UZU_SZ(uzu_gated_act_mul_args)
     UZU_SZ(uzu_quantized_embedding_lookup_args) UZU_SZ(uzu_unified_sampling_args) UZU_SZ(uzu_delta_net_conv_update_args)
     UZU_SZ(uzu_delta_net_update_args) UZU_SZ(uzu_engine_options) UZU_SZ(uzu_sampling_method) UZU_SZ(uzu_model_info)

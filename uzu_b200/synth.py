@@ -294,6 +294,17 @@ def tiny(kind="llama", quant: QuantSpec | None = None, layers=2) -> ModelSpec:
                          num_heads=4, num_groups=2, head_dim=64, rope=rope, qk_norm=True, qk_norm_scale_offset=1.0,
                          attn_gate=True, norm_eps=1e-6, norm_scale_offset=1.0, tied_embeddings=True, quant=quant,
                          dn_num_heads=4, dn_num_groups=2, dn_head_dim=128, dn_value_head_dim=128, dn_kernel_size=4)
+    if kind == "llama-512":        # dims that the fused decode kernels cover (k multiple of 512)
+        rope = dict(LLAMA3_ROPE, head_dim=64)
+        return ModelSpec(name="tiny-llama-512", model_dim=512, hidden_dim=1024, vocab_size=2048, layer_kinds=["attn"] * layers,
+                         num_heads=8, num_groups=2, head_dim=64, rope=rope, quant=quant)
+    if kind == "qwen-hybrid-512":
+        rope = {"type": "UnscaledRoPEConfig", "base": 1e6, "max_sequence_length": 4096, "head_dim": 32}
+        kinds = [("attn" if (i % 2 == 1) else "delta") for i in range(layers)]
+        return ModelSpec(name="tiny-qwen-hybrid-512", model_dim=512, hidden_dim=1024, vocab_size=2048, layer_kinds=kinds,
+                         num_heads=8, num_groups=2, head_dim=64, rope=rope, qk_norm=True, qk_norm_scale_offset=1.0, attn_gate=True,
+                         norm_eps=1e-6, norm_scale_offset=1.0, tied_embeddings=True, quant=quant, dn_num_heads=4, dn_num_groups=4,
+                         dn_head_dim=128, dn_value_head_dim=128, dn_kernel_size=4)
     raise ValueError(kind)
 
 
