@@ -26,20 +26,40 @@ __global__ void __launch_bounds__(256) delta_net_conv_update_kernel(const uzu_de
     st[taps - 1] = x;
 }
 
-// one CTA per v-head; HEAD_K_DIM = 128 (the only variant the reference instantiates)
+// A cluster of DN_CLUSTER CTAs per v-head; HEAD_K_DIM = 128 (the only variant the reference instantiates). Each CTA owns
+// head_v_dim / DN_CLUSTER state rows (one warp per row, two rows in flight per warp); the RMS statistic of the head's
+// output is exchanged through distributed shared memory and summed in rank order by every CTA (deterministic).
 constexpr int DN_WARPS = 8;
-__global__ void __launch_bounds__(DN_WARPS * 32) delta_net_update_kernel(const uzu_delta_net_update_args a) {
+constexpr int DN_CLUSTER = 8;
+__global__ void __cluster_dims__(DN_CLUSTER, 1, 1) __launch_bounds__(DN_WARPS * 32) delta_net_update_kernel(const uzu_delta_net_update_args a) {
     constexpr int DK = 128;
     __shared__ float sq[DK], sk[DK];
     __shared__ float so[256];
     __shared__ float red[32];
+    __shared__ float ss_parts[DN_CLUSTER];
     pdl_launch_dependents();
-    pdl_wait();
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");        // "this CTA is running": awaited before any DSMEM store
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t hv = blockIdx.x;
+    const uint32_t hv = blockIdx.x / DN_CLUSTER;
+    uint32_t crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     const uint32_t hk = hv / (a.num_v_heads / a.num_k_heads);
     const uint32_t conv_dim = 2 * a.key_dim + a.value_dim;
     const __nv_bfloat16* in_proj = reinterpret_cast<const __nv_bfloat16*>(a.in_proj);
+    const uint32_t rows_per_cta = (a.head_v_dim + DN_CLUSTER - 1) / DN_CLUSTER;
+    const uint32_t row0 = crank * rows_per_cta;
+    const uint32_t row1 = min(a.head_v_dim, row0 + rows_per_cta);
+    float* state = reinterpret_cast<float*>(a.state) + (size_t)hv * a.head_v_dim * DK;
+
+    // the recurrent state does not depend on the previous kernel: fetch this warp's rows before the grid dependency resolves
+    constexpr int RPW = 4;                                                       // rows in flight per warp
+    float4 srow[RPW];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+        const uint32_t i = row0 + warp + r * DN_WARPS;
+        srow[r] = i < row1 ? *(reinterpret_cast<const float4*>(state + (size_t)i * DK) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    pdl_wait();
 
     // L2-normalise q and k, scale q by Dk^-0.5 (update.rs:60-80)
     float qv = 0.0f, kv = 0.0f;
@@ -69,33 +89,56 @@ __global__ void __launch_bounds__(DN_WARPS * 32) delta_net_update_kernel(const u
     const float gdec = -expf(reinterpret_cast<const float*>(a.a_log)[hv]) * sp;
     const float decay = expf(gdec);
 
-    float* state = reinterpret_cast<float*>(a.state) + (size_t)hv * a.head_v_dim * DK;
     const float4 q4 = *reinterpret_cast<const float4*>(&sq[lane * 4]);
     const float4 k4 = *reinterpret_cast<const float4*>(&sk[lane * 4]);
-    for (uint32_t i = warp; i < a.head_v_dim; i += DN_WARPS) {
-        float4* rowp = reinterpret_cast<float4*>(state + (size_t)i * DK) + lane;
-        const float4 s = *rowp;
-        float sqa = s.x * q4.x + s.y * q4.y + s.z * q4.z + s.w * q4.w;
-        float ska = s.x * k4.x + s.y * k4.y + s.z * k4.z + s.w * k4.w;
-        sqa = warp_sum(sqa);
-        ska = warp_sum(ska);
-        const float v_i = bf2f(in_proj[2 * a.key_dim + hv * a.head_v_dim + i]);
-        const float retrieved = decay * ska;
-        const float delta = beta * (v_i - retrieved);
-        if (lane == 0) so[i] = decay * sqa + delta * kq;
-        float4 ns;
-        ns.x = decay * s.x + k4.x * delta;
-        ns.y = decay * s.y + k4.y * delta;
-        ns.z = decay * s.z + k4.z * delta;
-        ns.w = decay * s.w + k4.w * delta;
-        *rowp = ns;
+    for (uint32_t base = row0 + warp; base < row1; base += RPW * DN_WARPS) {
+        if (base != row0 + warp) {
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {
+                const uint32_t i = base + r * DN_WARPS;
+                if (i < row1) srow[r] = *(reinterpret_cast<const float4*>(state + (size_t)i * DK) + lane);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            const uint32_t i = base + r * DN_WARPS;
+            if (i >= row1) break;
+            const float4 s = srow[r];
+            float sqa = s.x * q4.x + s.y * q4.y + s.z * q4.z + s.w * q4.w;
+            float ska = s.x * k4.x + s.y * k4.y + s.z * k4.z + s.w * k4.w;
+            sqa = warp_sum(sqa);
+            ska = warp_sum(ska);
+            const float v_i = bf2f(in_proj[2 * a.key_dim + hv * a.head_v_dim + i]);
+            const float retrieved = decay * ska;
+            const float delta = beta * (v_i - retrieved);
+            if (lane == 0) so[i - row0] = decay * sqa + delta * kq;
+            float4 ns;
+            ns.x = decay * s.x + k4.x * delta;
+            ns.y = decay * s.y + k4.y * delta;
+            ns.z = decay * s.z + k4.z * delta;
+            ns.w = decay * s.w + k4.w * delta;
+            *(reinterpret_cast<float4*>(state + (size_t)i * DK) + lane) = ns;
+        }
     }
     __syncthreads();
-    const float ov = threadIdx.x < a.head_v_dim ? so[threadIdx.x] : 0.0f;
-    const float ss = block_sum(ov * ov, red);
+    const uint32_t nrows = row1 > row0 ? row1 - row0 : 0;
+    const float ov = threadIdx.x < nrows ? so[threadIdx.x] : 0.0f;
+    const float ss_local = block_sum(ov * ov, red);
+    // publish this CTA's partial into every CTA of the cluster (DSMEM), then sum the DN_CLUSTER partials in rank order
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+    if (threadIdx.x < DN_CLUSTER) {
+        const uint32_t local = (uint32_t)__cvta_generic_to_shared(&ss_parts[crank]);
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"((uint32_t)threadIdx.x));
+        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(ss_local) : "memory");
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    float ss = 0.0f;
+#pragma unroll
+    for (int c = 0; c < DN_CLUSTER; ++c) ss += ss_parts[c];
     const float inv_rms = 1.0f / sqrtf(ss / (float)a.head_v_dim + a.norm_epsilon);
-    if (threadIdx.x < a.head_v_dim) {
-        const uint32_t i = threadIdx.x;
+    if (threadIdx.x < nrows) {
+        const uint32_t i = row0 + threadIdx.x;
         const float nw = reinterpret_cast<const float*>(a.norm_weight)[i];
         const float z = bf2f(in_proj[conv_dim + hv * a.head_v_dim + i]);
         const float zs = act_f32(UZU_ACT_SILU, z);
@@ -127,7 +170,7 @@ void uzu_delta_net_update_encode(uzu_command_buffer* cmd, const uzu_delta_net_up
         cmd->record_error(UZU_ERROR_UNSUPPORTED, "delta_net_update: HEAD_K_DIM must be 128 and head_v_dim <= 256");
         return;
     }
-    uzu::launch(cmd, "delta_net_update_kernel", uzu::delta_net_update_kernel, dim3(a->num_v_heads), dim3(uzu::DN_WARPS * 32), 0, *a);
+    uzu::launch(cmd, "delta_net_update_kernel", uzu::delta_net_update_kernel, dim3(a->num_v_heads * uzu::DN_CLUSTER), dim3(uzu::DN_WARPS * 32), 0, *a);
 }
 
 }  // extern "C"
