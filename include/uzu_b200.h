@@ -180,7 +180,8 @@ UZU_API uzu_status uzu_matmul_validate(const uzu_matmul_args* args);   /* Matmul
  *   prologue 1: NormalizationKernel (RMS norm, optional residual add; the updated residual goes to `shortcut_out`, which must differ
  *               from `norm_shortcut_in`; 0 = do not write, for a second linear sharing the same norm),
  *   prologue 2: GatedActMulKernel (interleaved [value | gate] row of length 2k in `act_operand`),
- *   prologue 3: SigmoidGateKernel (x = attn * sigmoid(gate)).
+ *   prologue 3: SigmoidGateKernel (x = attn * sigmoid(gate)),
+ *   prologue 0: x = matmul.a (only meaningful together with an epilogue).
  * Same arithmetic and rounding points as the standalone kernels. uzu_fused_linear_supported() tells whether the fast path applies;
  * if not, the caller encodes the unfused sequence. `matmul.a` is ignored for prologue != 0. */
 typedef struct uzu_fused_linear_args {
@@ -191,7 +192,12 @@ typedef struct uzu_fused_linear_args {
     uint32_t norm_residual_add, norm_full_layer;
     uint64_t act_operand; uint32_t act_type;
     uint64_t sg_attn, sg_gate;
+    /* epilogue 1: the matmul's n = 2F rows are [up | gate] (DenseMlp's fused up projection, mlp/dense.rs:32-48); instead of the
+     * 2F row the kernel stores hidden[j] = GatedActMul(up_j, gate_j) (act_type) as bf16 [F] into matmul.d. prologue may be 0. */
+    uint32_t epilogue, reserved0;
 } uzu_fused_linear_args;
+/* Tuning sweeps only (tools/): override the decode GEMV's work split; 0 = heuristic. Process-wide, not thread-safe. */
+UZU_API void uzu_debug_set_qmv_tuning(int warps_per_tile, int k_slices, int ctas_per_sm, int stages);
 UZU_API int uzu_fused_linear_supported(uzu_context* ctx, const uzu_fused_linear_args* args);
 UZU_API void uzu_fused_linear_encode(uzu_command_buffer* cmd, const uzu_fused_linear_args* args);
 
@@ -416,6 +422,9 @@ UZU_API uint64_t uzu_engine_launch_count(const uzu_engine* e);   /* kernels laun
 UZU_API uzu_status uzu_engine_decode_timed(uzu_engine* e, uint32_t steps, double* out_seconds);
 UZU_API uzu_status uzu_engine_step_host(uzu_engine* e, uint32_t token_in, uint32_t* token_out);
 UZU_API uzu_status uzu_engine_time_linears(uzu_engine* e, uint32_t iters, double* out_seconds, uint64_t* out_launches);
+/* same, restricted to a subset: bit 0 mixer input projections (qkv / gate / in_proj), 1 mixer output projection, 2 MLP up, 3 MLP down,
+ * 4 readout, 5 MLP up with the GatedActMul epilogue */
+UZU_API uzu_status uzu_engine_time_linears_select(uzu_engine* e, uint32_t iters, uint32_t select, double* out_seconds, uint64_t* out_launches);
 
 #ifdef __cplusplus
 }

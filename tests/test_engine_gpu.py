@@ -224,3 +224,50 @@ def test_fused_linear_kernel_vs_oracle(ctx):
     b_attn, b_gate = ctx.upload(attn), ctx.upload(gate)
     got = mm(3, sg_attn=b_attn.ptr, sg_gate=b_gate.ptr)
     assert_f32_close(got, ref_mm(O.sigmoid_gate(gate, attn.copy())), rtol=2e-3, atol=2e-3, what="fused sigmoid gate")
+
+
+@pytest.mark.parametrize("act", ["silu", "gelu"])
+@pytest.mark.parametrize("F,k,with_norm", [(1536, 2048, False), (3584, 1024, True), (14336 // 4, 4096, True), (16, 512, False)])
+def test_gated_epilogue_matches_unfused_sequence(ctx, act, F, k, with_norm):
+    """up GEMV with the GatedActMul epilogue (paired tiles) == matmul -> gated_act_mul, bit for bit (same accumulation order in
+    both up to the k split over warps), and within tolerance of the oracle."""
+    import ctypes as C
+    from oracle import oracle as O
+    from tests.util import f32_to_bf16, bf16_to_f32
+    from tests import gpu_ops as G
+    rng = np.random.default_rng(F + k)
+    n = 2 * F
+    w = rng.integers(0, 256, (n, k // 2), dtype=np.uint8)
+    sc = f32_to_bf16(rng.uniform(0.005, 0.02, (n, k // 64)).astype(np.float32))
+    zp = rng.integers(0, 256, (n, (k // 64 + 1) // 2), dtype=np.uint8)
+    x = f32_to_bf16(rng.standard_normal((1, k)).astype(np.float32))
+    act_id = B.ACT_SILU if act == "silu" else B.ACT_GELU_APPROX
+    bw, bs, bz, bx = ctx.upload(w), ctx.upload(sc), ctx.upload(zp), ctx.upload(x)
+    bd = ctx.upload(np.zeros((1, F), np.uint16))
+    a = B.FusedLinearArgs(prologue=0, epilogue=1, act_type=act_id)
+    kw = {}
+    if with_norm:
+        sc_in = f32_to_bf16(rng.standard_normal((1, k)).astype(np.float32))
+        scales = (0.05 * rng.standard_normal(k)).astype(np.float32)
+        b_scin, b_scout, b_scales = ctx.upload(sc_in), ctx.upload(np.zeros((1, k), np.uint16)), ctx.upload(scales)
+        a = B.FusedLinearArgs(prologue=1, epilogue=1, act_type=act_id, norm_input=bx.ptr, norm_shortcut_in=b_scin.ptr, norm_scales=b_scales.ptr,
+                              shortcut_out=b_scout.ptr, norm_epsilon=1e-6, norm_scale_offset=1.0, norm_residual_add=1, norm_full_layer=0)
+        sc_ref = sc_in.copy()
+        x_eff = O.normalization(x, scales, shortcut=sc_ref, residual_add=True, epsilon=1e-6, scale_offset=1.0, full_layer=False)
+    else:
+        x_eff = x
+    a.matmul = B.MatmulArgs(a=bx.ptr, b=bw.ptr, b_scales=bs.ptr, b_zero_points=bz.ptr, d=bd.ptr, b_prologue=B.B_SCALE_ZERO_POINT, b_mode=B.QMODE_U4,
+                            b_group_size=64, b_transpose=1, ab_scale=1.0, m=1, n=n, k=k, weights_dt=B.DT_BF16, input_dt=B.DT_BF16, output_dt=B.DT_BF16)
+    assert ctx.lib.uzu_fused_linear_supported(ctx.h, C.byref(a)) == 1
+    with ctx.command_buffer("gated-epilogue") as cmd:
+        cmd.encode("uzu_fused_linear_encode", C.byref(a))
+    got = bd.numpy(np.uint16, (1, F))
+    # unfused GPU sequence on the same (normalised) input
+    up_gpu = G.matmul(ctx, x_eff, w, m=1, n=n, k=k, scales=sc, zero_points=zp, method=O.QM_ZERO_POINT, bits=4, group_size=64)
+    seq = G.gated_act_mul(ctx, up_gpu, F, act=act_id)
+    # same arithmetic, but the k split over warps may differ from the unfused GEMV's: allow 1 bf16 ulp on a few elements
+    from tests.util import assert_bf16_close
+    assert_bf16_close(got, seq, max_ulp=3, min_exact=0.95, what="gated epilogue vs unfused sequence")
+    ref = O.gated_act_mul(O.matmul(x_eff, w, m=1, n=n, k=k, scales=sc, zero_points=zp, method=O.QM_ZERO_POINT), F, act=act_id)
+    gf, rf = bf16_to_f32(got), bf16_to_f32(ref)
+    assert np.allclose(gf, rf, rtol=2e-2, atol=2e-2 * max(1.0, float(np.sqrt((rf ** 2).mean()))))

@@ -112,7 +112,7 @@ ModelInfo = _struct("uzu_model_info", [
 FusedLinearArgs = _struct("uzu_fused_linear_args", [
     ("matmul", MatmulArgs), ("prologue", u32), ("norm_input", u64), ("norm_shortcut_in", u64), ("norm_scales", u64), ("shortcut_out", u64),
     ("norm_epsilon", f32), ("norm_scale_offset", f32), ("norm_residual_add", u32), ("norm_full_layer", u32), ("act_operand", u64),
-    ("act_type", u32), ("sg_attn", u64), ("sg_gate", u64)])
+    ("act_type", u32), ("sg_attn", u64), ("sg_gate", u64), ("epilogue", u32), ("reserved0", u32)])
 
 ABI_STRUCTS = [FusedLinearArgs, RingParams, TrieNode, KvCopy, MatmulArgs, NormalizationArgs, QkvNormArgs, AttentionPrepareArgs, AttentionArgs,
                AttentionTwoPass2Args, KvCacheUpdateArgs, GatedActMulArgs, QuantizedEmbeddingLookupArgs, UnifiedSamplingArgs,
@@ -136,7 +136,7 @@ uzu_tensor_add_bias_encode uzu_tensor_add_swap_encode uzu_unified_sampling_encod
 uzu_delta_net_update_encode uzu_engine_create uzu_engine_destroy uzu_engine_info uzu_engine_reset uzu_engine_context_length
 uzu_engine_snapshot uzu_engine_restore uzu_engine_prefill uzu_engine_next uzu_engine_flush uzu_engine_decode_device
 uzu_engine_forward uzu_engine_launch_count uzu_engine_decode_timed uzu_engine_step_host
-uzu_engine_time_linears uzu_fused_linear_supported uzu_fused_linear_encode""".split()
+uzu_engine_time_linears uzu_engine_time_linears_select uzu_debug_set_qmv_tuning uzu_fused_linear_supported uzu_fused_linear_encode""".split()
 
 _lib = None
 
@@ -232,6 +232,8 @@ def load() -> C.CDLL:
         "uzu_engine_decode_timed": (C.c_int, [vp, u32, C.POINTER(C.c_double)]),
         "uzu_engine_step_host": (C.c_int, [vp, u32, C.POINTER(u32)]),
         "uzu_engine_time_linears": (C.c_int, [vp, u32, C.POINTER(C.c_double), C.POINTER(u64)]),
+        "uzu_engine_time_linears_select": (C.c_int, [vp, u32, u32, C.POINTER(C.c_double), C.POINTER(u64)]),
+        "uzu_debug_set_qmv_tuning": (None, [C.c_int, C.c_int, C.c_int, C.c_int]),
         "uzu_fused_linear_supported": (C.c_int, [vp, C.POINTER(FusedLinearArgs)]),
         "uzu_fused_linear_encode": (None, [vp, C.POINTER(FusedLinearArgs)]),
     }
@@ -463,7 +465,7 @@ class Engine:
         _check(self.lib.uzu_engine_step_host(self.h, int(token), C.byref(out)))
         return out.value
 
-    def time_linears(self, iters: int):
+    def time_linears(self, iters: int, select: int = 31):
         t, n = C.c_double(), u64()
-        _check(self.lib.uzu_engine_time_linears(self.h, iters, C.byref(t), C.byref(n)))
+        _check(self.lib.uzu_engine_time_linears_select(self.h, iters, select, C.byref(t), C.byref(n)))
         return t.value, n.value

@@ -112,12 +112,27 @@ __device__ __forceinline__ bool should_use_key(const uzu_attention_args& a, uint
 __device__ __forceinline__ float safe_exp_diff(float m, float gm) { return (m == -INFINITY) ? 0.0f : expf(m - gm); }
 
 constexpr int ATTN_WARPS = 4;
+constexpr int ATTN_CHUNK = 512;     // keys whose scores live in shared memory at once
+constexpr int ATTN_UNROLL = 4;      // key rows in flight per lane group
 
-template <int D, int G, int EPL>
+// Split-KV attention for short suffixes (decode) and, with nsplits = 1, for any suffix. One CTA = (G query heads sharing a KV
+// head, one query token, one key range). Per chunk of <= ATTN_CHUNK keys: (1) scores q.k for all keys of the chunk, K rows
+// loaded ATTN_UNROLL at a time with no dependency between them; (2) chunk max / exp / sum per head; (3) o += p.V with the V
+// rows streamed the same way. The running (m, l, o) is rescaled only once per chunk, so the key loop has no serial
+// softmax chain (the first version of this kernel updated (m, l, o) per key and spent most of its time waiting on loads).
+template <int D, int G>
 __global__ void __launch_bounds__(ATTN_WARPS * 32) attn_split_kernel(const AttnParams p) {
-    constexpr int LPK = D / EPL;     // lanes per key
-    constexpr int KPW = 32 / LPK;    // keys per warp step
+    constexpr int EPL = (D >= 128 && G < 8) ? 16 : 8;    // elements per lane (q and o live in registers: 2 * G * EPL floats)
+    constexpr int CH = (G * D > 1024) ? ATTN_CHUNK / 2 : ATTN_CHUNK;
+    constexpr int LPK = D / EPL;              // lanes per key row
+    constexpr int KPW = 32 / LPK;             // key rows per warp step
+    constexpr int STEP = ATTN_WARPS * KPW;    // key rows per CTA step
+    constexpr int U = ATTN_UNROLL;
     static_assert(LPK >= 1 && LPK <= 32 && (EPL % 8) == 0, "bad attention tiling");
+    __shared__ float sc[G][CH];
+    __shared__ float sm_o[ATTN_WARPS][G][D];
+    __shared__ float sm_m[G], sm_lc[G], sm_mfin[G], sm_lfin[G];
+    __shared__ unsigned int sm_ticket;
     pdl_launch_dependents();
     pdl_wait();
     uzu_attention_args a = p.a;
@@ -136,8 +151,8 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attn_split_kernel(const AttnP
     const uint32_t query_position = a.is_trie ? suffix_position + reinterpret_cast<const uzu_trie_node*>(a.trie)[qs].height
                                               : suffix_position + qs;
 
-    const __nv_bfloat16* keys = reinterpret_cast<const __nv_bfloat16*>(a.keys) + (size_t)kvh * a.k_head_stride;
-    const __nv_bfloat16* values = reinterpret_cast<const __nv_bfloat16*>(a.values) + (size_t)kvh * a.v_head_stride;
+    const __nv_bfloat16* keys = reinterpret_cast<const __nv_bfloat16*>(a.keys) + (size_t)kvh * a.k_head_stride + d0;
+    const __nv_bfloat16* values = reinterpret_cast<const __nv_bfloat16*>(a.values) + (size_t)kvh * a.v_head_stride + d0;
 
     float q[G][EPL];
 #pragma unroll
@@ -154,98 +169,137 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attn_split_kernel(const AttnP
             }
         }
     }
-    float m[G], l[G], o[G][EPL];
+    // running softmax state: (m, l) identical in every thread, o partial per lane group (summed at the end)
+    float m_run[G], l_run[G], o[G][EPL];
 #pragma unroll
     for (int h = 0; h < G; ++h) {
-        m[h] = -INFINITY;
-        l[h] = 0.0f;
+        m_run[h] = -INFINITY;
+        l_run[h] = 0.0f;
 #pragma unroll
         for (int e = 0; e < EPL; ++e) o[h][e] = 0.0f;
     }
-    if (a.has_sinks && split == 0 && warp == 0 && sub == 0) {
+    if (a.has_sinks && split == 0) {
 #pragma unroll
         for (int h = 0; h < G; ++h) {
-            m[h] = bf2f(reinterpret_cast<const __nv_bfloat16*>(a.sinks)[head0 + h]);
-            l[h] = 1.0f;  // every lane of the group carries the same (m, l)
+            m_run[h] = bf2f(reinterpret_cast<const __nv_bfloat16*>(a.sinks)[head0 + h]);
+            l_run[h] = 1.0f;
         }
     }
 
     const uint32_t begin = min(a.sequence_length, split * keys_per_split);
     const uint32_t end = min(a.sequence_length, begin + keys_per_split);
-    for (uint32_t base = begin + warp * KPW; base < end; base += ATTN_WARPS * KPW) {
-        const uint32_t i = base + sub;
-        const bool valid = i < end && should_use_key(a, qs, prefix_length, suffix_position, query_position, i);
-        float kf[EPL], vf[EPL];
-        if (valid) {
-            const __nv_bfloat16* kp = keys + (size_t)i * a.k_seq_stride + d0;
-            const __nv_bfloat16* vp = values + (size_t)i * a.v_seq_stride + d0;
+    for (uint32_t cbeg = begin; cbeg < end; cbeg += CH) {
+        const uint32_t n = min((uint32_t)CH, end - cbeg);
+        // ---- (1) scores ------------------------------------------------------------------------------------
+        for (uint32_t kb = warp * KPW; kb < n; kb += STEP * U) {
+            uint4 kr[U][EPL / 8];
+            bool ok[U];
 #pragma unroll
-            for (int v = 0; v < EPL / 8; ++v) {
-                const uint4 kr = *reinterpret_cast<const uint4*>(kp + v * 8);
-                const uint4 vr = *reinterpret_cast<const uint4*>(vp + v * 8);
-                const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kr);
-                const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vr);
+            for (int u = 0; u < U; ++u) {
+                const uint32_t kl = kb + u * STEP + sub, i = cbeg + kl;
+                ok[u] = kl < n && should_use_key(a, qs, prefix_length, suffix_position, query_position, i);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    kf[v * 8 + 2 * e] = __low2float(k2[e]);
-                    kf[v * 8 + 2 * e + 1] = __high2float(k2[e]);
-                    vf[v * 8 + 2 * e] = __low2float(v2[e]);
-                    vf[v * 8 + 2 * e + 1] = __high2float(v2[e]);
+                for (int v = 0; v < EPL / 8; ++v)
+                    kr[u][v] = ok[u] ? *reinterpret_cast<const uint4*>(keys + (size_t)i * a.k_seq_stride + v * 8) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t kl = kb + u * STEP + sub;
+                float kf[EPL];
+#pragma unroll
+                for (int v = 0; v < EPL / 8; ++v) {
+                    const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kr[u][v]);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { kf[v * 8 + 2 * e] = __low2float(k2[e]); kf[v * 8 + 2 * e + 1] = __high2float(k2[e]); }
+                }
+#pragma unroll
+                for (int h = 0; h < G; ++h) {
+                    float sdot = 0.0f;
+#pragma unroll
+                    for (int e = 0; e < EPL; ++e) sdot += q[h][e] * kf[e];
+#pragma unroll
+                    for (int off = LPK / 2; off > 0; off >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, off);
+                    if (li == 0 && kl < n) sc[h][kl] = ok[u] ? sdot : -INFINITY;
                 }
             }
-        } else {
-#pragma unroll
-            for (int e = 0; e < EPL; ++e) { kf[e] = 0.0f; vf[e] = 0.0f; }
         }
+        __syncthreads();
+        // ---- (2) chunk max, probabilities relative to the new running max, chunk sum (one warp per head) -----
 #pragma unroll
         for (int h = 0; h < G; ++h) {
-            float s = 0.0f;
-#pragma unroll
-            for (int e = 0; e < EPL; ++e) s += q[h][e] * kf[e];
-#pragma unroll
-            for (int off = LPK / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (valid) {
-                const float new_max = fmaxf(m[h], s);
-                const float factor = expf(m[h] - new_max);   // m = -inf -> 0
-                const float es = expf(s - new_max);
-                m[h] = new_max;
-                l[h] = l[h] * factor + es;
-#pragma unroll
-                for (int e = 0; e < EPL; ++e) o[h][e] = o[h][e] * factor + es * vf[e];
+            if ((h % ATTN_WARPS) != warp) continue;      // static register indexing of m_run
+            float mc = -INFINITY;
+            for (uint32_t kl = lane; kl < n; kl += 32) mc = fmaxf(mc, sc[h][kl]);
+            mc = warp_max(mc);
+            const float m_new = fmaxf(m_run[h], mc);
+            float lc = 0.0f;
+            for (uint32_t kl = lane; kl < n; kl += 32) {
+                const float sv = sc[h][kl];
+                const float pv = (sv == -INFINITY) ? 0.0f : expf(sv - m_new);
+                sc[h][kl] = pv;
+                lc += pv;
             }
+            lc = warp_sum(lc);
+            if (lane == 0) { sm_m[h] = m_new; sm_lc[h] = lc; }
         }
-    }
-
-    // ---- merge the KPW key groups of a warp ------------------------------------------------------------
-#pragma unroll
-    for (int off = LPK; off < 32; off <<= 1) {
+        __syncthreads();
 #pragma unroll
         for (int h = 0; h < G; ++h) {
-            const float m2 = __shfl_xor_sync(0xffffffffu, m[h], off);
-            const float l2 = __shfl_xor_sync(0xffffffffu, l[h], off);
-            const float gm = fmaxf(m[h], m2);
-            const float f1 = safe_exp_diff(m[h], gm), f2 = safe_exp_diff(m2, gm);
-            l[h] = l[h] * f1 + l2 * f2;
+            const float m_new = sm_m[h];
+            const float factor = safe_exp_diff(m_run[h], m_new);
+            l_run[h] = l_run[h] * factor + sm_lc[h];
+            m_run[h] = m_new;
 #pragma unroll
-            for (int e = 0; e < EPL; ++e) {
-                const float o2 = __shfl_xor_sync(0xffffffffu, o[h][e], off);
-                o[h][e] = o[h][e] * f1 + o2 * f2;
-            }
-            m[h] = gm;
+            for (int e = 0; e < EPL; ++e) o[h][e] *= factor;
         }
+        // ---- (3) o += p . V ---------------------------------------------------------------------------------
+        for (uint32_t kb = warp * KPW; kb < n; kb += STEP * U) {
+            uint4 vr[U][EPL / 8];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t kl = kb + u * STEP + sub, i = cbeg + kl;
+#pragma unroll
+                for (int v = 0; v < EPL / 8; ++v)
+                    vr[u][v] = kl < n ? *reinterpret_cast<const uint4*>(values + (size_t)i * a.v_seq_stride + v * 8) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t kl = kb + u * STEP + sub;
+                if (kl >= n) continue;
+                float vf[EPL];
+#pragma unroll
+                for (int v = 0; v < EPL / 8; ++v) {
+                    const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vr[u][v]);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { vf[v * 8 + 2 * e] = __low2float(v2[e]); vf[v * 8 + 2 * e + 1] = __high2float(v2[e]); }
+                }
+#pragma unroll
+                for (int h = 0; h < G; ++h) {
+                    const float pv = sc[h][kl];
+#pragma unroll
+                    for (int e = 0; e < EPL; ++e) o[h][e] += pv * vf[e];
+                }
+            }
+        }
+        __syncthreads();     // sc is rewritten by the next chunk
     }
 
-    // ---- merge the warps of the CTA through shared memory --------------------------------------------------
-    __shared__ float sm_o[ATTN_WARPS][G][D];
-    __shared__ float sm_m[ATTN_WARPS][G], sm_l[ATTN_WARPS][G];
-    __shared__ unsigned int sm_ticket;
+    // ---- sum the lane groups of a warp, then the warps of the CTA --------------------------------------------------------
+#pragma unroll
+    for (int off = LPK; off < 32; off <<= 1)
+#pragma unroll
+        for (int h = 0; h < G; ++h)
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) o[h][e] += __shfl_xor_sync(0xffffffffu, o[h][e], off);
     if (sub == 0) {
 #pragma unroll
-        for (int h = 0; h < G; ++h) {
+        for (int h = 0; h < G; ++h)
 #pragma unroll
             for (int e = 0; e < EPL; ++e) sm_o[warp][h][d0 + e] = o[h][e];
-            if (li == 0) { sm_m[warp][h] = m[h]; sm_l[warp][h] = l[h]; }
-        }
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int h = 0; h < G; ++h) { sm_mfin[h] = m_run[h]; sm_lfin[h] = l_run[h]; }
     }
     __syncthreads();
 
@@ -253,16 +307,10 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attn_split_kernel(const AttnP
     const bool direct = (p.nsplits == 1) && p.fuse_merge;
     for (int idx = threadIdx.x; idx < G * D; idx += blockDim.x) {
         const int h = idx / D, d = idx % D;
-        float gm = -INFINITY;
+        float ov = 0.0f;
 #pragma unroll
-        for (int w = 0; w < ATTN_WARPS; ++w) gm = fmaxf(gm, sm_m[w][h]);
-        float ov = 0.0f, lv = 0.0f;
-#pragma unroll
-        for (int w = 0; w < ATTN_WARPS; ++w) {
-            const float f = safe_exp_diff(sm_m[w][h], gm);
-            ov += sm_o[w][h][d] * f;
-            lv += sm_l[w][h] * f;
-        }
+        for (int w = 0; w < ATTN_WARPS; ++w) ov += sm_o[w][h][d];
+        const float lv = sm_lfin[h], gm = sm_mfin[h];
         const size_t o_off = (size_t)qs * H + head0 + h;
         if (direct) {
             p.final_out[o_off * D + d] = f2bf(ov / lv);
@@ -287,7 +335,7 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attn_split_kernel(const AttnP
         }
         return;
     }
-    // ---- in-kernel merge: the last CTA of this (token, head group) combines all splits -----------------------
+    // ---- in-kernel merge: the last CTA of this (token, head group) combines all splits (nsplits <= 32) -----------------
     __threadfence();
     __syncthreads();
     const uint32_t cidx = qs * gridDim.x + blockIdx.x;
@@ -295,18 +343,25 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attn_split_kernel(const AttnP
     __syncthreads();
     if (sm_ticket != p.nsplits - 1) return;
     __threadfence();
+    for (int h = warp; h < G; h += ATTN_WARPS) {        // one warp per head: split factors and the global sum
+        const size_t o_off = (size_t)qs * H + head0 + h;
+        const bool has = (uint32_t)lane < p.nsplits;
+        const float mymax = has ? __ldcg(&p.part_max[o_off * p.nb + lane]) : -INFINITY;
+        const float gmax = warp_max(mymax);
+        const float f = has ? expf(mymax - gmax) : 0.0f;
+        const float gsum = warp_sum(has ? __ldcg(&p.part_sum[o_off * p.nb + lane]) * f : 0.0f);
+        sc[h][lane] = f;
+        if (lane == 0) sm_lfin[h] = gsum;
+    }
+    __syncthreads();
     for (int idx = threadIdx.x; idx < G * D; idx += blockDim.x) {
         const int h = idx / D, d = idx % D;
         const size_t o_off = (size_t)qs * H + head0 + h;
-        float gm = -INFINITY;
-        for (uint32_t s = 0; s < p.nsplits; ++s) gm = fmaxf(gm, __ldcg(&p.part_max[o_off * p.nb + s]));
-        float gs = 0.0f, val = 0.0f;
-        for (uint32_t s = 0; s < p.nsplits; ++s) {
-            const float f = expf(__ldcg(&p.part_max[o_off * p.nb + s]) - gm);
-            gs += __ldcg(&p.part_sum[o_off * p.nb + s]) * f;
-            val += __ldcg(&p.part_o[(o_off * p.nb + s) * D + d]) * f;
-        }
-        p.final_out[o_off * D + d] = f2bf(val / gs);
+        const float* po = p.part_o + (o_off * p.nb) * D + d;
+        float val = 0.0f;
+#pragma unroll 8
+        for (uint32_t sp = 0; sp < p.nsplits; ++sp) val += __ldcg(po + (size_t)sp * D) * sc[h][sp];
+        p.final_out[o_off * D + d] = f2bf(val / sm_lfin[h]);
     }
     if (threadIdx.x == 0) p.counters[cidx] = 0;
 }
@@ -370,20 +425,20 @@ __global__ void __launch_bounds__(256) sigmoid_gate_kernel(const __nv_bfloat16* 
 // ---------------------------------------------------------------------------------------------------
 // host dispatch
 // ---------------------------------------------------------------------------------------------------
-template <int D, int G, int EPL>
+template <int D, int G>
 static void launch_attn(uzu_command_buffer* cmd, const AttnParams& p, uint32_t head_groups) {
     dim3 grid(head_groups, p.a.suffix_length, p.nsplits);
-    launch(cmd, "attn_split_kernel", attn_split_kernel<D, G, EPL>, grid, dim3(ATTN_WARPS * 32), 0, p);
+    launch(cmd, "attn_split_kernel", attn_split_kernel<D, G>, grid, dim3(ATTN_WARPS * 32), 0, p);
 }
 
 template <int D>
 static void launch_attn_g(uzu_command_buffer* cmd, const AttnParams& p, int g) {
     const uint32_t H = p.a.num_heads;
     switch (g) {
-        case 8: launch_attn<D, 8, 8>(cmd, p, H / 8); break;
-        case 4: launch_attn<D, 4, 16>(cmd, p, H / 4); break;
-        case 2: launch_attn<D, 2, 16>(cmd, p, H / 2); break;
-        default: launch_attn<D, 1, 16>(cmd, p, H); break;
+        case 8: launch_attn<D, 8>(cmd, p, H / 8); break;
+        case 4: launch_attn<D, 4>(cmd, p, H / 4); break;
+        case 2: launch_attn<D, 2>(cmd, p, H / 2); break;
+        default: launch_attn<D, 1>(cmd, p, H); break;
     }
 }
 

@@ -166,6 +166,22 @@ __device__ __forceinline__ float act_f32(uint32_t act, float x) {
     }
 }
 
+// the same function for translation units compiled WITH fma contraction (matmul.cu): explicit roundings so that fused
+// prologues / epilogues match the standalone kernels (built with -fmad=false) bit for bit
+__device__ __forceinline__ float act_f32_nofma(uint32_t act, float x) {
+    switch (act) {
+        case UZU_ACT_SILU: return __fdiv_rn(x, __fadd_rn(1.0f, expf(-x)));
+        case UZU_ACT_GELU_APPROX: {
+            const float x3 = __fmul_rn(__fmul_rn(__fmul_rn(0.044715f, x), x), x);
+            const float t = __fmul_rn(0.7978846f, __fadd_rn(x, x3));
+            return __fmul_rn(__fmul_rn(0.5f, x), __fadd_rn(1.0f, tanhf(t)));
+        }
+        case UZU_ACT_GELU_EXACT: return __fmul_rn(__fmul_rn(0.5f, x), __fadd_rn(1.0f, erff(__fmul_rn(x, 0.70710678118654752440f))));
+        case UZU_ACT_SOFTPLUS: return x > 20.0f ? x : logf(__fadd_rn(1.0f, expf(x)));
+        default: return x;
+    }
+}
+
 #endif  // __CUDACC__
 
 }  // namespace uzu

@@ -992,28 +992,45 @@ static uzu_fused_linear_args fused_norm_args(const Linear& l, const Norm& n, uin
     return f;
 }
 
+// Which launches the fused decode path folds away (UZU_FUSE_MASK, default all):
+//   bit 0: pre-mixer / pre-MLP RMSNorm (+ residual add) -> prologue of the consuming GEMV(s)
+//   bit 1: GatedActMul -> epilogue of the up GEMV (paired up / gate tiles)
+//   bit 2: SigmoidGate -> prologue of the attention out projection
+static uint32_t fuse_mask() {
+    static const uint32_t m = [] { const char* v = getenv("UZU_FUSE_MASK"); return v ? (uint32_t)atoi(v) : 7u; }();
+    return m;
+}
+
+static uzu_fused_linear_args fused_up_args(uzu_engine* e, const Layer& L, bool norm_fused, uint64_t sc_in, uint64_t sc_out) {
+    const bool gated = (fuse_mask() & 2u) != 0;
+    uzu_fused_linear_args f{};
+    if (norm_fused) f = fused_norm_args(L.up, L.pre_mlp, e->mixer_out.ptr(), sc_in, sc_out, true, gated ? e->gated.ptr() : e->fused_up.ptr());
+    else f.matmul = linear_args(L.up, e->hidden_b.ptr(), 1, gated ? e->gated.ptr() : e->fused_up.ptr());
+    if (gated) { f.epilogue = 1; f.act_type = L.act; }
+    return f;
+}
+
 static bool fused_decode_supported(uzu_engine* e) {
+    const uint32_t mask = fuse_mask();
     for (auto& L : e->layers) {
         if (L.pre_mixer.cfg.subtract_mean || L.pre_mlp.cfg.subtract_mean || !L.pre_mixer.cfg.has_scale || !L.pre_mlp.cfg.has_scale) return false;
         std::vector<uzu_fused_linear_args> fs;
         const uint64_t x = e->hidden_a.ptr(), s0 = e->shortcut.ptr(), s1 = e->shortcut2.ptr();
-        if (L.is_attention) {
-            if (L.attn.has_gate) {
-                fs.push_back(fused_norm_args(L.attn.gate, L.pre_mixer, x, s0, s1, true, e->gate.ptr()));
-                uzu_fused_linear_args g{};
-                g.matmul = linear_args(L.attn.out, 0, 1, e->mixer_out.ptr());
-                g.prologue = 3; g.sg_attn = e->attn_out.ptr(); g.sg_gate = e->gate.ptr();
-                fs.push_back(g);
+        if (mask & 1u) {
+            if (L.is_attention) {
+                if (L.attn.has_gate) fs.push_back(fused_norm_args(L.attn.gate, L.pre_mixer, x, s0, s1, true, e->gate.ptr()));
+                fs.push_back(fused_norm_args(L.attn.qkv, L.pre_mixer, x, s0, s1, true, e->qkv.ptr()));
+            } else {
+                fs.push_back(fused_norm_args(L.dn.in_proj, L.pre_mixer, x, s0, s1, true, e->in_proj.ptr()));
             }
-            fs.push_back(fused_norm_args(L.attn.qkv, L.pre_mixer, x, s0, s1, true, e->qkv.ptr()));
-        } else {
-            fs.push_back(fused_norm_args(L.dn.in_proj, L.pre_mixer, x, s0, s1, true, e->in_proj.ptr()));
         }
-        fs.push_back(fused_norm_args(L.up, L.pre_mlp, e->mixer_out.ptr(), s0, s1, true, e->fused_up.ptr()));
-        uzu_fused_linear_args d{};
-        d.matmul = linear_args(L.down, 0, 1, e->hidden_a.ptr());
-        d.prologue = 2; d.act_operand = e->fused_up.ptr(); d.act_type = L.act;
-        fs.push_back(d);
+        if (L.is_attention && L.attn.has_gate && (mask & 4u)) {
+            uzu_fused_linear_args g{};
+            g.matmul = linear_args(L.attn.out, 0, 1, e->mixer_out.ptr());
+            g.prologue = 3; g.sg_attn = e->attn_out.ptr(); g.sg_gate = e->gate.ptr();
+            fs.push_back(g);
+        }
+        if (mask & 3u) fs.push_back(fused_up_args(e, L, (mask & 1u) != 0, s0, s1));
         for (auto& f : fs)
             if (!uzu_fused_linear_supported(e->ctx, &f)) return false;
     }
@@ -1022,6 +1039,8 @@ static bool fused_decode_supported(uzu_engine* e) {
 
 static void encode_decoder_fused(uzu_engine* e, uzu_command_buffer* cmd, const PassCtx& pc) {
     const uint32_t H = e->model_dim;
+    const uint32_t mask = fuse_mask();
+    const bool fuse_norm = (mask & 1u) != 0, fuse_gated = (mask & 2u) != 0, fuse_sigmoid = (mask & 4u) != 0;
     // embedding lookup (embedding.rs:345-372)
     if (e->in_emb.w.prologue == UZU_B_FULL_PRECISION) {
         uzu_full_precision_embedding_lookup_encode(cmd, e->token_ids.ptr(), e->in_emb.w.values.ptr(), e->hidden_a.ptr(), 1, e->vocab, H, e->input_scale);
@@ -1035,6 +1054,8 @@ static void encode_decoder_fused(uzu_engine* e, uzu_command_buffer* cmd, const P
                                  : e->in_emb.w.prologue == UZU_B_SCALE_ZERO_POINT_DEQUANT ? UZU_QMETHOD_SCALE_ZERO_POINT : UZU_QMETHOD_SCALE_SYMMETRIC;
         uzu_quantized_embedding_lookup_encode(cmd, &la);
     }
+    // With the norm folded into its consumers the residual ping-pongs between two buffers (every consumer CTA re-reads the old
+    // residual while CTA 0 of the first consumer writes the new one); with a standalone norm it is updated in place in S[cur].
     uint64_t S[2] = {e->shortcut.ptr(), e->shortcut2.ptr()};
     int cur = 0;
     const uint64_t dyn = e->decode_state.ptr();
@@ -1042,17 +1063,23 @@ static void encode_decoder_fused(uzu_engine* e, uzu_command_buffer* cmd, const P
         Layer& L = e->layers[i];
         LayerState& St = e->state[i];
         const bool add = i > 0;   // layer 0: Copy mode (transformer_layer.rs:95-109)
+        bool wrote = false;
+        // `lin` consumes pre_mixer_norm(hidden_a): fused prologue or the standalone norm's output in hidden_b
+        auto mixer_in_linear = [&](const Linear& lin, uint64_t d) {
+            if (fuse_norm) {
+                auto f = fused_norm_args(lin, L.pre_mixer, e->hidden_a.ptr(), S[cur], wrote ? 0 : S[cur ^ 1], add, d);
+                uzu_fused_linear_encode(cmd, &f);
+                wrote = true;
+            } else {
+                encode_linear(cmd, lin, e->hidden_b.ptr(), 1, d);
+            }
+        };
+        if (!fuse_norm) encode_norm(cmd, L.pre_mixer, e->hidden_a.ptr(), e->hidden_b.ptr(), S[cur], add ? ShortcutAdd : ShortcutCopy, 1);
         if (L.is_attention) {
             const AttentionLayer& A = L.attn;
             const uint32_t D = A.head_dim, Hq = A.num_heads, Hkv = A.num_groups;
-            bool wrote = false;
-            if (A.has_gate) {
-                auto f = fused_norm_args(A.gate, L.pre_mixer, e->hidden_a.ptr(), S[cur], S[cur ^ 1], add, e->gate.ptr());
-                uzu_fused_linear_encode(cmd, &f);
-                wrote = true;
-            }
-            auto fq = fused_norm_args(A.qkv, L.pre_mixer, e->hidden_a.ptr(), S[cur], wrote ? 0 : S[cur ^ 1], add, e->qkv.ptr());
-            uzu_fused_linear_encode(cmd, &fq);
+            if (A.has_gate) mixer_in_linear(A.gate, e->gate.ptr());
+            mixer_in_linear(A.qkv, e->qkv.ptr());
             const uint32_t total_heads = Hq + 2 * Hkv;
             auto qkn = [&](const Norm& n, uint32_t off, uint32_t cnt) {
                 if (!n.present || cnt == 0) return;
@@ -1083,18 +1110,18 @@ static void encode_decoder_fused(uzu_engine* e, uzu_command_buffer* cmd, const P
             aa.scale = A.has_scale ? A.scale : 1.0f / sqrtf((float)D);
             aa.num_heads = Hq; aa.suffix_length = 1; aa.head_dim = D; aa.is_causal = A.is_causal; aa.dynamic_position = dyn;
             uzu_attention_single_pass_encode(cmd, &aa);
-            if (A.has_gate) {
+            if (A.has_gate && fuse_sigmoid) {
                 uzu_fused_linear_args g{};
                 g.matmul = linear_args(A.out, 0, 1, e->mixer_out.ptr());
                 g.prologue = 3; g.sg_attn = e->attn_out.ptr(); g.sg_gate = e->gate.ptr();
                 uzu_fused_linear_encode(cmd, &g);
             } else {
+                if (A.has_gate) uzu_sigmoid_gate_encode(cmd, e->gate.ptr(), e->attn_out.ptr(), Hq * D);
                 encode_linear(cmd, A.out, e->attn_out.ptr(), 1, e->mixer_out.ptr());
             }
         } else {
             const DeltaNetLayer& Dn = L.dn;
-            auto f = fused_norm_args(Dn.in_proj, L.pre_mixer, e->hidden_a.ptr(), S[cur], S[cur ^ 1], add, e->in_proj.ptr());
-            uzu_fused_linear_encode(cmd, &f);
+            mixer_in_linear(Dn.in_proj, e->in_proj.ptr());
             uzu_delta_net_conv_update_args ca{};
             ca.conv_weight = Dn.conv_weight.ptr(); ca.bias = Dn.conv_bias.ptr(); ca.in_out = e->in_proj.ptr(); ca.state = St.conv_state.ptr();
             ca.kernel_size = Dn.kernel_size; ca.conv_dim = Dn.conv_dim; ca.state_stride = Dn.kernel_size - 1; ca.has_bias = Dn.conv_has_bias;
@@ -1107,14 +1134,23 @@ static void encode_decoder_fused(uzu_engine* e, uzu_command_buffer* cmd, const P
             uzu_delta_net_update_encode(cmd, &ua);
             encode_linear(cmd, Dn.out_proj, e->delta_out.ptr(), 1, e->mixer_out.ptr());
         }
-        cur ^= 1;
-        auto fu = fused_norm_args(L.up, L.pre_mlp, e->mixer_out.ptr(), S[cur], S[cur ^ 1], true, e->fused_up.ptr());
-        uzu_fused_linear_encode(cmd, &fu);
-        cur ^= 1;
-        uzu_fused_linear_args fd{};
-        fd.matmul = linear_args(L.down, 0, 1, e->hidden_a.ptr());
-        fd.prologue = 2; fd.act_operand = e->fused_up.ptr(); fd.act_type = L.act;
-        uzu_fused_linear_encode(cmd, &fd);
+        if (fuse_norm) cur ^= 1;
+        // pre_mlp_norm + DenseMlp (mlp/dense.rs:32-48)
+        if (!fuse_norm) encode_norm(cmd, L.pre_mlp, e->mixer_out.ptr(), e->hidden_b.ptr(), S[cur], ShortcutAdd, 1);
+        if (fuse_norm || fuse_gated) {
+            auto fu = fused_up_args(e, L, fuse_norm, S[cur], S[cur ^ 1]);
+            uzu_fused_linear_encode(cmd, &fu);
+        } else {
+            encode_linear(cmd, L.up, e->hidden_b.ptr(), 1, e->fused_up.ptr());
+        }
+        if (fuse_norm) cur ^= 1;
+        if (!fuse_gated) {
+            uzu_gated_act_mul_args ga{};
+            ga.act_operand = e->fused_up.ptr(); ga.fp_out = e->gated.ptr(); ga.gated_dim = L.hidden_dim; ga.batch_dim = 1;
+            ga.act_type = L.act; ga.interleaved = 1;
+            uzu_gated_act_mul_encode(cmd, &ga);
+        }
+        encode_linear(cmd, L.down, e->gated.ptr(), 1, e->hidden_a.ptr());
     }
     // output norm with the residual add in place on the current residual buffer (transformer.rs:317-323), readout, logit transform
     encode_norm(cmd, e->out_norm, e->hidden_a.ptr(), e->normed_out.ptr(), S[cur], ShortcutAdd, 1);
@@ -1497,28 +1533,39 @@ uzu_status uzu_engine_step_host(uzu_engine* e, uint32_t token_in, uint32_t* toke
     });
 }
 
-uzu_status uzu_engine_time_linears(uzu_engine* e, uint32_t iters, double* out_seconds, uint64_t* out_launches) {
+uzu_status uzu_engine_time_linears_select(uzu_engine* e, uint32_t iters, uint32_t select, double* out_seconds, uint64_t* out_launches) {
     UZU_ENGINE_TRY({
         cudaStream_t s = e->ctx->stream;
         CmdGuard g(e->ctx, "linears");
         g.c->state = uzu_command_buffer::Encoding;
+        g.c->use_pdl = e->use_pdl && !(select & 0x80000000u);   // bit 31: plain stream-ordered launches
         cudaEvent_t a, b;
         cudaEventCreate(&a);
         cudaEventCreate(&b);
         auto once = [&]() {
             for (auto& L : e->layers) {
-                if (L.is_attention) {
-                    if (L.attn.has_gate) encode_linear(g.c, L.attn.gate, e->hidden_b.ptr(), 1, e->gate.ptr());
-                    encode_linear(g.c, L.attn.qkv, e->hidden_b.ptr(), 1, e->qkv.ptr());
-                    encode_linear(g.c, L.attn.out, e->attn_out.ptr(), 1, e->mixer_out.ptr());
-                } else {
-                    encode_linear(g.c, L.dn.in_proj, e->hidden_b.ptr(), 1, e->in_proj.ptr());
-                    encode_linear(g.c, L.dn.out_proj, e->delta_out.ptr(), 1, e->mixer_out.ptr());
+                if (select & 1u) {
+                    if (L.is_attention) {
+                        if (L.attn.has_gate) encode_linear(g.c, L.attn.gate, e->hidden_b.ptr(), 1, e->gate.ptr());
+                        encode_linear(g.c, L.attn.qkv, e->hidden_b.ptr(), 1, e->qkv.ptr());
+                    } else {
+                        encode_linear(g.c, L.dn.in_proj, e->hidden_b.ptr(), 1, e->in_proj.ptr());
+                    }
                 }
-                encode_linear(g.c, L.up, e->hidden_b.ptr(), 1, e->fused_up.ptr());
-                encode_linear(g.c, L.down, e->gated.ptr(), 1, e->hidden_a.ptr());
+                if (select & 2u) {
+                    if (L.is_attention) encode_linear(g.c, L.attn.out, e->attn_out.ptr(), 1, e->mixer_out.ptr());
+                    else encode_linear(g.c, L.dn.out_proj, e->delta_out.ptr(), 1, e->mixer_out.ptr());
+                }
+                if (select & 4u) encode_linear(g.c, L.up, e->hidden_b.ptr(), 1, e->fused_up.ptr());
+                if (select & 32u) {
+                    uzu_fused_linear_args f{};
+                    f.matmul = linear_args(L.up, e->hidden_b.ptr(), 1, e->gated.ptr());
+                    f.epilogue = 1; f.act_type = L.act;
+                    uzu_fused_linear_encode(g.c, &f);
+                }
+                if (select & 8u) encode_linear(g.c, L.down, e->gated.ptr(), 1, e->hidden_a.ptr());
             }
-            encode_linear(g.c, e->out_emb, e->normed_out.ptr(), 1, e->logits.ptr());
+            if (select & 16u) encode_linear(g.c, e->out_emb, e->normed_out.ptr(), 1, e->logits.ptr());
         };
         once();   // warm-up
         cudaStreamSynchronize(s);
@@ -1535,6 +1582,10 @@ uzu_status uzu_engine_time_linears(uzu_engine* e, uint32_t iters, double* out_se
         if (out_seconds) *out_seconds = (double)ms * 1e-3;
         if (out_launches) *out_launches = g.c->launches - before;
     });
+}
+
+uzu_status uzu_engine_time_linears(uzu_engine* e, uint32_t iters, double* out_seconds, uint64_t* out_launches) {
+    return uzu_engine_time_linears_select(e, iters, 31u, out_seconds, out_launches);
 }
 
 }  // extern "C"

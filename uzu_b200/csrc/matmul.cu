@@ -59,6 +59,9 @@ struct QmvParams {
     const float* pro_scales;         // norm scales f32 [k]
     float pro_eps, pro_scale_offset;
     uint32_t pro_residual_add, pro_full_layer, pro_act;
+    // fused epilogue (decode kernel): rows [0, F) are `up`, rows [F, 2F) are `gate`; a CTA walks tile i then tile i + F/16 and
+    // writes hidden[j] = bf16(bf16(up_j) * bf16(act(bf16(gate_j)))) (GatedActMul, gated_act_mul/mod.rs:5-12) instead of the 2F row
+    uint32_t epi_gated, epi_act, pair_tiles;
     uint32_t method;           // uzu_quantization_method
     uint32_t bits;
     uint32_t xor_mask;         // signed_codes
@@ -1096,7 +1099,7 @@ __global__ void __launch_bounds__(QS_WARPS * 32, 4) qmv_decode_kernel(const QmvP
 // registers can hold ~8 KB per warp, the ring holds QA_STAGES-1 x 4.5 KB per warp with no register cost,
 // each lane consuming exactly the bytes it copied (no cross-thread synchronisation on the ring).
 // -------------------------------------------------------------------------------------------------
-constexpr int QA_STAGES = 3;
+constexpr int QA_STAGES = 2;
 constexpr uint32_t QA_STAGE_BYTES = 4096 + 512;
 
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
@@ -1109,7 +1112,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-template <int NPG>
+template <int NPG, int STAGES>
 __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const QmvParams p) {
     static_assert(NPG == 64 || NPG == 128, "decode kernel covers int4 gs64 / gs128 and int8 gs64");
     constexpr int CPM = NPG >= 128 ? 1 : 2;
@@ -1123,11 +1126,11 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
     uint4* xs = reinterpret_cast<uint4*>(smem_raw);                            // [row_items] + one zero block of 4 x uint4
     float* sx = reinterpret_cast<float*>(smem_raw + (size_t)(row_items + 4) * 16);   // [ngroups]
     float* red = sx + ((ngroups + 3u) & ~3u);      // [2][QS_WARPS][16]
-    // per-warp cp.async ring: QA_STAGES x ([8 vectors][32 lanes] uint4 weights + [4 words][32 lanes] u32 scale / zero-point words)
-    uint8_t* ring_base = reinterpret_cast<uint8_t*>(red + 2 * QS_WARPS * 16) + (size_t)warp * QA_STAGES * QA_STAGE_BYTES;
+    // per-warp cp.async ring: STAGES x ([8 vectors][32 lanes] uint4 weights + [4 words][32 lanes] u32 scale / zero-point words)
+    uint8_t* ring_base = reinterpret_cast<uint8_t*>(red + 2 * QS_WARPS * 16) + (size_t)warp * STAGES * QA_STAGE_BYTES;
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring_base);
     // fused prologue: the produced activation row (bf16 [k]) lives after the rings
-    __nv_bfloat16* xrow = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(red + 2 * QS_WARPS * 16) + (size_t)QS_WARPS * QA_STAGES * QA_STAGE_BYTES);
+    __nv_bfloat16* xrow = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(red + 2 * QS_WARPS * 16) + (size_t)QS_WARPS * STAGES * QA_STAGE_BYTES);
     uint32_t magic;
     asm volatile("mov.b32 %0, 0x43004300;" : "=r"(magic));
 
@@ -1201,16 +1204,28 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
     const uint32_t WPT = p.warps_per_tile, TPC = QS_WARPS / WPT;
     const uint32_t tile_local = warp / WPT, kpart = warp % WPT;
     const uint32_t tiles = (p.n + 15u) / 16u;
-    const uint32_t tile_groups = (tiles + TPC - 1) / TPC;
+    // paired mode (GatedActMul epilogue; host guarantees kslices == 1 and WPT <= 2): the first TPC/2 tiles of a CTA item are
+    // `up` tiles q, the other TPC/2 the matching `gate` tiles q + F/16, so both halves of an output row finish in the same CTA
+    const bool paired = p.epi_gated != 0;
+    const uint32_t hp = TPC / 2u;
+    const uint32_t tile_groups = paired ? (p.pair_tiles + hp - 1) / hp : (tiles + TPC - 1) / TPC;
     const uint32_t items_cta = tile_groups * p.kslices;
+    const uint32_t item_first = blockIdx.x;
+    auto next_item = [&](uint32_t it_) { return it_ + gridDim.x; };
 
     auto setup_cta = [&](Item& it, uint32_t item) {
+        if (paired) {
+            const uint32_t base = item * hp + tile_local % hp;
+            setup(it, min(base, p.pair_tiles - 1u) + (tile_local / hp) * p.pair_tiles);
+            if (base >= p.pair_tiles) it.tile = 0xffffffffu;
+            return;
+        }
         const uint32_t tg = item / p.kslices;
         setup(it, (tg * TPC + tile_local) * p.kslices + item % p.kslices);
     };
     auto first_sc = [&](const Item& it) { return it.cb + kpart * 4u; };
 
-    // Two cursors walk this warp's stages (item ascending, super-chunk ascending): `ic` issues cp.async stages QA_STAGES-1
+    // Two cursors walk this warp's stages (item ascending, super-chunk ascending): `ic` issues cp.async stages STAGES-1
     // ahead of `cur`, the one being consumed, across item boundaries. The weights do not depend on the previous kernel, so
     // the first stages are requested before waiting on the producer of the activations (programmatic dependent launch).
     struct Cursor { uint32_t item, c0; Item it; };
@@ -1220,22 +1235,27 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
     };
     auto cursor_has = [&](const Cursor& c) { return c.item < items_cta && c.it.tile < tiles && c.c0 < c.it.ce; };
     Cursor ic;
-    cursor_begin(ic, blockIdx.x);
+    cursor_begin(ic, item_first);
     uint32_t issued = 0;
     auto issue_next = [&]() {
-        while (ic.item < items_cta && !cursor_has(ic)) cursor_begin(ic, ic.item + gridDim.x);
+        while (ic.item < items_cta && !cursor_has(ic)) cursor_begin(ic, next_item(ic.item));
         if (ic.item < items_cta) {
-            issue_stage(ic.it, ic.c0, issued % QA_STAGES);
+            issue_stage(ic.it, ic.c0, issued % STAGES);
             ic.c0 += 4u * WPT;
         }
-        cp_async_commit();       // always commit (possibly empty) so wait_group<QA_STAGES-2> means "oldest stage landed"
+        cp_async_commit();       // always commit (possibly empty) so wait_group<STAGES-1> means "oldest stage landed"
         ++issued;
     };
 #pragma unroll
-    for (int s_ = 0; s_ < QA_STAGES - 1; ++s_) issue_next();
+    for (int s_ = 0; s_ < STAGES - 1; ++s_) issue_next();
     Item cur;
-    uint32_t item = blockIdx.x;
+    uint32_t item = item_first;
     uint32_t consumed = 0;
+    if (p.prologue == 1) {
+        // the norm scales are static weights: pull them towards L2 while the producer of the activations is still running
+        for (uint32_t line = blockIdx.x * blockDim.x + tid; line < p.k / 32u; line += gridDim.x * blockDim.x)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pro_scales + (size_t)line * 32));
+    }
     pdl_launch_dependents();
     pdl_wait();
     if (tid < 4) xs[row_items + tid] = make_uint4(0, 0, 0, 0);
@@ -1345,8 +1365,8 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
                     for (int e = 0; e < 4; ++e) {
                         float m0, m1;
                         if (p.prologue == 2) {
-                            m0 = __bfloat162float(__float2bfloat16_rn(act_f32(p.pro_act, __low2float(g2[e]))));
-                            m1 = __bfloat162float(__float2bfloat16_rn(act_f32(p.pro_act, __high2float(g2[e]))));
+                            m0 = __bfloat162float(__float2bfloat16_rn(act_f32_nofma(p.pro_act, __low2float(g2[e]))));
+                            m1 = __bfloat162float(__float2bfloat16_rn(act_f32_nofma(p.pro_act, __high2float(g2[e]))));
                         } else {
                             m0 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-__low2float(g2[e]))));
                             m1 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-__high2float(g2[e]))));
@@ -1419,7 +1439,7 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
     __syncthreads();
 
     uint32_t parity = 0;
-    for (; item < items_cta; item += gridDim.x, parity ^= 1u) {
+    for (; item < items_cta; item = next_item(item), parity ^= 1u) {
         setup_cta(cur, item);
         const uint32_t tile = cur.tile, slice = cur.slice, ce = cur.ce;
         const uint32_t step = 4u * WPT;
@@ -1499,10 +1519,12 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
 
         if (tile < tiles) {
             for (uint32_t c0 = first_sc(cur); c0 < ce; c0 += step) {
-                cp_async_wait<QA_STAGES - 2>();
-                compute(consumed % QA_STAGES, c0);
-                ++consumed;
+                // refill the slot consumed last iteration first (each lane only ever reads back its own cp.async bytes, so
+                // there is no cross-lane hazard), then wait until the oldest of the STAGES outstanding stages has landed
                 issue_next();
+                cp_async_wait<STAGES - 1>();
+                compute(consumed % STAGES, c0);
+                ++consumed;
             }
         }
 
@@ -1513,7 +1535,7 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
         ra += __shfl_xor_sync(0xffffffffu, ra, 2);
         rb += __shfl_xor_sync(0xffffffffu, rb, 2);
         float* redp = red + parity * (QS_WARPS * 16);
-        if (WPT > 1) {
+        if (WPT > 1 || paired) {
             if (t == 0) {
                 redp[warp * 16 + g] = ra;
                 redp[warp * 16 + g + 8] = rb;
@@ -1529,7 +1551,25 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
             if (p.d_is_f32) reinterpret_cast<float*>(p.d)[row] = value;
             else reinterpret_cast<__nv_bfloat16*>(p.d)[row] = __float2bfloat16_rn(value);
         };
-        if (WPT == 1) {
+        if (paired) {
+            // warp f < TPC/2 finishes pair f: matmul outputs rounded to bf16 (+ bias) exactly as the unfused GEMV stores them,
+            // then GatedActMul's two roundings (gated_act_mul/mod.rs:5-12)
+            const uint32_t my_pair = item * hp + warp;
+            if (warp < hp && my_pair < p.pair_tiles && lane < 16) {
+                float up = 0.0f, gate = 0.0f;
+                for (uint32_t kp = 0; kp < WPT; ++kp) {
+                    up += redp[(warp * WPT + kp) * 16 + lane];
+                    gate += redp[((warp + hp) * WPT + kp) * 16 + lane];
+                }
+                const uint32_t row = my_pair * 16u + lane;
+                up = p.ab_scale * up; gate = p.ab_scale * gate;
+                if (p.bias) { up += __bfloat162float(p.bias[row]); gate += __bfloat162float(p.bias[row + p.pair_tiles * 16u]); }
+                up = __bfloat162float(__float2bfloat16_rn(up));
+                gate = __bfloat162float(__float2bfloat16_rn(gate));
+                const float m_ = __bfloat162float(__float2bfloat16_rn(act_f32_nofma(p.epi_act, gate)));
+                reinterpret_cast<__nv_bfloat16*>(p.d)[row] = __float2bfloat16_rn(__fmul_rn(up, m_));
+            }
+        } else if (WPT == 1) {
             // every warp owns a whole tile: finish it from registers, no CTA-level synchronisation at all
             if (tile < tiles) {
                 if (p.kslices == 1) {
@@ -1725,15 +1765,27 @@ static void launch_qmv_decode(uzu_command_buffer* cmd, const QmvParams& p, uint3
     launch(cmd, "qmv_decode_kernel", qmv_decode_kernel<NPG>, dim3(grid), dim3(QS_WARPS * 32), smem, p);
 }
 
-template <int NPG>
-static void launch_qmv_decode_async(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
+template <int NPG, int STAGES>
+static void launch_qmv_decode_async_s(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(qmv_decode_async_kernel<NPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(qmv_decode_async_kernel<NPG, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    launch(cmd, "qmv_decode_async_kernel", qmv_decode_async_kernel<NPG>, dim3(grid), dim3(QS_WARPS * 32), smem, p);
+    launch(cmd, "qmv_decode_async_kernel", qmv_decode_async_kernel<NPG, STAGES>, dim3(grid), dim3(QS_WARPS * 32), smem, p);
 }
+template <int NPG>
+static void launch_qmv_decode_async(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem, int stages) {
+    switch (stages) {
+        case 2: launch_qmv_decode_async_s<NPG, 2>(cmd, p, grid, smem); break;
+        case 4: launch_qmv_decode_async_s<NPG, 4>(cmd, p, grid, smem); break;
+        default: launch_qmv_decode_async_s<NPG, 3>(cmd, p, grid, smem); break;
+    }
+}
+
+// Tuning overrides for sweeps (0 = heuristic). Not part of the reference-facing API; set through uzu_debug_set_qmv_tuning.
+struct QmvTuning { int wpt = 0, dks = 0, per_sm = 0, stages = 0; };
+static QmvTuning g_tune;
 
 template <int NPG, int MT>
 static void launch_qmv_stream(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
@@ -1863,23 +1915,47 @@ static bool encode_matmul(uzu_command_buffer* cmd, uzu_context* ctx_for_query, c
                     dsc *= 2;
                     dks = (scs + dsc - 1) / dsc;
                 }
+                const bool want_paired = fused && fused->epilogue == 1;
+                if (g_tune.dks > 0 && !want_paired) {
+                    dks = std::min((uint32_t)g_tune.dks, scs);
+                    dsc = (scs + dks - 1) / dks;
+                    dks = (scs + dsc - 1) / dsc;
+                    if ((size_t)tiles * dks * 16 * 4 > ctx->splitk_ws_bytes || tiles > ctx->splitk_counter_count) { dks = 1; dsc = scs; }
+                }
                 uint32_t wpt = dsc >= 4 ? 4u : (dsc >= 2 ? 2u : 1u);
                 // plenty of row tiles: give every warp whole rows (no cross-warp reduction, no CTA sync); else split k in the CTA
                 const uint32_t resident_warps = 4u * 3u * (uint32_t)ctx->sm_count;
                 if (tiles >= 2u * resident_warps) wpt = 1;
                 else if (tiles * 2u >= 2u * resident_warps && wpt > 2) wpt = 2;
+                if (g_tune.wpt > 0) wpt = std::min((uint32_t)g_tune.wpt, dsc >= 4 ? 4u : (dsc >= 2 ? 2u : 1u));
+                const int stages = g_tune.stages >= 2 && g_tune.stages <= 4 ? g_tune.stages : QA_STAGES;
+                const uint32_t per_sm_cap = g_tune.per_sm > 0 ? (uint32_t)g_tune.per_sm : 4u;
                 const uint32_t tgroups = (tiles + (4 / wpt) - 1) / (4 / wpt);
                 p.chunks_per_slice = dsc * QS_SC;
                 p.kslices = dks;
                 p.warps_per_tile = wpt;
                 const size_t dsmem = stream_smem + 2 * QS_WARPS * 16 * 4 + 64;
                 static const bool use_regs = getenv("UZU_QMV_REGS") != nullptr;
-                const size_t asmem = dsmem + (size_t)QS_WARPS * QA_STAGES * QA_STAGE_BYTES;
-                const size_t fsmem = asmem + (fused ? (size_t)a.k * 2 + 64 : 0);
+                const size_t asmem = dsmem + (size_t)QS_WARPS * stages * QA_STAGE_BYTES;
+                const size_t fsmem = asmem + (fused && fused->prologue ? (size_t)a.k * 2 + 64 : 0);
                 if (fused) {
                     if (fsmem > 200u * 1024u || (a.k % 8) != 0) return false;
+                    uint32_t pair_groups = 0;
+                    if (fused->epilogue == 1) {
+                        // gated-act epilogue: rows [0,F) up, [F,2F) gate; every CTA owns whole pairs, so no global k split
+                        if ((a.n & 1u) || ((a.n / 2) % 16u) != 0 || a.output_dt != UZU_DT_BF16 || (a.d_transform & (UZU_D_ACCUMULATE | UZU_D_SOFT_CAP))) return false;
+                        dks = 1; dsc = scs;
+                        // both halves of a pair meet in one CTA: at most 2 warps per tile (TPC >= 2)
+                        wpt = dsc >= 2 ? 2u : 1u;
+                        if (tiles >= 2u * resident_warps) wpt = 1;
+                        if (g_tune.wpt > 0) wpt = std::min((uint32_t)g_tune.wpt, dsc >= 2 ? 2u : 1u);
+                        p.chunks_per_slice = dsc * QS_SC; p.kslices = 1; p.warps_per_tile = wpt;
+                        p.epi_gated = 1; p.epi_act = fused->act_type; p.pair_tiles = a.n / 32u;
+                        pair_groups = (p.pair_tiles + (2 / wpt) - 1) / (2 / wpt);
+                    } else if (fused->epilogue != 0) return false;
                     if (dry_run) return true;
                     p.prologue = fused->prologue;
+                    if (fused->prologue == 0) p.x = (const __nv_bfloat16*)a.a;
                     if (fused->prologue == 1) {
                         p.pro_a = (const __nv_bfloat16*)fused->norm_input;
                         p.pro_b = (const __nv_bfloat16*)fused->norm_shortcut_in;
@@ -1890,25 +1966,25 @@ static bool encode_matmul(uzu_command_buffer* cmd, uzu_context* ctx_for_query, c
                     } else if (fused->prologue == 2) {
                         p.pro_a = (const __nv_bfloat16*)fused->act_operand;
                         p.pro_act = fused->act_type;
-                    } else {
+                    } else if (fused->prologue == 3) {
                         p.pro_a = (const __nv_bfloat16*)fused->sg_attn;
                         p.pro_b = (const __nv_bfloat16*)fused->sg_gate;
                     }
-                    const uint32_t per_sm = std::max(1u, std::min(4u, (uint32_t)((220u * 1024u) / (fsmem + 1024u))));
-                    const uint32_t aitems = std::max(1u, tgroups * dks), amax = per_sm * (uint32_t)ctx->sm_count;
+                    const uint32_t per_sm = std::max(1u, std::min(per_sm_cap, (uint32_t)((220u * 1024u) / (fsmem + 1024u))));
+                    const uint32_t aitems = pair_groups ? pair_groups : std::max(1u, tgroups * dks), amax = per_sm * (uint32_t)ctx->sm_count;
                     const uint32_t rounds = (aitems + amax - 1) / amax;
                     const uint32_t agrid = (aitems + rounds - 1) / rounds;
-                    if (npg == 64) launch_qmv_decode_async<64>(cmd, p, agrid, fsmem);
-                    else launch_qmv_decode_async<128>(cmd, p, agrid, fsmem);
+                    if (npg == 64) launch_qmv_decode_async<64>(cmd, p, agrid, fsmem, stages);
+                    else launch_qmv_decode_async<128>(cmd, p, agrid, fsmem, stages);
                     return true;
                 }
                 if (!use_regs && asmem <= 200u * 1024u) {
-                    const uint32_t per_sm = std::max(1u, std::min(4u, (uint32_t)((220u * 1024u) / (asmem + 1024u))));
+                    const uint32_t per_sm = std::max(1u, std::min(per_sm_cap, (uint32_t)((220u * 1024u) / (asmem + 1024u))));
                     const uint32_t aitems = std::max(1u, tgroups * dks), amax = per_sm * (uint32_t)ctx->sm_count;
                     const uint32_t rounds = (aitems + amax - 1) / amax;
                     const uint32_t agrid = (aitems + rounds - 1) / rounds;     // same number of items for (almost) every CTA
-                    if (npg == 64) launch_qmv_decode_async<64>(cmd, p, agrid, asmem);
-                    else launch_qmv_decode_async<128>(cmd, p, agrid, asmem);
+                    if (npg == 64) launch_qmv_decode_async<64>(cmd, p, agrid, asmem, stages);
+                    else launch_qmv_decode_async<128>(cmd, p, agrid, asmem, stages);
                     continue;
                 }
                 const uint32_t dgrid = std::min(std::min(grid, 4u * (uint32_t)ctx->sm_count), std::max(1u, tgroups * dks));   // 128 regs -> 4 CTAs / SM
@@ -2007,6 +2083,10 @@ void uzu_matmul_encode(uzu_command_buffer* cmd, const uzu_matmul_args* args) {
     uzu::encode_matmul(cmd, cmd->ctx, *args);
 }
 
+void uzu_debug_set_qmv_tuning(int warps_per_tile, int k_slices, int ctas_per_sm, int stages) {
+    uzu::g_tune.wpt = warps_per_tile; uzu::g_tune.dks = k_slices; uzu::g_tune.per_sm = ctas_per_sm; uzu::g_tune.stages = stages;
+}
+
 int uzu_fused_linear_supported(uzu_context* ctx, const uzu_fused_linear_args* args) {
     if (!ctx || !args || uzu::validate(&args->matmul)) {
         // validate() wants matmul.a non-null; the fused path ignores it, so tolerate a == 0 here
@@ -2015,13 +2095,14 @@ int uzu_fused_linear_supported(uzu_context* ctx, const uzu_fused_linear_args* ar
         if (!m.a) m.a = m.d;
         if (uzu::validate(&m)) return 0;
     }
-    if (args->prologue < 1 || args->prologue > 3) return 0;
+    if (args->prologue > 3 || args->epilogue > 1 || (args->prologue == 0 && args->epilogue == 0)) return 0;
+    if (args->prologue == 0 && !args->matmul.a) return 0;
     if (args->prologue == 1 && (!args->norm_input || !args->norm_scales || (args->norm_residual_add && !args->norm_shortcut_in) ||
                                 (args->shortcut_out && args->shortcut_out == args->norm_shortcut_in))) return 0;
     if (args->prologue == 2 && !args->act_operand) return 0;
     if (args->prologue == 3 && (!args->sg_attn || !args->sg_gate)) return 0;
     uzu_matmul_args m = args->matmul;
-    m.a = 0;
+    if (args->prologue != 0) m.a = 0;
     return uzu::encode_matmul(nullptr, ctx, m, args, true) ? 1 : 0;
 }
 
@@ -2032,7 +2113,7 @@ void uzu_fused_linear_encode(uzu_command_buffer* cmd, const uzu_fused_linear_arg
         return;
     }
     uzu_matmul_args m = args->matmul;
-    m.a = 0;
+    if (args->prologue != 0) m.a = 0;
     uzu::encode_matmul(cmd, cmd->ctx, m, args, false);
 }
 
