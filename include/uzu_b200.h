@@ -179,7 +179,7 @@ UZU_API uzu_status uzu_matmul_validate(const uzu_matmul_args* args);   /* Matmul
 /* Fused decode linear (extension; m = 1): Matmul whose activation row is produced inside the GEMV, replacing a separate launch of
  *   prologue 1: NormalizationKernel (RMS norm, optional residual add; the updated residual goes to `shortcut_out`, which must differ
  *               from `norm_shortcut_in`; 0 = do not write, for a second linear sharing the same norm),
- *   prologue 2: GatedActMulKernel (interleaved [value | gate] row of length 2k in `act_operand`),
+ *   prologue 2: reserved (GatedActMul moved to the producing GEMV's epilogue, see `epilogue`),
  *   prologue 3: SigmoidGateKernel (x = attn * sigmoid(gate)),
  *   prologue 0: x = matmul.a (only meaningful together with an epilogue).
  * Same arithmetic and rounding points as the standalone kernels. uzu_fused_linear_supported() tells whether the fast path applies;
@@ -423,7 +423,8 @@ UZU_API uzu_status uzu_engine_decode_timed(uzu_engine* e, uint32_t steps, double
 UZU_API uzu_status uzu_engine_step_host(uzu_engine* e, uint32_t token_in, uint32_t* token_out);
 UZU_API uzu_status uzu_engine_time_linears(uzu_engine* e, uint32_t iters, double* out_seconds, uint64_t* out_launches);
 /* same, restricted to a subset: bit 0 mixer input projections (qkv / gate / in_proj), 1 mixer output projection, 2 MLP up, 3 MLP down,
- * 4 readout, 5 MLP up with the GatedActMul epilogue */
+ * 4 readout, 5 MLP up with the GatedActMul epilogue, 6 attention mix (q/k norm, RoPE + KV append, attention core, gate) at the
+ * current context length, 7 DeltaNet conv + state update; bit 31: plain stream-ordered launches (no programmatic dependent launch) */
 UZU_API uzu_status uzu_engine_time_linears_select(uzu_engine* e, uint32_t iters, uint32_t select, double* out_seconds, uint64_t* out_launches);
 
 #ifdef __cplusplus

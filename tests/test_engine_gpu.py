@@ -214,11 +214,6 @@ def test_fused_linear_kernel_vs_oracle(ctx):
         x = O.normalization(inp, scales, shortcut=sc_ref, residual_add=True, epsilon=1e-6, scale_offset=1.0, full_layer=full_layer)
         assert (b_scout.numpy(np.uint16, (1, k)) == sc_ref).all()
         assert_f32_close(got, ref_mm(x), rtol=2e-3, atol=2e-3, what="fused norm")
-    # 2) gated act: x = up * silu(gate) from the interleaved [value | gate] row
-    up = f32_to_bf16(rng.standard_normal((1, 2 * k)).astype(np.float32) * 2)
-    b_up = ctx.upload(up)
-    got = mm(2, act_operand=b_up.ptr, act_type=B.ACT_SILU)
-    assert_f32_close(got, ref_mm(O.gated_act_mul(up, k)), rtol=2e-3, atol=2e-3, what="fused gated act")
     # 3) sigmoid gate
     attn = f32_to_bf16(rng.standard_normal((1, k)).astype(np.float32)); gate = f32_to_bf16(rng.standard_normal((1, k)).astype(np.float32) * 3)
     b_attn, b_gate = ctx.upload(attn), ctx.upload(gate)

@@ -113,7 +113,7 @@ __device__ __forceinline__ float safe_exp_diff(float m, float gm) { return (m ==
 
 constexpr int ATTN_WARPS = 4;
 constexpr int ATTN_CHUNK = 512;     // keys whose scores live in shared memory at once
-constexpr int ATTN_UNROLL = 4;      // key rows in flight per lane group
+constexpr int ATTN_UNROLL = 2;      // key rows per lane group per round (one more round is always in flight)
 
 // Split-KV attention for short suffixes (decode) and, with nsplits = 1, for any suffix. One CTA = (G query heads sharing a KV
 // head, one query token, one key range). Per chunk of <= ATTN_CHUNK keys: (1) scores q.k for all keys of the chunk, K rows
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attn_split_kernel(const AttnP
     uint32_t keys_per_split = p.keys_per_split;
     if (a.dynamic_position) {
         a.sequence_length = *reinterpret_cast<const uint32_t*>(a.dynamic_position) + a.suffix_length;
-        keys_per_split = (a.sequence_length + p.nsplits - 1) / p.nsplits;
+        keys_per_split = ((a.sequence_length + p.nsplits - 1) / p.nsplits + 15u) & ~15u;   // whole CTA steps per split
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane / LPK, li = lane % LPK, d0 = li * EPL;
@@ -186,29 +186,43 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attn_split_kernel(const AttnP
         }
     }
 
+    // no ring / trie / window: every key below sequence_length is visible except the causal part of the suffix itself
+    const bool plain_mask = !a.is_kv_cache_ring && !a.is_trie && !a.is_sliding_window;
+    auto key_visible = [&](uint32_t i) {
+        if (plain_mask) return !(a.is_causal && i >= prefix_length && (i - prefix_length) > qs);
+        return should_use_key(a, qs, prefix_length, suffix_position, query_position, i);
+    };
+    // one round = U key rows per lane group; the rows of round r + 1 are requested before round r is consumed
+    auto load_round = [&](const __nv_bfloat16* base, uint32_t seq_stride, uint32_t cbeg, uint32_t n, uint32_t kb, bool masked,
+                          uint4 (&dst)[U][EPL / 8], bool (&ok)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t kl = kb + u * STEP + sub, i = cbeg + kl;
+            ok[u] = kl < n && (!masked || key_visible(i));
+#pragma unroll
+            for (int v = 0; v < EPL / 8; ++v)
+                dst[u][v] = ok[u] ? *reinterpret_cast<const uint4*>(base + (size_t)i * seq_stride + v * 8) : make_uint4(0, 0, 0, 0);
+        }
+    };
+
     const uint32_t begin = min(a.sequence_length, split * keys_per_split);
     const uint32_t end = min(a.sequence_length, begin + keys_per_split);
     for (uint32_t cbeg = begin; cbeg < end; cbeg += CH) {
         const uint32_t n = min((uint32_t)CH, end - cbeg);
+        uint4 cur[U][EPL / 8], nxt[U][EPL / 8];
+        bool okc[U], okn[U];
         // ---- (1) scores ------------------------------------------------------------------------------------
+        load_round(keys, a.k_seq_stride, cbeg, n, warp * KPW, true, cur, okc);
         for (uint32_t kb = warp * KPW; kb < n; kb += STEP * U) {
-            uint4 kr[U][EPL / 8];
-            bool ok[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t kl = kb + u * STEP + sub, i = cbeg + kl;
-                ok[u] = kl < n && should_use_key(a, qs, prefix_length, suffix_position, query_position, i);
-#pragma unroll
-                for (int v = 0; v < EPL / 8; ++v)
-                    kr[u][v] = ok[u] ? *reinterpret_cast<const uint4*>(keys + (size_t)i * a.k_seq_stride + v * 8) : make_uint4(0, 0, 0, 0);
-            }
+            const bool more = kb + STEP * U < n;
+            if (more) load_round(keys, a.k_seq_stride, cbeg, n, kb + STEP * U, true, nxt, okn);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const uint32_t kl = kb + u * STEP + sub;
                 float kf[EPL];
 #pragma unroll
                 for (int v = 0; v < EPL / 8; ++v) {
-                    const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kr[u][v]);
+                    const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&cur[u][v]);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) { kf[v * 8 + 2 * e] = __low2float(k2[e]); kf[v * 8 + 2 * e + 1] = __high2float(k2[e]); }
                 }
@@ -219,10 +233,20 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attn_split_kernel(const AttnP
                     for (int e = 0; e < EPL; ++e) sdot += q[h][e] * kf[e];
 #pragma unroll
                     for (int off = LPK / 2; off > 0; off >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, off);
-                    if (li == 0 && kl < n) sc[h][kl] = ok[u] ? sdot : -INFINITY;
+                    if (li == 0 && kl < n) sc[h][kl] = okc[u] ? sdot : -INFINITY;
+                }
+            }
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    okc[u] = okn[u];
+#pragma unroll
+                    for (int v = 0; v < EPL / 8; ++v) cur[u][v] = nxt[u][v];
                 }
             }
         }
+        // the first V rows travel while the chunk statistics are computed
+        load_round(values, a.v_seq_stride, cbeg, n, warp * KPW, false, cur, okc);
         __syncthreads();
         // ---- (2) chunk max, probabilities relative to the new running max, chunk sum (one warp per head) -----
 #pragma unroll
@@ -254,22 +278,16 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attn_split_kernel(const AttnP
         }
         // ---- (3) o += p . V ---------------------------------------------------------------------------------
         for (uint32_t kb = warp * KPW; kb < n; kb += STEP * U) {
-            uint4 vr[U][EPL / 8];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t kl = kb + u * STEP + sub, i = cbeg + kl;
-#pragma unroll
-                for (int v = 0; v < EPL / 8; ++v)
-                    vr[u][v] = kl < n ? *reinterpret_cast<const uint4*>(values + (size_t)i * a.v_seq_stride + v * 8) : make_uint4(0, 0, 0, 0);
-            }
+            const bool more = kb + STEP * U < n;
+            if (more) load_round(values, a.v_seq_stride, cbeg, n, kb + STEP * U, false, nxt, okn);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const uint32_t kl = kb + u * STEP + sub;
-                if (kl >= n) continue;
+                if (!okc[u]) continue;
                 float vf[EPL];
 #pragma unroll
                 for (int v = 0; v < EPL / 8; ++v) {
-                    const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vr[u][v]);
+                    const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&cur[u][v]);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) { vf[v * 8 + 2 * e] = __low2float(v2[e]); vf[v * 8 + 2 * e + 1] = __high2float(v2[e]); }
                 }
@@ -278,6 +296,14 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attn_split_kernel(const AttnP
                     const float pv = sc[h][kl];
 #pragma unroll
                     for (int e = 0; e < EPL; ++e) o[h][e] += pv * vf[e];
+                }
+            }
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    okc[u] = okn[u];
+#pragma unroll
+                    for (int v = 0; v < EPL / 8; ++v) cur[u][v] = nxt[u][v];
                 }
             }
         }
@@ -359,8 +385,11 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attn_split_kernel(const AttnP
         const size_t o_off = (size_t)qs * H + head0 + h;
         const float* po = p.part_o + (o_off * p.nb) * D + d;
         float val = 0.0f;
-#pragma unroll 8
-        for (uint32_t sp = 0; sp < p.nsplits; ++sp) val += __ldcg(po + (size_t)sp * D) * sc[h][sp];
+        float pv[32];                                   // all split partials of this output in flight at once
+#pragma unroll
+        for (uint32_t sp = 0; sp < 32; ++sp) pv[sp] = sp < p.nsplits ? __ldcg(po + (size_t)sp * D) : 0.0f;
+#pragma unroll
+        for (uint32_t sp = 0; sp < 32; ++sp) val += sp < p.nsplits ? pv[sp] * sc[h][sp] : 0.0f;
         p.final_out[o_off * D + d] = f2bf(val / sm_lfin[h]);
     }
     if (threadIdx.x == 0) p.counters[cidx] = 0;
@@ -520,7 +549,7 @@ void uzu_attention_single_pass_encode(uzu_command_buffer* cmd, const uzu_attenti
     p.fuse_merge = 1;
     p.nsplits = nsplits;
     p.nb = nsplits;
-    p.keys_per_split = (a->sequence_length + nsplits - 1) / nsplits;
+    p.keys_per_split = nsplits > 1 ? (((a->sequence_length + nsplits - 1) / nsplits + 15u) & ~15u) : a->sequence_length;
     if (nsplits > 1) {
         const size_t units = (size_t)a->suffix_length * a->num_heads * nsplits;
         const size_t need = units * (a->head_dim + 2) * sizeof(float);
@@ -568,7 +597,7 @@ void uzu_attention_two_pass1_encode(uzu_command_buffer* cmd, const uzu_attention
     p.fuse_merge = 0;
     p.nsplits = std::max(1u, std::min(std::min(want, cap), 32u));
     p.nb = 32;  // TOTAL_BLOCKS_COUNT (attention_two_pass.rs:10)
-    p.keys_per_split = (a->sequence_length + p.nsplits - 1) / p.nsplits;
+    p.keys_per_split = p.nsplits > 1 ? (((a->sequence_length + p.nsplits - 1) / p.nsplits + 15u) & ~15u) : a->sequence_length;
     uzu::dispatch_attn(cmd, p, g);
 }
 

@@ -839,13 +839,23 @@ struct PassCtx {
     bool dynamic = false;   // decode-graph mode: positions come from the device DecodeState
 };
 
+// q/k norms, RoPE + KV append, attention core, optional sigmoid gate: everything between the qkv and the out projections
+static void encode_attention_mix(uzu_engine* e, uzu_command_buffer* cmd, const Layer& L, LayerState& S, const PassCtx& pc, bool with_gate);
+
 static uint64_t encode_attention(uzu_engine* e, uzu_command_buffer* cmd, const Layer& L, LayerState& S, uint64_t hidden, const PassCtx& pc) {
+    const AttentionLayer& A = L.attn;
+    // gate projection first (mode.rs:54-61); `hidden` is not modified by our linears, so no copy is needed
+    if (A.has_gate) encode_linear(cmd, A.gate, hidden, pc.m, e->gate.ptr());
+    encode_linear(cmd, A.qkv, hidden, pc.m, e->qkv.ptr());
+    encode_attention_mix(e, cmd, L, S, pc, true);
+    encode_linear(cmd, A.out, e->attn_out.ptr(), pc.m, e->mixer_out.ptr());
+    return e->mixer_out.ptr();
+}
+
+static void encode_attention_mix(uzu_engine* e, uzu_command_buffer* cmd, const Layer& L, LayerState& S, const PassCtx& pc, bool with_gate) {
     const AttentionLayer& A = L.attn;
     const uint32_t m = pc.m, D = A.head_dim, Hq = A.num_heads, Hkv = A.num_groups;
     const uint64_t dyn = pc.dynamic ? e->decode_state.ptr() : 0;  // &DecodeState::position (first member)
-    // gate projection first (mode.rs:54-61); `hidden` is not modified by our linears, so no copy is needed
-    if (A.has_gate) encode_linear(cmd, A.gate, hidden, m, e->gate.ptr());
-    encode_linear(cmd, A.qkv, hidden, m, e->qkv.ptr());
     const uint32_t total_heads = Hq + 2 * Hkv;
     auto qkn = [&](const Norm& n, uint32_t off, uint32_t cnt) {
         if (!n.present || cnt == 0) return;
@@ -898,9 +908,7 @@ static uint64_t encode_attention(uzu_engine* e, uzu_command_buffer* cmd, const L
         aa.out = e->attn_out.ptr();
         uzu_attention_single_pass_encode(cmd, &aa);
     }
-    if (A.has_gate) uzu_sigmoid_gate_encode(cmd, e->gate.ptr(), e->attn_out.ptr(), m * Hq * D);
-    encode_linear(cmd, A.out, e->attn_out.ptr(), m, e->mixer_out.ptr());
-    return e->mixer_out.ptr();
+    if (A.has_gate && with_gate) uzu_sigmoid_gate_encode(cmd, e->gate.ptr(), e->attn_out.ptr(), m * Hq * D);
 }
 
 static uint64_t encode_delta_net(uzu_engine* e, uzu_command_buffer* cmd, const Layer& L, LayerState& S, uint64_t hidden, const PassCtx& pc) {
@@ -1539,6 +1547,7 @@ uzu_status uzu_engine_time_linears_select(uzu_engine* e, uint32_t iters, uint32_
         CmdGuard g(e->ctx, "linears");
         g.c->state = uzu_command_buffer::Encoding;
         g.c->use_pdl = e->use_pdl && !(select & 0x80000000u);   // bit 31: plain stream-ordered launches
+        if (select & 64u) state_prepare(e, e->context_length + 1);
         cudaEvent_t a, b;
         cudaEventCreate(&a);
         cudaEventCreate(&b);
@@ -1564,6 +1573,25 @@ uzu_status uzu_engine_time_linears_select(uzu_engine* e, uint32_t iters, uint32_
                     uzu_fused_linear_encode(g.c, &f);
                 }
                 if (select & 8u) encode_linear(g.c, L.down, e->gated.ptr(), 1, e->hidden_a.ptr());
+                if ((select & 64u) && L.is_attention) {     // attention mix at the current context (rewrites the same KV row each time)
+                    PassCtx pc{};
+                    pc.m = 1;
+                    encode_attention_mix(e, g.c, L, e->state[&L - &e->layers[0]], pc, true);
+                }
+                if ((select & 128u) && !L.is_attention) {   // DeltaNet conv + state update (advances the recurrent state)
+                    const DeltaNetLayer& D = L.dn;
+                    LayerState& S = e->state[&L - &e->layers[0]];
+                    uzu_delta_net_conv_update_args ca{};
+                    ca.conv_weight = D.conv_weight.ptr(); ca.bias = D.conv_bias.ptr(); ca.in_out = e->in_proj.ptr(); ca.state = S.conv_state.ptr();
+                    ca.kernel_size = D.kernel_size; ca.conv_dim = D.conv_dim; ca.state_stride = D.kernel_size - 1; ca.has_bias = D.conv_has_bias;
+                    uzu_delta_net_conv_update_encode(g.c, &ca);
+                    uzu_delta_net_update_args ua{};
+                    ua.in_proj = e->in_proj.ptr(); ua.a_log = D.a_log.ptr(); ua.dt_bias = D.dt_bias.ptr(); ua.norm_weight = D.norm_weight.ptr();
+                    ua.state = S.ssm_state.ptr(); ua.out = e->delta_out.ptr();
+                    ua.num_v_heads = D.num_heads; ua.num_k_heads = D.num_groups; ua.head_v_dim = D.value_head_dim; ua.key_dim = D.key_dim;
+                    ua.value_dim = D.value_dim; ua.norm_epsilon = D.norm_epsilon; ua.head_k_dim = D.head_dim;
+                    uzu_delta_net_update_encode(g.c, &ua);
+                }
             }
             if (select & 16u) encode_linear(g.c, e->out_emb, e->normed_out.ptr(), 1, e->logits.ptr());
         };

@@ -1112,8 +1112,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-template <int NPG, int STAGES>
+// METHOD / BITS / FUSED are compile-time so that the hot loop carries one dequantisation variant and the plain GEMV carries no
+// prologue / epilogue code: the first single-instance version was ~10.5 K SASS instructions and stalled mostly on instruction
+// fetch (ncu: no_instruction was the top stall at 1-2 warps per scheduler).
+// PRO: 0 none, 1 RMSNorm (+ residual add), 3 sigmoid gate (prologue 2, gated act, moved to the producer's epilogue); EPI: GatedActMul
+template <int NPG, int STAGES, int METHOD, int BITS, int PRO, bool EPI>
 __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const QmvParams p) {
+    constexpr uint32_t method = METHOD, bits = BITS;
     static_assert(NPG == 64 || NPG == 128, "decode kernel covers int4 gs64 / gs128 and int8 gs64");
     constexpr int CPM = NPG >= 128 ? 1 : 2;
     constexpr int GPS = 512 / NPG;    // groups per super-chunk: 8 or 4
@@ -1141,8 +1146,8 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
         const uint8_t *za_base, *zb_base;      // zero points (bytes) or MLX biases
         uint32_t za_off, zb_off;               // byte offset of this lane's first zero-point byte at super-chunk 0
     };
-    const float mult128 = p.bits == 4 ? 128.0f : 128.0f * 17.0f;
-    const float sym_mid = p.bits == 4 ? 8.0f : 128.0f;
+    const float mult128 = bits == 4 ? 128.0f : 128.0f * 17.0f;
+    const float sym_mid = bits == 4 ? 8.0f : 128.0f;
     const bool lane_has_groups = 2 * t < GPS;       // NPG = 128: only lanes t = 0, 1 own columns
     // which chunk of a super-chunk this lane feeds into the MMA B operand (column n = g)
     const int b_chunk = CPM == 2 ? (g >> 1) : g;
@@ -1158,18 +1163,18 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
         it.wb_base = p.w + (size_t)row_b * p.row_bytes + (size_t)t * 16;
         it.sa_base = p.scales + (size_t)row_a * ngroups + 2 * t;
         it.sb_base = p.scales + (size_t)row_b * ngroups + 2 * t;
-        if (p.method == UZU_QMETHOD_SCALE_BIAS) {
+        if (method == UZU_QMETHOD_SCALE_BIAS) {
             it.za_base = reinterpret_cast<const uint8_t*>(p.biases + (size_t)row_a * ngroups + 2 * t);
             it.zb_base = reinterpret_cast<const uint8_t*>(p.biases + (size_t)row_b * ngroups + 2 * t);
-        } else if (p.bits == 4) {
+        } else if (bits == 4) {
             it.za_base = p.zero_points + (size_t)row_a * p.zp_stride + t;
             it.zb_base = p.zero_points + (size_t)row_b * p.zp_stride + t;
         } else {
             it.za_base = p.zero_points + (size_t)row_a * p.zp_stride + 2 * t;
             it.zb_base = p.zero_points + (size_t)row_b * p.zp_stride + 2 * t;
         }
-        it.za_off = row_a * p.zp_stride + (p.bits == 4 ? t : 2 * t);
-        it.zb_off = row_b * p.zp_stride + (p.bits == 4 ? t : 2 * t);
+        it.za_off = row_a * p.zp_stride + (bits == 4 ? t : 2 * t);
+        it.zb_off = row_b * p.zp_stride + (bits == 4 ? t : 2 * t);
     };
     // one stage = one super-chunk of this warp: 8 x 16 B of packed weights per lane + its scale / zero-point words,
     // copied global -> shared with cp.async (no registers held while in flight)
@@ -1185,12 +1190,12 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
             const uint32_t gi = (c0 * 128u) / NPG;
             cp_async4(wbase, it.sa_base + gi);
             cp_async4(wbase + 128u, it.sb_base + gi);
-            if (p.method == UZU_QMETHOD_SCALE_ZERO_POINT) {
+            if (method == UZU_QMETHOD_SCALE_ZERO_POINT) {
                 // copy the aligned 32-bit word that holds this lane's zero-point byte(s); the consumer shifts them out
-                const uint32_t goff = p.bits == 4 ? gi / 2 : gi;
+                const uint32_t goff = bits == 4 ? gi / 2 : gi;
                 cp_async4(wbase + 256u, p.zero_points + ((it.za_off + goff) & ~3u));
                 cp_async4(wbase + 384u, p.zero_points + ((it.zb_off + goff) & ~3u));
-            } else if (p.method == UZU_QMETHOD_SCALE_BIAS) {
+            } else if (method == UZU_QMETHOD_SCALE_BIAS) {
                 cp_async4(wbase + 256u, it.za_base + (size_t)gi * 2);
                 cp_async4(wbase + 384u, it.zb_base + (size_t)gi * 2);
             }
@@ -1206,7 +1211,7 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
     const uint32_t tiles = (p.n + 15u) / 16u;
     // paired mode (GatedActMul epilogue; host guarantees kslices == 1 and WPT <= 2): the first TPC/2 tiles of a CTA item are
     // `up` tiles q, the other TPC/2 the matching `gate` tiles q + F/16, so both halves of an output row finish in the same CTA
-    const bool paired = p.epi_gated != 0;
+    constexpr bool paired = EPI;
     const uint32_t hp = TPC / 2u;
     const uint32_t tile_groups = paired ? (p.pair_tiles + hp - 1) / hp : (tiles + TPC - 1) / TPC;
     const uint32_t items_cta = tile_groups * p.kslices;
@@ -1251,7 +1256,7 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
     Item cur;
     uint32_t item = item_first;
     uint32_t consumed = 0;
-    if (p.prologue == 1) {
+    if (PRO == 1) {
         // the norm scales are static weights: pull them towards L2 while the producer of the activations is still running
         for (uint32_t line = blockIdx.x * blockDim.x + tid; line < p.k / 32u; line += gridDim.x * blockDim.x)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pro_scales + (size_t)line * 32));
@@ -1261,13 +1266,13 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
     if (tid < 4) xs[row_items + tid] = make_uint4(0, 0, 0, 0);
 
     const __nv_bfloat16* xsrc = p.x;
-    if (p.prologue != 0) {
+    if (PRO != 0) {
         // ---- fused prologue: every CTA recomputes the (tiny) activation row; same arithmetic and rounding points as the
         // standalone kernels (normalization.rs:50-125, gated_act_mul/mod.rs:5-12, sigmoid_gate.rs:7-22) -------------------------
         const uint32_t K = p.k;
-        constexpr int PB = 4;   // items (8 elements each) per thread per batch: all global loads of a batch are issued before use
+        constexpr int PB = 2;   // items (8 elements each) per thread per batch: all global loads of a batch are issued before use
         const uint32_t stride = blockDim.x * 8u;
-        if (p.prologue == 1) {
+        if (PRO == 1) {
             float ssq = 0.0f;
             for (uint32_t base = tid * 8u; base < K; base += stride * PB) {
                 uint4 va[PB], vb[PB];
@@ -1341,9 +1346,9 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
                 }
             }
         } else {
-            // prologue 2: x = value * act(gate) from [value | gate]; prologue 3: x = attn * sigmoid(gate)
+            // prologue 3: x = attn * sigmoid(gate)
             const __nv_bfloat16* pv = p.pro_a;
-            const __nv_bfloat16* pg = p.prologue == 2 ? p.pro_a + K : p.pro_b;
+            const __nv_bfloat16* pg = p.pro_b;
             for (uint32_t base = tid * 8u; base < K; base += stride * PB) {
                 uint4 vv[PB], vg[PB];
 #pragma unroll
@@ -1363,14 +1368,8 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
                     const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&vg[u]);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        float m0, m1;
-                        if (p.prologue == 2) {
-                            m0 = __bfloat162float(__float2bfloat16_rn(act_f32_nofma(p.pro_act, __low2float(g2[e]))));
-                            m1 = __bfloat162float(__float2bfloat16_rn(act_f32_nofma(p.pro_act, __high2float(g2[e]))));
-                        } else {
-                            m0 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-__low2float(g2[e]))));
-                            m1 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-__high2float(g2[e]))));
-                        }
+                        const float m0 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-__low2float(g2[e]))));
+                        const float m1 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-__high2float(g2[e]))));
                         v2[e] = __floats2bfloat162_rn(__fmul_rn(__low2float(v2[e]), m0), __fmul_rn(__high2float(v2[e]), m1));
                     }
                     *reinterpret_cast<uint4*>(xrow + i) = vv[u];
@@ -1392,7 +1391,7 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
                 const uint32_t pos = it * 8u;
                 v[u] = make_uint4(0, 0, 0, 0);
                 if (it < nc_all * 16u && pos < p.np) {
-                    if (p.bits == 4) v[u] = *reinterpret_cast<const uint4*>(xsrc + pos);
+                    if (bits == 4) v[u] = *reinterpret_cast<const uint4*>(xsrc + pos);
                     else {
                         const uint2 h = *reinterpret_cast<const uint2*>(xsrc + pos / 2);
                         v[u].x = h.x; v[u].y = h.y;
@@ -1406,7 +1405,7 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
                 const uint32_t pos = it * 8u;
                 uint4 out;
                 float part = 0.0f;
-                if (p.bits == 4) {
+                if (bits == 4) {
                     out.x = __byte_perm(v[u].x, v[u].z, 0x5410);
                     out.y = __byte_perm(v[u].x, v[u].z, 0x7632);
                     out.z = __byte_perm(v[u].y, v[u].w, 0x5410);
@@ -1480,16 +1479,16 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
                 const float2 sxv = *reinterpret_cast<const float2*>(sx + gi);
                 const uint32_t bsa = swd[0], bsb = swd[32];
                 uint32_t bca = swd[64], bcb = swd[96];
-                if (p.method == UZU_QMETHOD_SCALE_ZERO_POINT) {
-                    const uint32_t goff = p.bits == 4 ? ((c0 * 128u) / NPG) / 2 : (c0 * 128u) / NPG;
+                if (method == UZU_QMETHOD_SCALE_ZERO_POINT) {
+                    const uint32_t goff = bits == 4 ? ((c0 * 128u) / NPG) / 2 : (c0 * 128u) / NPG;
                     bca >>= ((cur.za_off + goff) & 3u) * 8u;
                     bcb >>= ((cur.zb_off + goff) & 3u) * 8u;
                 }
                 const float sa0 = __uint_as_float(bsa << 16), sa1 = __uint_as_float(bsa & 0xffff0000u);
                 const float sb0 = __uint_as_float(bsb << 16), sb1 = __uint_as_float(bsb & 0xffff0000u);
-                if (p.method == UZU_QMETHOD_SCALE_ZERO_POINT) {
+                if (method == UZU_QMETHOD_SCALE_ZERO_POINT) {
                     float ka0, ka1, kb0, kb1;   // value = s * (d + k * Sx)
-                    if (p.bits == 4) {
+                    if (bits == 4) {
                         ka0 = -((float)(bca & 15u) + mult128); ka1 = -((float)((bca >> 4) & 15u) + mult128);
                         kb0 = -((float)(bcb & 15u) + mult128); kb1 = -((float)((bcb >> 4) & 15u) + mult128);
                     } else {
@@ -1500,7 +1499,7 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
                     acc1 += sa1 * (d[1] + ka1 * sxv.y);
                     acc2 += sb0 * (d[2] + kb0 * sxv.x);
                     acc3 += sb1 * (d[3] + kb1 * sxv.y);
-                } else if (p.method == UZU_QMETHOD_SCALE_BIAS) {
+                } else if (method == UZU_QMETHOD_SCALE_BIAS) {
                     const float ba0 = __uint_as_float(bca << 16), ba1 = __uint_as_float(bca & 0xffff0000u);
                     const float bb0 = __uint_as_float(bcb << 16), bb1 = __uint_as_float(bcb & 0xffff0000u);
                     acc0 += sa0 * (d[0] - mult128 * sxv.x) + ba0 * sxv.x;
@@ -1765,26 +1764,47 @@ static void launch_qmv_decode(uzu_command_buffer* cmd, const QmvParams& p, uint3
     launch(cmd, "qmv_decode_kernel", qmv_decode_kernel<NPG>, dim3(grid), dim3(QS_WARPS * 32), smem, p);
 }
 
-template <int NPG, int STAGES>
-static void launch_qmv_decode_async_s(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
+template <int NPG, int METHOD, int BITS, int PRO, bool EPI>
+static void launch_qmv_decode_async_i(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(qmv_decode_async_kernel<NPG, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(qmv_decode_async_kernel<NPG, QA_STAGES, METHOD, BITS, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    launch(cmd, "qmv_decode_async_kernel", qmv_decode_async_kernel<NPG, STAGES>, dim3(grid), dim3(QS_WARPS * 32), smem, p);
+    launch(cmd, "qmv_decode_async_kernel", qmv_decode_async_kernel<NPG, QA_STAGES, METHOD, BITS, PRO, EPI>, dim3(grid), dim3(QS_WARPS * 32), smem, p);
+}
+template <int NPG, int PRO, bool EPI>
+static void launch_qmv_decode_async_f(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
+    if (p.bits == 4) {
+        switch (p.method) {
+            case UZU_QMETHOD_SCALE_ZERO_POINT: launch_qmv_decode_async_i<NPG, UZU_QMETHOD_SCALE_ZERO_POINT, 4, PRO, EPI>(cmd, p, grid, smem); break;
+            case UZU_QMETHOD_SCALE_BIAS: launch_qmv_decode_async_i<NPG, UZU_QMETHOD_SCALE_BIAS, 4, PRO, EPI>(cmd, p, grid, smem); break;
+            default: launch_qmv_decode_async_i<NPG, UZU_QMETHOD_SCALE_SYMMETRIC, 4, PRO, EPI>(cmd, p, grid, smem); break;
+        }
+    } else {
+        if constexpr (PRO == 0 && !EPI) {     // the fused variants are instantiated for 4-bit weights only (host: fused_linear_supported)
+            switch (p.method) {
+                case UZU_QMETHOD_SCALE_ZERO_POINT: launch_qmv_decode_async_i<NPG, UZU_QMETHOD_SCALE_ZERO_POINT, 8, 0, false>(cmd, p, grid, smem); break;
+                case UZU_QMETHOD_SCALE_BIAS: launch_qmv_decode_async_i<NPG, UZU_QMETHOD_SCALE_BIAS, 8, 0, false>(cmd, p, grid, smem); break;
+                default: launch_qmv_decode_async_i<NPG, UZU_QMETHOD_SCALE_SYMMETRIC, 8, 0, false>(cmd, p, grid, smem); break;
+            }
+        }
+    }
 }
 template <int NPG>
-static void launch_qmv_decode_async(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem, int stages) {
-    switch (stages) {
-        case 2: launch_qmv_decode_async_s<NPG, 2>(cmd, p, grid, smem); break;
-        case 4: launch_qmv_decode_async_s<NPG, 4>(cmd, p, grid, smem); break;
-        default: launch_qmv_decode_async_s<NPG, 3>(cmd, p, grid, smem); break;
+static void launch_qmv_decode_async(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
+    const uint32_t key = p.prologue * 2u + (p.epi_gated ? 1u : 0u);
+    switch (key) {
+        case 0: launch_qmv_decode_async_f<NPG, 0, false>(cmd, p, grid, smem); break;
+        case 1: launch_qmv_decode_async_f<NPG, 0, true>(cmd, p, grid, smem); break;
+        case 2: launch_qmv_decode_async_f<NPG, 1, false>(cmd, p, grid, smem); break;
+        case 3: launch_qmv_decode_async_f<NPG, 1, true>(cmd, p, grid, smem); break;
+        default: launch_qmv_decode_async_f<NPG, 3, false>(cmd, p, grid, smem); break;   // 6: sigmoid gate
     }
 }
 
 // Tuning overrides for sweeps (0 = heuristic). Not part of the reference-facing API; set through uzu_debug_set_qmv_tuning.
-struct QmvTuning { int wpt = 0, dks = 0, per_sm = 0, stages = 0; };
+struct QmvTuning { int wpt = 0, dks = 0, per_sm = 0, stages = 0; };   // `stages` is kept for ABI stability; the ring depth is fixed at QA_STAGES
 static QmvTuning g_tune;
 
 template <int NPG, int MT>
@@ -1928,7 +1948,7 @@ static bool encode_matmul(uzu_command_buffer* cmd, uzu_context* ctx_for_query, c
                 if (tiles >= 2u * resident_warps) wpt = 1;
                 else if (tiles * 2u >= 2u * resident_warps && wpt > 2) wpt = 2;
                 if (g_tune.wpt > 0) wpt = std::min((uint32_t)g_tune.wpt, dsc >= 4 ? 4u : (dsc >= 2 ? 2u : 1u));
-                const int stages = g_tune.stages >= 2 && g_tune.stages <= 4 ? g_tune.stages : QA_STAGES;
+                const int stages = QA_STAGES;
                 const uint32_t per_sm_cap = g_tune.per_sm > 0 ? (uint32_t)g_tune.per_sm : 4u;
                 const uint32_t tgroups = (tiles + (4 / wpt) - 1) / (4 / wpt);
                 p.chunks_per_slice = dsc * QS_SC;
@@ -1939,7 +1959,7 @@ static bool encode_matmul(uzu_command_buffer* cmd, uzu_context* ctx_for_query, c
                 const size_t asmem = dsmem + (size_t)QS_WARPS * stages * QA_STAGE_BYTES;
                 const size_t fsmem = asmem + (fused && fused->prologue ? (size_t)a.k * 2 + 64 : 0);
                 if (fused) {
-                    if (fsmem > 200u * 1024u || (a.k % 8) != 0) return false;
+                    if (fsmem > 200u * 1024u || (a.k % 8) != 0 || bits != 4) return false;
                     uint32_t pair_groups = 0;
                     if (fused->epilogue == 1) {
                         // gated-act epilogue: rows [0,F) up, [F,2F) gate; every CTA owns whole pairs, so no global k split
@@ -1963,9 +1983,6 @@ static bool encode_matmul(uzu_command_buffer* cmd, uzu_context* ctx_for_query, c
                         p.pro_scales = (const float*)fused->norm_scales;
                         p.pro_eps = fused->norm_epsilon; p.pro_scale_offset = fused->norm_scale_offset;
                         p.pro_residual_add = fused->norm_residual_add; p.pro_full_layer = fused->norm_full_layer;
-                    } else if (fused->prologue == 2) {
-                        p.pro_a = (const __nv_bfloat16*)fused->act_operand;
-                        p.pro_act = fused->act_type;
                     } else if (fused->prologue == 3) {
                         p.pro_a = (const __nv_bfloat16*)fused->sg_attn;
                         p.pro_b = (const __nv_bfloat16*)fused->sg_gate;
@@ -1974,8 +1991,8 @@ static bool encode_matmul(uzu_command_buffer* cmd, uzu_context* ctx_for_query, c
                     const uint32_t aitems = pair_groups ? pair_groups : std::max(1u, tgroups * dks), amax = per_sm * (uint32_t)ctx->sm_count;
                     const uint32_t rounds = (aitems + amax - 1) / amax;
                     const uint32_t agrid = (aitems + rounds - 1) / rounds;
-                    if (npg == 64) launch_qmv_decode_async<64>(cmd, p, agrid, fsmem, stages);
-                    else launch_qmv_decode_async<128>(cmd, p, agrid, fsmem, stages);
+                    if (npg == 64) launch_qmv_decode_async<64>(cmd, p, agrid, fsmem);
+                    else launch_qmv_decode_async<128>(cmd, p, agrid, fsmem);
                     return true;
                 }
                 if (!use_regs && asmem <= 200u * 1024u) {
@@ -1983,8 +2000,8 @@ static bool encode_matmul(uzu_command_buffer* cmd, uzu_context* ctx_for_query, c
                     const uint32_t aitems = std::max(1u, tgroups * dks), amax = per_sm * (uint32_t)ctx->sm_count;
                     const uint32_t rounds = (aitems + amax - 1) / amax;
                     const uint32_t agrid = (aitems + rounds - 1) / rounds;     // same number of items for (almost) every CTA
-                    if (npg == 64) launch_qmv_decode_async<64>(cmd, p, agrid, asmem, stages);
-                    else launch_qmv_decode_async<128>(cmd, p, agrid, asmem, stages);
+                    if (npg == 64) launch_qmv_decode_async<64>(cmd, p, agrid, asmem);
+                    else launch_qmv_decode_async<128>(cmd, p, agrid, asmem);
                     continue;
                 }
                 const uint32_t dgrid = std::min(std::min(grid, 4u * (uint32_t)ctx->sm_count), std::max(1u, tgroups * dks));   // 128 regs -> 4 CTAs / SM
@@ -2095,11 +2112,11 @@ int uzu_fused_linear_supported(uzu_context* ctx, const uzu_fused_linear_args* ar
         if (!m.a) m.a = m.d;
         if (uzu::validate(&m)) return 0;
     }
-    if (args->prologue > 3 || args->epilogue > 1 || (args->prologue == 0 && args->epilogue == 0)) return 0;
+    if (args->prologue > 3 || args->prologue == 2 || args->epilogue > 1 || (args->prologue == 0 && args->epilogue == 0)) return 0;
+    if (args->prologue == 3 && args->epilogue) return 0;
     if (args->prologue == 0 && !args->matmul.a) return 0;
     if (args->prologue == 1 && (!args->norm_input || !args->norm_scales || (args->norm_residual_add && !args->norm_shortcut_in) ||
                                 (args->shortcut_out && args->shortcut_out == args->norm_shortcut_in))) return 0;
-    if (args->prologue == 2 && !args->act_operand) return 0;
     if (args->prologue == 3 && (!args->sg_attn || !args->sg_gate)) return 0;
     uzu_matmul_args m = args->matmul;
     if (args->prologue != 0) m.a = 0;
