@@ -224,7 +224,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     max_ctx = max(1024, prefill + K + W + 64)
 
     ctx = B.Context(local_rank)
-    eng = B.Engine(ctx, mdir, max_context_length=max_ctx, use_cuda_graph=not args.no_graph, fused_decode=args.fused)
+    eng = B.Engine(ctx, mdir, max_context_length=max_ctx, use_cuda_graph=not args.no_graph, fused_decode=not args.no_fused)
     info = eng.info
     rng = np.random.default_rng(0)
     prompt = rng.integers(0, info.vocab_size, prefill).astype(np.uint32)
@@ -298,7 +298,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "model_dim": info.model_dim, "vocab": info.vocab_size, "weight_bytes_per_token": info.weight_bytes_per_token,
             "kv_bytes_per_token_at_mid_ctx": int(info.kv_bytes_per_token_per_ctx * ctx_mid), "state_bytes_per_token": info.state_bytes_per_token,
             "cache_policy": f"inputs larger than L2: {info.weight_bytes_per_token / 1e6:.0f} MB of weights streamed every step vs 126 MB L2",
-            "cuda_graph": not args.no_graph, "fused_decode": bool(args.fused), "prefill_tokens_per_s": prefill / prefill_s,
+            "cuda_graph": not args.no_graph, "fused_decode": not args.no_fused, "prefill_tokens_per_s": prefill / prefill_s,
             "whole_step_hbm_frac": bytes_per_token * (K / seconds) / 1e9 / peak,
             "gemv_launches_per_token": lin_launches // iters, "gemv_ms_per_token": 1000.0 * gemv_s_per_token,
         },
@@ -331,7 +331,8 @@ def main():
     ap.add_argument("--workload", default="qwen3.5-0.8b-int4", choices=sorted(WORKLOADS))
     ap.add_argument("--prefill", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--fused", action="store_true", help="fold norm / gated-act / sigmoid-gate launches into the consuming GEMV (experimental: slower in round 1)")
+    ap.add_argument("--fused", action="store_true", help="(default) fold norm / gated-act / sigmoid-gate launches into the neighbouring GEMV")
+    ap.add_argument("--no-fused", action="store_true", help="encode the reference's kernel sequence one launch per kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -7,11 +7,12 @@ There is no fallback: a missing library raises at load(), a missing GPU raises a
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libuzu_b200.so"
+LIB_PATH = Path(os.environ.get("UZU_B200_LIB") or Path(__file__).resolve().parent / "lib" / "libuzu_b200.so")   # override: kernel experiments
 
 u32, u64, f32 = C.c_uint32, C.c_uint64, C.c_float
 
@@ -366,7 +367,7 @@ class CommandBuffer:
 class Engine:
     """Engine + LanguageModel + LanguageModelState + stream (engine/language_model/*)."""
 
-    def __init__(self, ctx: Context, model_dir, max_context_length=8192, use_cuda_graph=True, fused_decode=False):
+    def __init__(self, ctx: Context, model_dir, max_context_length=8192, use_cuda_graph=True, fused_decode=True):
         self.ctx, self.lib = ctx, ctx.lib
         opts = EngineOptions(max_context_length=max_context_length, use_cuda_graph=int(use_cuda_graph),
                              fused_decode=int(fused_decode), tp_rank=0, tp_size=1)

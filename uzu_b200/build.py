@@ -60,7 +60,10 @@ def _compile(src: Path, extra, verbose: bool, force: bool):
 def build(force: bool = False, verbose: bool = False) -> Path:
     OBJ.mkdir(exist_ok=True)
     LIB.parent.mkdir(exist_ok=True)
-    srcs = [(CSRC / name, flags) for name, flags in SOURCES.items() if (CSRC / name).exists()]
+    # kernel experiments: UZU_B200_EXTRA_NVCC="-DFOO=1" adds flags to matmul.cu, UZU_B200_LIB_OUT names the output library
+    extra = os.environ.get("UZU_B200_EXTRA_NVCC", "").split()
+    lib = Path(os.environ["UZU_B200_LIB_OUT"]) if os.environ.get("UZU_B200_LIB_OUT") else LIB
+    srcs = [(CSRC / name, flags + (extra if name == "matmul.cu" else [])) for name, flags in SOURCES.items() if (CSRC / name).exists()]
     with ThreadPoolExecutor(max_workers=8) as ex:
         results = list(ex.map(lambda sf: _compile(sf[0], sf[1], verbose, force), srcs))
     objs = [o for o, _ in results]
@@ -68,14 +71,14 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if verbose:
         for l in logs:
             print(l)
-    relink = force or bool(logs) or not LIB.exists() or any(o.stat().st_mtime > LIB.stat().st_mtime for o in objs)
+    relink = force or bool(logs) or bool(extra) or not lib.exists() or any(o.stat().st_mtime > lib.stat().st_mtime for o in objs)
     if relink:
-        cmd = [NVCC, "-shared", "-o", str(LIB), *map(str, objs), "-ccbin", HOST_CXX, "-gencode", "arch=compute_100a,code=sm_100a",
+        cmd = [NVCC, "-shared", "-o", str(lib), *map(str, objs), "-ccbin", HOST_CXX, "-gencode", "arch=compute_100a,code=sm_100a",
                "-cudart", "static", "-Xlinker", "-z,defs", "-lpthread", "-ldl", "-lrt"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

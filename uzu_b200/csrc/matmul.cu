@@ -62,6 +62,7 @@ struct QmvParams {
     // fused epilogue (decode kernel): rows [0, F) are `up`, rows [F, 2F) are `gate`; a CTA walks tile i then tile i + F/16 and
     // writes hidden[j] = bf16(bf16(up_j) * bf16(act(bf16(gate_j)))) (GatedActMul, gated_act_mul/mod.rs:5-12) instead of the 2F row
     uint32_t epi_gated, epi_act, pair_tiles;
+    uint32_t stages;                 // cp.async ring depth of the decode kernel (host-side dispatch only)
     uint32_t method;           // uzu_quantization_method
     uint32_t bits;
     uint32_t xor_mask;         // signed_codes
@@ -84,8 +85,16 @@ __device__ __forceinline__ uint32_t nib_pair(uint32_t w, int shift) { return ((w
 // Same, tuned for the decode kernel where the integer ALU pipe is the limiter: the shift is a multiply-high
 // (IMAD.HI runs on the FMA pipe, which is otherwise idle) and (x & mask) | magic is forced into ONE LOP3 by keeping
 // the magic constant in a register (ptxas emits two LOP3 when both constants are immediates).
+#ifndef UZU_QA_SHIFT_MODE
+#define UZU_QA_SHIFT_MODE 1     // 0: every shift on the FMA pipe (IMAD.HI); 1: plain shifts (ALU pipe); 2: shift by 8 on the ALU pipe, 4 / 12 on FMA.
+                                // Measured (Llama-3-8B linears, B200): mode 1 is 13-19% faster than mode 0 once the kernel is small
+                                // enough not to stall on instruction fetch (IMAD.HI showed up as dispatch stalls in ncu).
+#endif
 __device__ __forceinline__ uint32_t nib_pair_fast(uint32_t w, int shift, uint32_t magic_reg) {
-    const uint32_t sh = shift == 0 ? w : __umulhi(w, 1u << (32 - shift));
+    uint32_t sh;
+    if (shift == 0) sh = w;
+    else if (UZU_QA_SHIFT_MODE == 1 || (UZU_QA_SHIFT_MODE == 2 && shift == 8)) sh = w >> shift;
+    else sh = __umulhi(w, 1u << (32 - shift));
     uint32_t d;
     asm("lop3.b32 %0, %1, 0x000f000f, %2, 0xEA;" : "=r"(d) : "r"(sh), "r"(magic_reg));
     return d;
@@ -1099,7 +1108,10 @@ __global__ void __launch_bounds__(QS_WARPS * 32, 4) qmv_decode_kernel(const QmvP
 // registers can hold ~8 KB per warp, the ring holds QA_STAGES-1 x 4.5 KB per warp with no register cost,
 // each lane consuming exactly the bytes it copied (no cross-thread synchronisation on the ring).
 // -------------------------------------------------------------------------------------------------
-constexpr int QA_STAGES = 2;
+#ifndef UZU_QA_ACCS
+#define UZU_QA_ACCS 2
+#endif
+constexpr int QA_STAGES = 2;         // base ring depth used for shared-memory sizing; the launch may deepen it (pick_stages)
 constexpr uint32_t QA_STAGE_BYTES = 4096 + 512;
 
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
@@ -1450,6 +1462,9 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
             const uint32_t* swd = reinterpret_cast<const uint32_t*>(ring_base + (size_t)slot * QA_STAGE_BYTES + 4096) + lane;
             // two independent accumulator fragments halve the dependent HMMA chain (32 MMAs per super-chunk)
             float d[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d2[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#if UZU_QA_ACCS == 4
+            float d3[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#endif
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint4 va = sw[j * 32], vb = sw[(4 + j) * 32];
@@ -1467,10 +1482,22 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
                     const uint4 xb = xrow[w_];
                     const uint32_t a0 = nib_pair_fast(wav[w_], 0, magic), a1 = nib_pair_fast(wav[w_], 4, magic), a2 = nib_pair_fast(wav[w_], 8, magic), a3 = nib_pair_fast(wav[w_], 12, magic);
                     const uint32_t b0 = nib_pair_fast(wbv[w_], 0, magic), b1 = nib_pair_fast(wbv[w_], 4, magic), b2 = nib_pair_fast(wbv[w_], 8, magic), b3 = nib_pair_fast(wbv[w_], 12, magic);
-                    mma_16816(d, a0, b0, a1, b1, xb.x, xb.y);
-                    mma_16816(d2, a2, b2, a3, b3, xb.z, xb.w);
+#if UZU_QA_ACCS == 4
+                    if (w_ & 1) {
+                        mma_16816(d3, a0, b0, a1, b1, xb.x, xb.y);
+                        mma_16816(d4, a2, b2, a3, b3, xb.z, xb.w);
+                    } else
+#endif
+                    {
+                        mma_16816(d, a0, b0, a1, b1, xb.x, xb.y);
+                        mma_16816(d2, a2, b2, a3, b3, xb.z, xb.w);
+                    }
                 }
             }
+#if UZU_QA_ACCS == 4
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { d[i] += d3[i]; d2[i] += d4[i]; }
+#endif
 #pragma unroll
             for (int i = 0; i < 4; ++i) d[i] += d2[i];
             // this lane's two D columns (2t, 2t+1) hold groups gi + 2t and gi + 2t + 1 of rows g (d0, d1) and g+8 (d2, d3)
@@ -1764,14 +1791,22 @@ static void launch_qmv_decode(uzu_command_buffer* cmd, const QmvParams& p, uint3
     launch(cmd, "qmv_decode_kernel", qmv_decode_kernel<NPG>, dim3(grid), dim3(QS_WARPS * 32), smem, p);
 }
 
-template <int NPG, int METHOD, int BITS, int PRO, bool EPI>
-static void launch_qmv_decode_async_i(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
+template <int NPG, int STAGES, int METHOD, int BITS, int PRO, bool EPI>
+static void launch_qmv_decode_async_s(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(qmv_decode_async_kernel<NPG, QA_STAGES, METHOD, BITS, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(qmv_decode_async_kernel<NPG, STAGES, METHOD, BITS, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    launch(cmd, "qmv_decode_async_kernel", qmv_decode_async_kernel<NPG, QA_STAGES, METHOD, BITS, PRO, EPI>, dim3(grid), dim3(QS_WARPS * 32), smem, p);
+    launch(cmd, "qmv_decode_async_kernel", qmv_decode_async_kernel<NPG, STAGES, METHOD, BITS, PRO, EPI>, dim3(grid), dim3(QS_WARPS * 32), smem, p);
+}
+template <int NPG, int METHOD, int BITS, int PRO, bool EPI>
+static void launch_qmv_decode_async_i(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
+    switch (p.stages) {
+        case 4: launch_qmv_decode_async_s<NPG, 4, METHOD, BITS, PRO, EPI>(cmd, p, grid, smem); break;
+        case 3: launch_qmv_decode_async_s<NPG, 3, METHOD, BITS, PRO, EPI>(cmd, p, grid, smem); break;
+        default: launch_qmv_decode_async_s<NPG, 2, METHOD, BITS, PRO, EPI>(cmd, p, grid, smem); break;
+    }
 }
 template <int NPG, int PRO, bool EPI>
 static void launch_qmv_decode_async_f(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
@@ -1804,7 +1839,7 @@ static void launch_qmv_decode_async(uzu_command_buffer* cmd, const QmvParams& p,
 }
 
 // Tuning overrides for sweeps (0 = heuristic). Not part of the reference-facing API; set through uzu_debug_set_qmv_tuning.
-struct QmvTuning { int wpt = 0, dks = 0, per_sm = 0, stages = 0; };   // `stages` is kept for ABI stability; the ring depth is fixed at QA_STAGES
+struct QmvTuning { int wpt = 0, dks = 0, per_sm = 0, stages = 0; };   // stages: 2..4 forces the cp.async ring depth
 static QmvTuning g_tune;
 
 template <int NPG, int MT>
@@ -1948,15 +1983,33 @@ static bool encode_matmul(uzu_command_buffer* cmd, uzu_context* ctx_for_query, c
                 if (tiles >= 2u * resident_warps) wpt = 1;
                 else if (tiles * 2u >= 2u * resident_warps && wpt > 2) wpt = 2;
                 if (g_tune.wpt > 0) wpt = std::min((uint32_t)g_tune.wpt, dsc >= 4 ? 4u : (dsc >= 2 ? 2u : 1u));
-                const int stages = QA_STAGES;
                 const uint32_t per_sm_cap = g_tune.per_sm > 0 ? (uint32_t)g_tune.per_sm : 4u;
+                // Ring depth: 2 stages let 4 CTAs share an SM (best when the grid fills the machine); when the grid is smaller than
+                // what deeper rings still leave room for, the spare shared memory buys a longer prefetch per warp instead.
+                auto pick_stages = [&](size_t smem2, uint32_t grid2, size_t& smem_out) {
+                    int st = 2;
+                    smem_out = smem2;
+                    if (g_tune.stages >= 2 && g_tune.stages <= 4) {
+                        st = g_tune.stages;
+                    } else {
+                        for (int cand = 4; cand > 2; --cand) {
+                            const size_t sm = smem2 + (size_t)QS_WARPS * (cand - 2) * QA_STAGE_BYTES;
+                            if (sm > 200u * 1024u) continue;
+                            const uint32_t per = std::min(per_sm_cap, (uint32_t)((220u * 1024u) / (sm + 1024u)));
+                            if (per >= 1 && per * (uint32_t)ctx->sm_count >= grid2) { st = cand; break; }
+                        }
+                    }
+                    smem_out = smem2 + (size_t)QS_WARPS * (st - 2) * QA_STAGE_BYTES;
+                    if (smem_out > 200u * 1024u) { st = 2; smem_out = smem2; }
+                    return st;
+                };
                 const uint32_t tgroups = (tiles + (4 / wpt) - 1) / (4 / wpt);
                 p.chunks_per_slice = dsc * QS_SC;
                 p.kslices = dks;
                 p.warps_per_tile = wpt;
                 const size_t dsmem = stream_smem + 2 * QS_WARPS * 16 * 4 + 64;
                 static const bool use_regs = getenv("UZU_QMV_REGS") != nullptr;
-                const size_t asmem = dsmem + (size_t)QS_WARPS * stages * QA_STAGE_BYTES;
+                const size_t asmem = dsmem + (size_t)QS_WARPS * QA_STAGES * QA_STAGE_BYTES;
                 const size_t fsmem = asmem + (fused && fused->prologue ? (size_t)a.k * 2 + 64 : 0);
                 if (fused) {
                     if (fsmem > 200u * 1024u || (a.k % 8) != 0 || bits != 4) return false;
@@ -1991,8 +2044,10 @@ static bool encode_matmul(uzu_command_buffer* cmd, uzu_context* ctx_for_query, c
                     const uint32_t aitems = pair_groups ? pair_groups : std::max(1u, tgroups * dks), amax = per_sm * (uint32_t)ctx->sm_count;
                     const uint32_t rounds = (aitems + amax - 1) / amax;
                     const uint32_t agrid = (aitems + rounds - 1) / rounds;
-                    if (npg == 64) launch_qmv_decode_async<64>(cmd, p, agrid, fsmem);
-                    else launch_qmv_decode_async<128>(cmd, p, agrid, fsmem);
+                    size_t lsmem = fsmem;
+                    p.stages = pick_stages(fsmem, agrid, lsmem);
+                    if (npg == 64) launch_qmv_decode_async<64>(cmd, p, agrid, lsmem);
+                    else launch_qmv_decode_async<128>(cmd, p, agrid, lsmem);
                     return true;
                 }
                 if (!use_regs && asmem <= 200u * 1024u) {
@@ -2000,8 +2055,10 @@ static bool encode_matmul(uzu_command_buffer* cmd, uzu_context* ctx_for_query, c
                     const uint32_t aitems = std::max(1u, tgroups * dks), amax = per_sm * (uint32_t)ctx->sm_count;
                     const uint32_t rounds = (aitems + amax - 1) / amax;
                     const uint32_t agrid = (aitems + rounds - 1) / rounds;     // same number of items for (almost) every CTA
-                    if (npg == 64) launch_qmv_decode_async<64>(cmd, p, agrid, asmem);
-                    else launch_qmv_decode_async<128>(cmd, p, agrid, asmem);
+                    size_t lsmem = asmem;
+                    p.stages = pick_stages(asmem, agrid, lsmem);
+                    if (npg == 64) launch_qmv_decode_async<64>(cmd, p, agrid, lsmem);
+                    else launch_qmv_decode_async<128>(cmd, p, agrid, lsmem);
                     continue;
                 }
                 const uint32_t dgrid = std::min(std::min(grid, 4u * (uint32_t)ctx->sm_count), std::max(1u, tgroups * dks));   // 128 regs -> 4 CTAs / SM
