@@ -123,14 +123,14 @@ constexpr int ATTN_UNROLL = 2;      // key rows per lane group per round (one mo
 template <int D, int G>
 __global__ void __launch_bounds__(ATTN_WARPS * 32) attn_split_kernel(const AttnParams p) {
     constexpr int EPL = (D >= 128 && G < 8) ? 16 : 8;    // elements per lane (q and o live in registers: 2 * G * EPL floats)
-    constexpr int CH = (G * D > 1024) ? ATTN_CHUNK / 2 : ATTN_CHUNK;
+    constexpr int CH = (G >= 8) ? ATTN_CHUNK / 2 : ATTN_CHUNK;   // scores [G][CH] + partial outputs stay under the 48 KB static limit
     constexpr int LPK = D / EPL;              // lanes per key row
     constexpr int KPW = 32 / LPK;             // key rows per warp step
     constexpr int STEP = ATTN_WARPS * KPW;    // key rows per CTA step
     constexpr int U = ATTN_UNROLL;
     static_assert(LPK >= 1 && LPK <= 32 && (EPL % 8) == 0, "bad attention tiling");
     __shared__ float sc[G][CH];
-    __shared__ float sm_o[ATTN_WARPS][G][D];
+    __shared__ float sm_o[ATTN_WARPS * KPW][G][D];     // one partial output per lane group (<= 32 KB for every instantiation)
     __shared__ float sm_m[G], sm_lc[G], sm_mfin[G], sm_lfin[G];
     __shared__ unsigned int sm_ticket;
     pdl_launch_dependents();
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attn_split_kernel(const AttnP
                 for (int h = 0; h < G; ++h) {
                     float sdot = 0.0f;
 #pragma unroll
-                    for (int e = 0; e < EPL; ++e) sdot += q[h][e] * kf[e];
+                    for (int e = 0; e < EPL; ++e) sdot = fmaf(q[h][e], kf[e], sdot);   // this file is built with -fmad=false: ask for the FMA
 #pragma unroll
                     for (int off = LPK / 2; off > 0; off >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, off);
                     if (li == 0 && kl < n) sc[h][kl] = okc[u] ? sdot : -INFINITY;
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attn_split_kernel(const AttnP
                 for (int h = 0; h < G; ++h) {
                     const float pv = sc[h][kl];
 #pragma unroll
-                    for (int e = 0; e < EPL; ++e) o[h][e] += pv * vf[e];
+                    for (int e = 0; e < EPL; ++e) o[h][e] = fmaf(pv, vf[e], o[h][e]);
                 }
             }
             if (more) {
@@ -310,19 +310,12 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attn_split_kernel(const AttnP
         __syncthreads();     // sc is rewritten by the next chunk
     }
 
-    // ---- sum the lane groups of a warp, then the warps of the CTA --------------------------------------------------------
+    // ---- every lane group parks its partial output in shared memory; summed below, ATTN_WARPS * KPW terms per output -------
 #pragma unroll
-    for (int off = LPK; off < 32; off <<= 1)
+    for (int h = 0; h < G; ++h)
 #pragma unroll
-        for (int h = 0; h < G; ++h)
-#pragma unroll
-            for (int e = 0; e < EPL; ++e) o[h][e] += __shfl_xor_sync(0xffffffffu, o[h][e], off);
-    if (sub == 0) {
-#pragma unroll
-        for (int h = 0; h < G; ++h)
-#pragma unroll
-            for (int e = 0; e < EPL; ++e) sm_o[warp][h][d0 + e] = o[h][e];
-    }
+        for (int v = 0; v < EPL / 4; ++v)
+            *reinterpret_cast<float4*>(&sm_o[warp * KPW + sub][h][d0 + v * 4]) = make_float4(o[h][v * 4], o[h][v * 4 + 1], o[h][v * 4 + 2], o[h][v * 4 + 3]);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int h = 0; h < G; ++h) { sm_mfin[h] = m_run[h]; sm_lfin[h] = l_run[h]; }
@@ -335,7 +328,7 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attn_split_kernel(const AttnP
         const int h = idx / D, d = idx % D;
         float ov = 0.0f;
 #pragma unroll
-        for (int w = 0; w < ATTN_WARPS; ++w) ov += sm_o[w][h][d];
+        for (int w = 0; w < ATTN_WARPS * KPW; ++w) ov += sm_o[w][h][d];
         const float lv = sm_lfin[h], gm = sm_mfin[h];
         const size_t o_off = (size_t)qs * H + head0 + h;
         if (direct) {
