@@ -243,6 +243,21 @@ typedef struct uzu_attention_prepare_args {
 } uzu_attention_prepare_args;
 UZU_API void uzu_attention_prepare_encode(uzu_command_buffer* cmd, const uzu_attention_prepare_args* args);
 
+/* Extension: QKVNorm (queries), QKVNorm (keys) and AttentionPrepare in ONE launch (Attention::encode runs them back to back on the
+ * same qkv rows, mixer/attention/mode.rs; qkv_norm.rs:7-35 + attention_prepare.rs:34-52). Same arithmetic and rounding points as the
+ * three kernels (the normalised row is rounded to bf16 before RoPE exactly as the in-place QKVNorm stores it); the qkv buffer itself is
+ * left untouched. head_dim <= 256. A norm with `present == 0` is skipped. */
+typedef struct uzu_qk_norm_config {
+    uint64_t scales;               /* f32 [head_dim] (has_scales) */
+    float epsilon, scale_offset;
+    uint32_t present, full_layer, has_scales, reserved0;
+} uzu_qk_norm_config;
+typedef struct uzu_attention_prepare_norm_args {
+    uzu_attention_prepare_args prepare;
+    uzu_qk_norm_config q_norm, k_norm;
+} uzu_attention_prepare_norm_args;
+UZU_API void uzu_attention_prepare_norm_encode(uzu_command_buffer* cmd, const uzu_attention_prepare_norm_args* args);
+
 /* AttentionSinglePassKernel / AttentionTwoPass1Kernel share this argument block:
  * backends/cpu/kernel/attention/attention_single_pass.rs:13-37, attention_two_pass.rs:15-40. */
 typedef struct uzu_attention_args {
@@ -354,6 +369,16 @@ typedef struct uzu_delta_net_update_args {
     uint32_t head_k_dim;           /* HEAD_K_DIM variant: 128 */
 } uzu_delta_net_update_args;
 UZU_API void uzu_delta_net_update_encode(uzu_command_buffer* cmd, const uzu_delta_net_update_args* args);
+/* Extension: DeltaNetConvUpdate folded into DeltaNetUpdate (DeltaNet::encode runs them back to back, mixer/delta_net.rs). `update.in_proj`
+ * is the RAW projection row (== conv.in_out, which is NOT rewritten); every CTA convolves the q / k / v channels it consumes with the
+ * conv kernel's arithmetic (bf16-rounded SiLU output) and the rolling conv state is advanced once per channel. Requires
+ * num_v_heads == num_k_heads (each k head is read by exactly one v head's CTA cluster), kernel_size <= 8. */
+typedef struct uzu_delta_net_fused_update_args {
+    uzu_delta_net_update_args update;
+    uzu_delta_net_conv_update_args conv;
+} uzu_delta_net_fused_update_args;
+UZU_API int uzu_delta_net_fused_update_supported(const uzu_delta_net_fused_update_args* args);
+UZU_API void uzu_delta_net_fused_update_encode(uzu_command_buffer* cmd, const uzu_delta_net_fused_update_args* args);
 
 /* ---- Host engine (C++ mirror of the reference's backend-agnostic Rust host code) ---------- *
  * No Rust toolchain exists in the build image, so the layer above the kernels -- Engine /

@@ -266,3 +266,78 @@ def test_gated_epilogue_matches_unfused_sequence(ctx, act, F, k, with_norm):
     ref = O.gated_act_mul(O.matmul(x_eff, w, m=1, n=n, k=k, scales=sc, zero_points=zp, method=O.QM_ZERO_POINT), F, act=act_id)
     gf, rf = bf16_to_f32(got), bf16_to_f32(ref)
     assert np.allclose(gf, rf, rtol=2e-2, atol=2e-2 * max(1.0, float(np.sqrt((rf ** 2).mean()))))
+
+
+def test_attention_prepare_norm_matches_three_kernels(ctx):
+    """QKVNorm(q) + QKVNorm(k) + AttentionPrepare in one launch == the three launches, bit for bit (queries, K row, V row)."""
+    import ctypes as C
+    from tests.util import f32_to_bf16
+    rng = np.random.default_rng(11)
+    for (Hq, Hkv, D, rope_dim, full_layer) in [(8, 2, 256, 64, 0), (4, 4, 128, 128, 1), (2, 1, 64, 32, 0)]:
+        total = Hq + 2 * Hkv
+        qkv = f32_to_bf16(rng.standard_normal((1, total * D)).astype(np.float32) * 2)
+        qs = (0.1 * rng.standard_normal(D)).astype(np.float32); ks = (0.1 * rng.standard_normal(D)).astype(np.float32)
+        cos = rng.uniform(-1, 1, (1, rope_dim)).astype(np.float32); sin = rng.uniform(-1, 1, (1, rope_dim)).astype(np.float32)
+        outs = []
+        for fused in (False, True):
+            b_qkv, b_q = ctx.upload(qkv.copy()), ctx.upload(np.zeros((Hq, 1, D), np.uint16))
+            b_k, b_v = ctx.upload(np.zeros((4, Hkv * D), np.uint16)), ctx.upload(np.zeros((4, Hkv * D), np.uint16))
+            b_qs, b_ks, b_cos, b_sin = ctx.upload(qs), ctx.upload(ks), ctx.upload(cos), ctx.upload(sin)
+            pa = B.AttentionPrepareArgs(qkv=b_qkv.ptr, queries=b_q.ptr, keys=b_k.ptr, values=b_v.ptr, cosines=b_cos.ptr, sines=b_sin.ptr, num_q_heads=Hq,
+                                        num_kv_heads=Hkv, head_dim=D, rope_dim=rope_dim, kv_token_offset=2, batch_dim=1, has_kv=1, has_rope=1)
+            with ctx.command_buffer("prep") as cmd:
+                if fused:
+                    pn = B.AttentionPrepareNormArgs(prepare=pa)
+                    pn.q_norm = B.QkNormConfig(scales=b_qs.ptr, epsilon=1e-6, scale_offset=1.0, present=1, full_layer=full_layer, has_scales=1)
+                    pn.k_norm = B.QkNormConfig(scales=b_ks.ptr, epsilon=1e-6, scale_offset=1.0, present=1, full_layer=full_layer, has_scales=1)
+                    cmd.encode("uzu_attention_prepare_norm_encode", C.byref(pn))
+                else:
+                    for (sc, off, cnt) in ((b_qs, 0, Hq), (b_ks, Hq, Hkv)):
+                        qa = B.QkvNormArgs(scales=sc.ptr, qkv_output=b_qkv.ptr, batch_size=1, total_heads=total, head_dim=D, epsilon=1e-6, scale_offset=1.0,
+                                           head_offset=off, head_count=cnt, full_layer=full_layer, in_place=1, has_scales=1)
+                        cmd.encode("uzu_qkv_norm_encode", C.byref(qa))
+                    cmd.encode("uzu_attention_prepare_encode", C.byref(pa))
+            outs.append((b_q.numpy(np.uint16, (Hq, 1, D)), b_k.numpy(np.uint16, (4, Hkv * D)), b_v.numpy(np.uint16, (4, Hkv * D))))
+        for u, f in zip(*outs):
+            assert (u == f).all()
+        assert outs[1][1][2].any() and not outs[1][1][1].any()      # row kv_token_offset written, neighbours untouched
+
+
+def test_delta_net_fused_conv_update_matches_two_kernels(ctx):
+    """DeltaNetConvUpdate folded into DeltaNetUpdate == the two launches, bit for bit (output, recurrent state, conv state), 3 steps."""
+    import ctypes as C
+    from tests.util import f32_to_bf16
+    rng = np.random.default_rng(12)
+    Hv = Hk = 4; Dk = 128; Dv = 128; ks = 4
+    key_dim, value_dim = Hk * Dk, Hv * Dv
+    conv_dim = 2 * key_dim + value_dim
+    total = conv_dim + value_dim + 2 * Hv
+    w = (0.3 * rng.standard_normal((conv_dim, ks))).astype(np.float32); bias = (0.1 * rng.standard_normal(conv_dim)).astype(np.float32)
+    a_log = rng.uniform(-1, 1, Hv).astype(np.float32); dt_bias = rng.uniform(-1, 1, Hv).astype(np.float32)
+    nw = rng.uniform(0.5, 1.5, Dv).astype(np.float32)
+    st0 = (0.1 * rng.standard_normal((Hv, Dv, Dk))).astype(np.float32); cs0 = (0.5 * rng.standard_normal((conv_dim, ks - 1))).astype(np.float32)
+    xs = [f32_to_bf16(rng.standard_normal((1, total)).astype(np.float32)) for _ in range(3)]
+    res = []
+    for fused in (False, True):
+        b_w, b_bias, b_al, b_dt, b_nw = ctx.upload(w), ctx.upload(bias), ctx.upload(a_log), ctx.upload(dt_bias), ctx.upload(nw)
+        b_st, b_cs, b_out = ctx.upload(st0.copy()), ctx.upload(cs0.copy()), ctx.upload(np.zeros((1, value_dim), np.uint16))
+        outs = []
+        for x in xs:
+            b_x = ctx.upload(x.copy())
+            ca = B.DeltaNetConvUpdateArgs(conv_weight=b_w.ptr, bias=b_bias.ptr, in_out=b_x.ptr, state=b_cs.ptr, kernel_size=ks, conv_dim=conv_dim,
+                                          state_stride=ks - 1, has_bias=1)
+            ua = B.DeltaNetUpdateArgs(in_proj=b_x.ptr, a_log=b_al.ptr, dt_bias=b_dt.ptr, norm_weight=b_nw.ptr, state=b_st.ptr, out=b_out.ptr, num_v_heads=Hv,
+                                      num_k_heads=Hk, head_v_dim=Dv, key_dim=key_dim, value_dim=value_dim, norm_epsilon=1e-6, head_k_dim=Dk)
+            with ctx.command_buffer("dn") as cmd:
+                if fused:
+                    fa = B.DeltaNetFusedUpdateArgs(update=ua, conv=ca)
+                    assert ctx.lib.uzu_delta_net_fused_update_supported(C.byref(fa)) == 1
+                    cmd.encode("uzu_delta_net_fused_update_encode", C.byref(fa))
+                else:
+                    cmd.encode("uzu_delta_net_conv_update_encode", C.byref(ca))
+                    cmd.encode("uzu_delta_net_update_encode", C.byref(ua))
+            outs.append(b_out.numpy(np.uint16, (1, value_dim)).copy())
+        res.append((outs, b_st.numpy(np.float32, st0.shape).copy(), b_cs.numpy(np.float32, cs0.shape).copy()))
+    for o_u, o_f in zip(res[0][0], res[1][0]):
+        assert (o_u == o_f).all()
+    assert (res[0][1] == res[1][1]).all() and (res[0][2] == res[1][2]).all()

@@ -61,6 +61,12 @@ AttentionPrepareArgs = _struct("uzu_attention_prepare_args", [
     ("num_q_heads", u32), ("num_kv_heads", u32), ("head_dim", u32), ("rope_dim", u32), ("kv_token_offset", u32),
     ("batch_dim", u32), ("has_kv", u32), ("has_rope", u32), ("dynamic_position", u64)])
 
+QkNormConfig = _struct("uzu_qk_norm_config", [
+    ("scales", u64), ("epsilon", f32), ("scale_offset", f32), ("present", u32), ("full_layer", u32), ("has_scales", u32), ("reserved0", u32)])
+
+AttentionPrepareNormArgs = _struct("uzu_attention_prepare_norm_args", [
+    ("prepare", AttentionPrepareArgs), ("q_norm", QkNormConfig), ("k_norm", QkNormConfig)])
+
 AttentionArgs = _struct("uzu_attention_args", [
     ("queries", u64), ("keys", u64), ("values", u64), ("out", u64), ("sums", u64), ("maxs", u64),
     ("gqa_factor", u32), ("sequence_length", u32), ("k_head_stride", u32), ("k_seq_stride", u32), ("v_head_stride", u32),
@@ -97,6 +103,8 @@ DeltaNetUpdateArgs = _struct("uzu_delta_net_update_args", [
     ("num_v_heads", u32), ("num_k_heads", u32), ("head_v_dim", u32), ("key_dim", u32), ("value_dim", u32),
     ("norm_epsilon", f32), ("head_k_dim", u32)])
 
+DeltaNetFusedUpdateArgs = _struct("uzu_delta_net_fused_update_args", [("update", DeltaNetUpdateArgs), ("conv", DeltaNetConvUpdateArgs)])
+
 EngineOptions = _struct("uzu_engine_options", [
     ("max_context_length", u32), ("use_cuda_graph", u32), ("fused_decode", u32), ("tp_rank", u32), ("tp_size", u32),
     ("reserved", u64 * 4)])
@@ -115,7 +123,7 @@ FusedLinearArgs = _struct("uzu_fused_linear_args", [
     ("norm_epsilon", f32), ("norm_scale_offset", f32), ("norm_residual_add", u32), ("norm_full_layer", u32), ("act_operand", u64),
     ("act_type", u32), ("sg_attn", u64), ("sg_gate", u64), ("epilogue", u32), ("reserved0", u32)])
 
-ABI_STRUCTS = [FusedLinearArgs, RingParams, TrieNode, KvCopy, MatmulArgs, NormalizationArgs, QkvNormArgs, AttentionPrepareArgs, AttentionArgs,
+ABI_STRUCTS = [DeltaNetFusedUpdateArgs, QkNormConfig, AttentionPrepareNormArgs, FusedLinearArgs, RingParams, TrieNode, KvCopy, MatmulArgs, NormalizationArgs, QkvNormArgs, AttentionPrepareArgs, AttentionArgs,
                AttentionTwoPass2Args, KvCacheUpdateArgs, GatedActMulArgs, QuantizedEmbeddingLookupArgs, UnifiedSamplingArgs,
                DeltaNetConvUpdateArgs, DeltaNetUpdateArgs, EngineOptions, SamplingMethod, ModelInfo]
 
@@ -130,14 +138,14 @@ uzu_command_buffer_encode_copy uzu_command_buffer_encode_fill uzu_command_buffer
 uzu_command_buffer_push_debug_group uzu_command_buffer_pop_debug_group uzu_command_buffer_end_encoding
 uzu_command_buffer_submit uzu_command_buffer_wait_until_completed uzu_command_buffer_gpu_execution_time
 uzu_command_buffer_launch_count uzu_matmul_encode uzu_matmul_validate uzu_normalization_encode uzu_qkv_norm_encode
-uzu_attention_prepare_encode uzu_attention_single_pass_encode uzu_attention_two_pass1_encode uzu_attention_two_pass2_encode
+uzu_attention_prepare_encode uzu_attention_prepare_norm_encode uzu_attention_single_pass_encode uzu_attention_two_pass1_encode uzu_attention_two_pass2_encode
 uzu_kv_cache_update_encode uzu_sigmoid_gate_encode uzu_gated_act_mul_encode uzu_quantized_embedding_lookup_encode
 uzu_full_precision_embedding_lookup_encode uzu_logit_transform_encode uzu_tensor_add_scale_encode uzu_tensor_copy_encode
 uzu_tensor_add_bias_encode uzu_tensor_add_swap_encode uzu_unified_sampling_encode uzu_delta_net_conv_update_encode
 uzu_delta_net_update_encode uzu_engine_create uzu_engine_destroy uzu_engine_info uzu_engine_reset uzu_engine_context_length
 uzu_engine_snapshot uzu_engine_restore uzu_engine_prefill uzu_engine_next uzu_engine_flush uzu_engine_decode_device
 uzu_engine_forward uzu_engine_launch_count uzu_engine_decode_timed uzu_engine_step_host
-uzu_engine_time_linears uzu_engine_time_linears_select uzu_debug_set_qmv_tuning uzu_fused_linear_supported uzu_fused_linear_encode""".split()
+uzu_delta_net_fused_update_supported uzu_delta_net_fused_update_encode uzu_engine_time_linears uzu_engine_time_linears_select uzu_debug_set_qmv_tuning uzu_fused_linear_supported uzu_fused_linear_encode""".split()
 
 _lib = None
 
@@ -201,6 +209,9 @@ def load() -> C.CDLL:
         "uzu_normalization_encode": (None, [vp, C.POINTER(NormalizationArgs)]),
         "uzu_qkv_norm_encode": (None, [vp, C.POINTER(QkvNormArgs)]),
         "uzu_attention_prepare_encode": (None, [vp, C.POINTER(AttentionPrepareArgs)]),
+        "uzu_attention_prepare_norm_encode": (None, [vp, C.POINTER(AttentionPrepareNormArgs)]),
+        "uzu_delta_net_fused_update_supported": (C.c_int, [C.POINTER(DeltaNetFusedUpdateArgs)]),
+        "uzu_delta_net_fused_update_encode": (None, [vp, C.POINTER(DeltaNetFusedUpdateArgs)]),
         "uzu_attention_single_pass_encode": (None, [vp, C.POINTER(AttentionArgs)]),
         "uzu_attention_two_pass1_encode": (None, [vp, C.POINTER(AttentionArgs)]),
         "uzu_attention_two_pass2_encode": (None, [vp, C.POINTER(AttentionTwoPass2Args)]),

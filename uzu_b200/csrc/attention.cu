@@ -65,6 +65,77 @@ __global__ void __launch_bounds__(256) attention_prepare_kernel(const uzu_attent
     }
 }
 
+// QKVNorm(q) + QKVNorm(k) + AttentionPrepare in one launch: one CTA per (head, token). The RMS statistic is summed by warp 0 in the
+// standalone kernel's order (lane-strided, then the xor tree), the normalised row is rounded to bf16 as the in-place QKVNorm
+// stores it, and RoPE reads that bf16 row from shared memory: bit-identical to the three-kernel sequence.
+__global__ void __launch_bounds__(256) attention_prepare_norm_kernel(const uzu_attention_prepare_norm_args n) {
+    __shared__ __nv_bfloat16 row[256];
+    __shared__ float rms_s;
+    pdl_launch_dependents();
+    pdl_wait();
+    const uzu_attention_prepare_args& a = n.prepare;
+    const uint32_t total_heads = a.has_kv ? a.num_q_heads + 2 * a.num_kv_heads : a.num_q_heads;
+    const uint32_t b = blockIdx.y, h = blockIdx.x;
+    const __nv_bfloat16* head = reinterpret_cast<const __nv_bfloat16*>(a.qkv) + ((size_t)b * total_heads + h) * a.head_dim;
+    const bool is_query = !a.has_kv || h < a.num_q_heads;
+    const bool is_key = a.has_kv && h >= a.num_q_heads && h < a.num_q_heads + a.num_kv_heads;
+    const uzu_qk_norm_config& nc = is_query ? n.q_norm : n.k_norm;
+    const bool normed = (is_query || is_key) && nc.present;
+    const float* cosines = reinterpret_cast<const float*>(a.cosines);
+    const float* sines = reinterpret_cast<const float*>(a.sines);
+    uint32_t kv_token_offset = a.kv_token_offset;
+    if (a.dynamic_position) {
+        kv_token_offset = *reinterpret_cast<const uint32_t*>(a.dynamic_position);
+        if (a.has_rope) {
+            cosines += (size_t)kv_token_offset * a.rope_dim;
+            sines += (size_t)kv_token_offset * a.rope_dim;
+        }
+    }
+    if (normed && threadIdx.x < 32) {
+        float total = 0.0f;
+        for (uint32_t i = threadIdx.x; i < a.head_dim; i += 32) {
+            const float v = bf2f(head[i]);
+            total += v * v;
+        }
+        total = warp_sum(total);
+        const float mean_square = total / (float)a.head_dim;
+        if (threadIdx.x == 0) rms_s = 1.0f / sqrtf(mean_square + nc.epsilon);
+    }
+    __syncthreads();
+    for (uint32_t d = threadIdx.x; d < a.head_dim; d += blockDim.x) {
+        __nv_bfloat16 r = head[d];
+        if (normed) {
+            const float normalized = bf2f(r) * rms_s;
+            const float* scales = reinterpret_cast<const float*>(nc.scales);
+            if (!nc.has_scales) r = f2bf(normalized);
+            else if (nc.full_layer) r = f2bf(normalized * (scales[d] + nc.scale_offset));
+            else r = f2bf(bf2f(f2bf(normalized)) * bf2f(f2bf(scales[d] + nc.scale_offset)));
+        }
+        row[d] = r;
+    }
+    __syncthreads();
+    for (uint32_t d = threadIdx.x; d < a.head_dim; d += blockDim.x) {
+        __nv_bfloat16 e = row[d];
+        if (a.has_rope && d < a.rope_dim && (is_query || is_key)) {
+            const uint32_t half = a.rope_dim / 2;
+            const uint32_t paired = d < half ? d + half : d - half;
+            const float input = bf2f(e);
+            const float pv = bf2f(row[paired]);
+            const float signed_p = d < half ? -pv : pv;
+            const float c = cosines[(size_t)b * a.rope_dim + d];
+            const float s = sines[(size_t)b * a.rope_dim + d];
+            e = f2bf(input * c + signed_p * s);
+        }
+        if (is_query) {
+            reinterpret_cast<__nv_bfloat16*>(a.queries)[((size_t)h * a.batch_dim + b) * a.head_dim + d] = e;
+        } else if (is_key) {
+            reinterpret_cast<__nv_bfloat16*>(a.keys)[((size_t)(kv_token_offset + b) * a.num_kv_heads + (h - a.num_q_heads)) * a.head_dim + d] = e;
+        } else {
+            reinterpret_cast<__nv_bfloat16*>(a.values)[((size_t)(kv_token_offset + b) * a.num_kv_heads + (h - a.num_q_heads - a.num_kv_heads)) * a.head_dim + d] = e;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // mask (mask.rs:3-62)
 // ---------------------------------------------------------------------------------------------------
@@ -520,6 +591,26 @@ void uzu_attention_prepare_encode(uzu_command_buffer* cmd, const uzu_attention_p
     dim3 grid(total_heads, a->batch_dim);
     uint32_t threads = a->head_dim >= 256 ? 256 : (a->head_dim >= 128 ? 128 : 64);
     uzu::launch(cmd, "attention_prepare_kernel", uzu::attention_prepare_kernel, grid, dim3(threads), 0, *a);
+}
+
+void uzu_attention_prepare_norm_encode(uzu_command_buffer* cmd, const uzu_attention_prepare_norm_args* n) {
+    if (!uzu::encodable(cmd, "attention_prepare_norm")) return;
+    const uzu_attention_prepare_args* a = &n->prepare;
+    if (!a->qkv || !a->queries || a->head_dim == 0 || (a->has_kv && (!a->keys || !a->values || a->num_kv_heads == 0)) ||
+        (a->has_rope && (!a->cosines || !a->sines || a->rope_dim == 0 || a->rope_dim > a->head_dim || (a->rope_dim & 1))) ||
+        (a->num_q_heads == 0 && !a->has_kv) || (n->q_norm.present && n->q_norm.has_scales && !n->q_norm.scales) ||
+        (n->k_norm.present && n->k_norm.has_scales && !n->k_norm.scales)) {
+        cmd->record_error(UZU_ERROR_INVALID_ARGUMENT, "attention_prepare_norm: inconsistent arguments");
+        return;
+    }
+    if (a->head_dim > 256) {
+        cmd->record_error(UZU_ERROR_UNSUPPORTED, "attention_prepare_norm: head_dim must be <= 256 (encode QKVNorm + AttentionPrepare separately)");
+        return;
+    }
+    const uint32_t total_heads = a->has_kv ? a->num_q_heads + 2 * a->num_kv_heads : a->num_q_heads;
+    if (a->batch_dim == 0 || total_heads == 0) return;
+    const uint32_t threads = a->head_dim >= 256 ? 256 : (a->head_dim >= 128 ? 128 : 64);
+    uzu::launch(cmd, "attention_prepare_norm_kernel", uzu::attention_prepare_norm_kernel, dim3(total_heads, a->batch_dim), dim3(threads), 0, *n);
 }
 
 void uzu_attention_single_pass_encode(uzu_command_buffer* cmd, const uzu_attention_args* a) {

@@ -1004,8 +1004,10 @@ static uzu_fused_linear_args fused_norm_args(const Linear& l, const Norm& n, uin
 //   bit 0: pre-mixer / pre-MLP RMSNorm (+ residual add) -> prologue of the consuming GEMV(s)
 //   bit 1: GatedActMul -> epilogue of the up GEMV (paired up / gate tiles)
 //   bit 2: SigmoidGate -> prologue of the attention out projection
+//   bit 3: QKVNorm(q) + QKVNorm(k) + AttentionPrepare -> one launch
+//   bit 4: DeltaNetConvUpdate -> inside DeltaNetUpdate (one k head per v head only)
 static uint32_t fuse_mask() {
-    static const uint32_t m = [] { const char* v = getenv("UZU_FUSE_MASK"); return v ? (uint32_t)atoi(v) : 7u; }();
+    static const uint32_t m = [] { const char* v = getenv("UZU_FUSE_MASK"); return v ? (uint32_t)atoi(v) : 31u; }();
     return m;
 }
 
@@ -1048,7 +1050,7 @@ static bool fused_decode_supported(uzu_engine* e) {
 static void encode_decoder_fused(uzu_engine* e, uzu_command_buffer* cmd, const PassCtx& pc) {
     const uint32_t H = e->model_dim;
     const uint32_t mask = fuse_mask();
-    const bool fuse_norm = (mask & 1u) != 0, fuse_gated = (mask & 2u) != 0, fuse_sigmoid = (mask & 4u) != 0;
+    const bool fuse_norm = (mask & 1u) != 0, fuse_gated = (mask & 2u) != 0, fuse_sigmoid = (mask & 4u) != 0, fuse_qknorm = (mask & 8u) != 0, fuse_conv = (mask & 16u) != 0;
     // embedding lookup (embedding.rs:345-372)
     if (e->in_emb.w.prologue == UZU_B_FULL_PRECISION) {
         uzu_full_precision_embedding_lookup_encode(cmd, e->token_ids.ptr(), e->in_emb.w.values.ptr(), e->hidden_a.ptr(), 1, e->vocab, H, e->input_scale);
@@ -1089,18 +1091,6 @@ static void encode_decoder_fused(uzu_engine* e, uzu_command_buffer* cmd, const P
             if (A.has_gate) mixer_in_linear(A.gate, e->gate.ptr());
             mixer_in_linear(A.qkv, e->qkv.ptr());
             const uint32_t total_heads = Hq + 2 * Hkv;
-            auto qkn = [&](const Norm& n, uint32_t off, uint32_t cnt) {
-                if (!n.present || cnt == 0) return;
-                uzu_qkv_norm_args qa{};
-                qa.scales = n.scales.ptr(); qa.qkv_output = e->qkv.ptr();
-                qa.batch_size = 1; qa.total_heads = total_heads; qa.head_dim = D;
-                qa.epsilon = n.cfg.epsilon; qa.scale_offset = n.cfg.scale_offset;
-                qa.head_offset = off; qa.head_count = cnt; qa.full_layer = n.cfg.full_layer;
-                qa.in_place = 1; qa.has_scales = n.cfg.has_scale;
-                uzu_qkv_norm_encode(cmd, &qa);
-            };
-            qkn(A.qnorm, 0, Hq);
-            qkn(A.knorm, Hq, Hkv);
             uzu_attention_prepare_args pa{};
             pa.qkv = e->qkv.ptr(); pa.queries = e->queries.ptr(); pa.keys = St.keys; pa.values = St.values;
             pa.num_q_heads = Hq; pa.num_kv_heads = Hkv; pa.head_dim = D; pa.kv_token_offset = St.length; pa.batch_dim = 1; pa.has_kv = 1;
@@ -1110,7 +1100,32 @@ static void encode_decoder_fused(uzu_engine* e, uzu_command_buffer* cmd, const P
                 pa.cosines = e->rope_cos[A.rope_index].ptr(); pa.sines = e->rope_sin[A.rope_index].ptr();
             }
             pa.dynamic_position = dyn;
-            uzu_attention_prepare_encode(cmd, &pa);
+            if (fuse_qknorm && (A.qnorm.present || A.knorm.present) && D <= 256) {
+                uzu_attention_prepare_norm_args pn{};
+                pn.prepare = pa;
+                auto cfg = [](const Norm& nm) {
+                    uzu_qk_norm_config c{};
+                    c.present = nm.present; c.scales = nm.scales.ptr(); c.epsilon = nm.cfg.epsilon; c.scale_offset = nm.cfg.scale_offset;
+                    c.full_layer = nm.cfg.full_layer; c.has_scales = nm.cfg.has_scale;
+                    return c;
+                };
+                pn.q_norm = cfg(A.qnorm); pn.k_norm = cfg(A.knorm);
+                uzu_attention_prepare_norm_encode(cmd, &pn);
+            } else {
+                auto qkn = [&](const Norm& n, uint32_t off, uint32_t cnt) {
+                    if (!n.present || cnt == 0) return;
+                    uzu_qkv_norm_args qa{};
+                    qa.scales = n.scales.ptr(); qa.qkv_output = e->qkv.ptr();
+                    qa.batch_size = 1; qa.total_heads = total_heads; qa.head_dim = D;
+                    qa.epsilon = n.cfg.epsilon; qa.scale_offset = n.cfg.scale_offset;
+                    qa.head_offset = off; qa.head_count = cnt; qa.full_layer = n.cfg.full_layer;
+                    qa.in_place = 1; qa.has_scales = n.cfg.has_scale;
+                    uzu_qkv_norm_encode(cmd, &qa);
+                };
+                qkn(A.qnorm, 0, Hq);
+                qkn(A.knorm, Hq, Hkv);
+                uzu_attention_prepare_encode(cmd, &pa);
+            }
             uzu_attention_args aa{};
             aa.queries = e->queries.ptr(); aa.keys = St.keys; aa.values = St.values; aa.out = e->attn_out.ptr();
             aa.gqa_factor = Hq / Hkv; aa.sequence_length = St.length + 1;
@@ -1130,16 +1145,21 @@ static void encode_decoder_fused(uzu_engine* e, uzu_command_buffer* cmd, const P
         } else {
             const DeltaNetLayer& Dn = L.dn;
             mixer_in_linear(Dn.in_proj, e->in_proj.ptr());
-            uzu_delta_net_conv_update_args ca{};
+            uzu_delta_net_fused_update_args fa{};
+            uzu_delta_net_conv_update_args& ca = fa.conv;
             ca.conv_weight = Dn.conv_weight.ptr(); ca.bias = Dn.conv_bias.ptr(); ca.in_out = e->in_proj.ptr(); ca.state = St.conv_state.ptr();
             ca.kernel_size = Dn.kernel_size; ca.conv_dim = Dn.conv_dim; ca.state_stride = Dn.kernel_size - 1; ca.has_bias = Dn.conv_has_bias;
-            uzu_delta_net_conv_update_encode(cmd, &ca);
-            uzu_delta_net_update_args ua{};
+            uzu_delta_net_update_args& ua = fa.update;
             ua.in_proj = e->in_proj.ptr(); ua.a_log = Dn.a_log.ptr(); ua.dt_bias = Dn.dt_bias.ptr(); ua.norm_weight = Dn.norm_weight.ptr();
             ua.state = St.ssm_state.ptr(); ua.out = e->delta_out.ptr();
             ua.num_v_heads = Dn.num_heads; ua.num_k_heads = Dn.num_groups; ua.head_v_dim = Dn.value_head_dim; ua.key_dim = Dn.key_dim;
             ua.value_dim = Dn.value_dim; ua.norm_epsilon = Dn.norm_epsilon; ua.head_k_dim = Dn.head_dim;
-            uzu_delta_net_update_encode(cmd, &ua);
+            if (fuse_conv && uzu_delta_net_fused_update_supported(&fa)) {
+                uzu_delta_net_fused_update_encode(cmd, &fa);
+            } else {
+                uzu_delta_net_conv_update_encode(cmd, &ca);
+                uzu_delta_net_update_encode(cmd, &ua);
+            }
             encode_linear(cmd, Dn.out_proj, e->delta_out.ptr(), 1, e->mixer_out.ptr());
         }
         if (fuse_norm) cur ^= 1;
