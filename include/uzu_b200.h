@@ -198,6 +198,11 @@ typedef struct uzu_fused_linear_args {
 } uzu_fused_linear_args;
 /* Tuning sweeps only (tools/): override the decode GEMV's work split; 0 = heuristic. Process-wide, not thread-safe. */
 UZU_API void uzu_debug_set_qmv_tuning(int warps_per_tile, int k_slices, int ctas_per_sm, int stages);
+/* Prefill path (m >= 64, quantized B, bf16 A): uzu_matmul_encode runs the tcgen05 tensor-core GEMM with an in-kernel dequant stage
+ * (csrc/prefill_gemm.cu); UZU_PREFILL_GEMM_MIN_M=<m> moves the threshold, 0 disables it. Probe hook (tools/umma_probe.py only):
+ * override the UMMA shared-memory layout (0 = SWIZZLE_128B, 1 = no swizzle; < 0 = built-in default), descriptor words and the
+ * instruction descriptor (0 = default), and force the tokens-per-CTA factor mt (0 = heuristic). Process-wide, not thread-safe. */
+UZU_API void uzu_debug_set_umma(int layout, uint32_t desc_hi, uint32_t desc_lbo, uint32_t k_step, uint32_t idesc, int mt);
 UZU_API int uzu_fused_linear_supported(uzu_context* ctx, const uzu_fused_linear_args* args);
 UZU_API void uzu_fused_linear_encode(uzu_command_buffer* cmd, const uzu_fused_linear_args* args);
 

@@ -26,6 +26,7 @@ COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-st
 SOURCES = {
     "runtime.cu": [],
     "matmul.cu": [],
+    "prefill_gemm.cu": [],
     "attention.cu": ["-fmad=false"],
     "norm.cu": ["-fmad=false"],
     "elementwise.cu": ["-fmad=false"],

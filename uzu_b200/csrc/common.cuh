@@ -97,6 +97,10 @@ inline void launch(uzu_command_buffer* cmd, const char* what, void (*kernel)(KAr
 }
 #endif
 
+// tcgen05 prefill GEMM (prefill_gemm.cu), dispatched from encode_matmul (matmul.cu)
+bool prefill_gemm_applicable(const uzu_matmul_args& a);
+void encode_prefill_gemm(uzu_command_buffer* cmd, const uzu_matmul_args& a);
+
 inline bool encodable(uzu_command_buffer* cmd, const char* what) {
     if (!cmd) return false;
     if (cmd->state != uzu_command_buffer::Encoding) {

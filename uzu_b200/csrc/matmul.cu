@@ -1879,6 +1879,11 @@ static void launch_generic(uzu_command_buffer* cmd, const uzu_matmul_args& a) {
 
 // returns true when the fused fast path (decode kernel) handled the call; with `fused` set and `dry_run`, only reports applicability
 static bool encode_matmul(uzu_command_buffer* cmd, uzu_context* ctx_for_query, const uzu_matmul_args& a, const uzu_fused_linear_args* fused = nullptr, bool dry_run = false) {
+    // prefill (m >= 64 tokens): tensor-core GEMM with an in-kernel dequant stage (prefill_gemm.cu)
+    if (!fused && !dry_run && cmd && prefill_gemm_applicable(a)) {
+        encode_prefill_gemm(cmd, a);
+        return true;
+    }
     const bool quant = a.b_prologue != UZU_B_FULL_PRECISION;
     const uint32_t bits = a.b_mode == UZU_QMODE_U4 ? 4 : 8;
     const uint32_t np = quant ? a.k * bits / 4 : 0;          // nibbles per row
