@@ -18,6 +18,8 @@ workload = BASELINE.json configs[1]: Qwen3.5-0.8B int4, prefill 512, decode 128.
   --impl reference   times the same CPU restatement with all host threads (the reference itself is Rust and cannot be
              built here: no rustc/cargo in the image).
 Multi-GPU: the BASELINE models that fit one GPU run as independent replicas (weak scaling, no collective on the path).
+`--tp P` (with --gpus P) runs ONE model sharded over the P ranks instead (uzu_b200/tp.py shards by attention head / FFN column /
+vocabulary row; two NCCL all-reduces per layer + one all-gather of the logits): value = tokens/s of that single replica, "strong".
 """
 from __future__ import annotations
 
@@ -41,6 +43,7 @@ WORKLOADS = {
     "qwen3.5-0.8b-int4-dense": ("qwen3.5-0.8b", dict(bits=4, group_size=64, hybrid=False), 512, 128),
     "llama3-8b-int4": ("llama3-8b", dict(bits=4, group_size=64), 2048, 256),
     "llama3-8b-int8": ("llama3-8b", dict(bits=8, group_size=64), 4096, 512),
+    "llama3-70b-int4": ("llama3-70b", dict(bits=4, group_size=64), 2048, 256),      # needs --tp 8 (37 GB of weights, 4.7 GB per rank)
     "tiny": (None, {}, 32, 16),
 }
 
@@ -77,6 +80,19 @@ def model_dir_for(workload: str, seed: int = 0) -> Path:
     finally:
         os.close(fd)
         os.unlink(lock)
+    return d
+
+
+def shard_dir_for(full_dir: Path, rank: int, size: int) -> Path:
+    """The rank's tensor-parallel shard of a synthetic checkpoint (written once per rank, next to the full model)."""
+    from uzu_b200 import tp as tpmod
+    d = full_dir.parent / f"{full_dir.name}-tp{size}-rank{rank}"
+    done = d / ".done"
+    if not done.exists():
+        t0 = time.time()
+        tpmod.shard_checkpoint(full_dir, d, rank, size)
+        done.write_text("ok")
+        log(f"[bench] wrote tensor-parallel shard {d} in {time.time() - t0:.1f}s")
     return d
 
 
@@ -144,6 +160,17 @@ def hbm_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def tensor_peak():
+    """Dense bf16 TFLOP/s to divide the prefill GEMM by: the sustained cuBLAS figure of MEASURED_PEAKS.json (a GEMM timed inside a pass)."""
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json cuBLAS bf16, sustained)"
+        except Exception:
+            pass
+    return 1500.0, "fallback (B200_PROFILING.md)"
 
 
 def cpu_baseline(model_dir: Path, threads: int, tokens: int, prompt_len: int = 4):
@@ -224,7 +251,21 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     max_ctx = max(1024, prefill + K + W + 64)
 
     ctx = B.Context(local_rank)
-    eng = B.Engine(ctx, mdir, max_context_length=max_ctx, use_cuda_graph=not args.no_graph, fused_decode=not args.no_fused)
+    tp = args.tp if args.tp > 1 else 1
+    if tp > 1:
+        # one tensor-parallel group over all ranks: rank 0's NCCL unique id travels over torch.distributed, every rank loads its shard
+        if world != tp:
+            raise SystemExit(f"--tp {tp} needs exactly {tp} ranks (torchrun --nproc-per-node {tp}); got WORLD_SIZE={world}")
+        import torch
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.tensor(list(B.tp_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        ctx.tp_init(rank, world, bytes(idt.cpu().tolist()))
+        mdir = shard_dir_for(mdir, rank, world)
+    eng = B.Engine(ctx, mdir, max_context_length=max_ctx, use_cuda_graph=not args.no_graph, fused_decode=not args.no_fused,
+                   tp_rank=rank if tp > 1 else 0, tp_size=tp)
+    replicas = 1 if tp > 1 else world
     info = eng.info
     rng = np.random.default_rng(0)
     prompt = rng.integers(0, info.vocab_size, prefill).astype(np.uint32)
@@ -252,7 +293,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         seconds = max_over_ranks(dist, seconds, "cuda")
         dist.barrier()
     clocks = sampler.stop()
-    value = whole_job_value(world, K, seconds)
+    value = whole_job_value(replicas, K, seconds)
 
     # ---- end to end through host buffers ----
     eng.restore()
@@ -268,7 +309,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         tok = eng.step_host(tok)
     e2e_s = time.perf_counter() - t0
     e2e_s = max_over_ranks(dist, e2e_s, "cuda")
-    e2e_value = whole_job_value(world, K, e2e_s)
+    e2e_value = whole_job_value(replicas, K, e2e_s)
 
     # ---- roofline of the dominant kernel (fused dequant + GEMV) ----
     iters = 10
@@ -283,17 +324,29 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             traffic = json.loads(tfile.read_text()).get(workload)
         except Exception:
             traffic = None
+    # ---- prefill GEMM (tcgen05 tensor cores, in-kernel dequant): every linear of one prefill pass, useful TFLOP/s ----
+    prefill_gemm = None
+    try:
+        pm = min(prefill, 1024)
+        if pm >= 64:
+            p_s, p_flops = eng.time_prefill_linears(pm, 3)
+            tpeak, tsrc = tensor_peak()
+            prefill_gemm = {"rows": pm, "ms_per_pass": 1000.0 * p_s, "useful_tflops": p_flops / p_s / 1e12, "peak_tflops": tpeak,
+                            "frac": p_flops / p_s / 1e12 / tpeak, "peak_source": tsrc,
+                            "note": "useful flops = 2*m*N*K; the kernel issues 2x that (exact hi/lo bf16 weight planes)"}
+    except Exception as ex:  # must not take the decode measurement down
+        prefill_gemm = {"error": str(ex)[:200]}
     ctx_mid = prefill + K / 2
     bytes_per_token = info.weight_bytes_per_token + info.kv_bytes_per_token_per_ctx * ctx_mid + info.state_bytes_per_token
 
     line = {
         "metric": "decode tokens/sec/GPU (int4)" if "int4" in workload else "decode tokens/sec/GPU",
         "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1000.0 * seconds / K,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong" if tp > 1 else "weak", "vs_baseline": None,
         "dtype": "bf16 activations x int4 weights, f32 accumulate" if "int4" in workload else "bf16 activations x int8 weights, f32 accumulate",
         "data": "synthetic",
         "config": {
-            "workload": f"{workload}: prefill {prefill}, decode {K}, batch 1, greedy", "parallelism": "replicas" if world > 1 else "single",
+            "workload": f"{workload}: prefill {prefill}, decode {K}, batch 1, greedy", "parallelism": f"tp{tp}" if tp > 1 else ("replicas" if world > 1 else "single"),
             "layers": info.num_layers, "attention_layers": info.num_attention_layers, "delta_net_layers": info.num_delta_net_layers,
             "model_dim": info.model_dim, "vocab": info.vocab_size, "weight_bytes_per_token": info.weight_bytes_per_token,
             "kv_bytes_per_token_at_mid_ctx": int(info.kv_bytes_per_token_per_ctx * ctx_mid), "state_bytes_per_token": info.state_bytes_per_token,
@@ -301,6 +354,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "cuda_graph": not args.no_graph, "fused_decode": not args.no_fused, "prefill_tokens_per_s": prefill / prefill_s,
             "whole_step_hbm_frac": bytes_per_token * (K / seconds) / 1e9 / peak,
             "gemv_launches_per_token": lin_launches // iters, "gemv_ms_per_token": 1000.0 * gemv_s_per_token,
+            "prefill_gemm": prefill_gemm,
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "qmv_kernel (fused int4 dequant + GEMV, all linears + readout of one token)", "peak_source": peak_src},
@@ -334,6 +388,7 @@ def main():
     ap.add_argument("--fused", action="store_true", help="(default) fold norm / gated-act / sigmoid-gate launches into the neighbouring GEMV")
     ap.add_argument("--no-fused", action="store_true", help="encode the reference's kernel sequence one launch per kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tp", type=int, default=1, help="tensor-parallel size: shard ONE model over this many ranks (= --gpus) instead of replicas")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -206,6 +206,24 @@ UZU_API void uzu_debug_set_umma(int layout, uint32_t desc_hi, uint32_t desc_lbo,
 UZU_API int uzu_fused_linear_supported(uzu_context* ctx, const uzu_fused_linear_args* args);
 UZU_API void uzu_fused_linear_encode(uzu_command_buffer* cmd, const uzu_fused_linear_args* args);
 
+/* ---- Tensor parallelism (extension; the reference is single-device) -------------------------------------------
+ * One process per GPU. Rank 0 creates a 128-byte NCCL unique id, the host program distributes it (bench.py: torch.distributed
+ * broadcast), every rank calls uzu_context_tp_init on its context. The engine then loads the checkpoint shard written by
+ * uzu_b200/tp.py (config.json "tensor_parallel" block) and inserts the two exchange steps below. NCCL is dlopen'ed at first use
+ * (UZU_NCCL_LIB overrides the soname), so the library itself has no link-time dependency on it. */
+UZU_API uzu_status uzu_tp_get_unique_id(uint8_t* out128);
+UZU_API uzu_status uzu_context_tp_init(uzu_context* ctx, uint32_t rank, uint32_t size, const uint8_t* unique_id128);
+UZU_API void uzu_context_tp_destroy(uzu_context* ctx);
+UZU_API uint32_t uzu_context_tp_size(const uzu_context* ctx);
+UZU_API uint32_t uzu_context_tp_rank(const uzu_context* ctx);
+/* Row-parallel projection epilogue: sum the f32 partials [count] over the ranks in place (ncclAllReduce on the context stream),
+ * then round to bf16 once into out_bf16. With a 1-rank context only the rounding runs. */
+UZU_API void uzu_tp_all_reduce_encode(uzu_command_buffer* cmd, uint64_t partial_f32, uint32_t count, uint64_t out_bf16);
+/* Vocab-parallel readout: every rank's [rows, cols_local] 2-byte logits -> [rows, tp_size * cols_local] on every rank.
+ * `scratch` (tp_size * rows * cols_local * 2 bytes) is needed for rows > 1 only. */
+typedef struct uzu_tp_all_gather_args { uint64_t src, dst, scratch; uint32_t rows, cols_local; } uzu_tp_all_gather_args;
+UZU_API void uzu_tp_all_gather_encode(uzu_command_buffer* cmd, const uzu_tp_all_gather_args* args);
+
 /* NormalizationKernel: backends/cpu/kernel/normalization/normalization.rs:7-49 */
 typedef struct uzu_normalization_args {
     uint64_t input;                /* optional(!in_place) */
@@ -452,6 +470,9 @@ UZU_API uint64_t uzu_engine_launch_count(const uzu_engine* e);   /* kernels laun
 UZU_API uzu_status uzu_engine_decode_timed(uzu_engine* e, uint32_t steps, double* out_seconds);
 UZU_API uzu_status uzu_engine_step_host(uzu_engine* e, uint32_t token_in, uint32_t* token_out);
 UZU_API uzu_status uzu_engine_time_linears(uzu_engine* e, uint32_t iters, double* out_seconds, uint64_t* out_launches);
+/*  time_prefill_linears: every linear of one PREFILL pass over m rows (all layers, no readout) back to back; returns seconds per pass
+ *                and the useful flops of one pass (2*m*N*K summed): the tensor-core GEMM's achieved TFLOP/s = flops / seconds. */
+UZU_API uzu_status uzu_engine_time_prefill_linears(uzu_engine* e, uint32_t m, uint32_t iters, double* out_seconds, double* out_flops);
 /* same, restricted to a subset: bit 0 mixer input projections (qkv / gate / in_proj), 1 mixer output projection, 2 MLP up, 3 MLP down,
  * 4 readout, 5 MLP up with the GatedActMul epilogue, 6 attention mix (q/k norm, RoPE + KV append, attention core, gate) at the
  * current context length, 7 DeltaNet conv + state update; bit 31: plain stream-ordered launches (no programmatic dependent launch) */

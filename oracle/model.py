@@ -75,13 +75,22 @@ class _Linear:
 
 
 class OracleModel:
-    def __init__(self, path, threads: int = 1, max_context: int = 4096):
+    """`tp_reduce` / `tp_gather`: the two exchange steps of a tensor-parallel shard written by uzu_b200.tp.shard_checkpoint
+    (config.json carries a "tensor_parallel" block): f32 partial sums [m, H] of the row-parallel out / down projections are summed
+    over ranks (all-reduce) and rounded to bf16 once; the vocab-parallel readout's [rows, V/P] logits are concatenated (all-gather).
+    The reference has no tensor parallelism; the 1-rank model is the oracle for the P-rank one."""
+
+    def __init__(self, path, threads: int = 1, max_context: int = 4096, tp_reduce=None, tp_gather=None):
         path = Path(path)
         cfg = json.loads((path / "config.json").read_text())
         self.cfg = cfg
         dec = cfg["decoder_config"]
         tr = dec["transformer_config"]
         self.H, self.F, self.V = tr["model_dim"], tr["hidden_dim"], dec["vocab_size"]
+        self.tp = cfg.get("tensor_parallel")
+        self.tp_reduce, self.tp_gather = tp_reduce, tp_gather
+        if self.tp is not None and self.tp["size"] > 1:
+            assert tp_reduce is not None and tp_gather is not None, "a tensor-parallel shard needs the exchange hooks"
         self.layers_cfg = tr["layer_configs"]
         self.out_norm_cfg = tr["output_norm_config"]
         self.emb_cfg = dec["embedding_config"]
@@ -94,7 +103,8 @@ class OracleModel:
             self.in_emb = self.out_emb = _Linear(T, M, p + "embedding", self.V, self.H, threads)
         else:
             self.in_emb = _Linear(T, M, p + "input_embedding", self.V, self.H, threads)
-            self.out_emb = _Linear(T, M, p + "output_embedding", self.V, self.H, threads)
+            v_out = self.tp["vocab_size_local"] if self.tp is not None else self.V
+            self.out_emb = _Linear(T, M, p + "output_embedding", v_out, self.H, threads)
         self.layers = []
         for i, lc in enumerate(self.layers_cfg):
             lp = f"decoder.transformer.layers.{i}."
@@ -177,7 +187,13 @@ class OracleModel:
         if gate is not None:
             O.sigmoid_gate(gate, out)
         st["len"] = prefix + m  # encode_accept(0..m): flat path, no copies (state.rs:174-237)
-        return L["out"](out)
+        return self._row_parallel(L["out"], out)
+
+    def _row_parallel(self, linear, x):
+        """out / down projection. Tensor-parallel shard: this rank's K slice gives an f32 partial; sum over ranks, round once."""
+        if self.tp is None or self.tp["size"] == 1:
+            return linear(x)
+        return O.f32_to_bf16(self.tp_reduce(linear(x, d_f32=True)))
 
     def _delta_net(self, L, st, hidden):
         mc = L["mixer"]
@@ -220,13 +236,15 @@ class OracleModel:
             act = L["cfg"]["mlp_config"]["activation"]
             assert act["type"] == "SiLU"
             gated = O.gated_act_mul(up, L["F"], O.ACT_SILU)
-            hidden = L["down"](gated)
+            hidden = self._row_parallel(L["down"], gated)
         b, e = output_rows
         # output_norm over rows [b,e) with residual add into the same rows of shortcut (transformer.rs:317-323)
         sc_rows = np.ascontiguousarray(shortcut[b:e])
         normed = self._norm(np.ascontiguousarray(hidden[b:e]), "decoder.transformer.output_norm", self.out_norm_cfg,
                             shortcut=sc_rows, residual_add=True)
         logits = self.out_emb(normed)
+        if self.tp is not None and self.tp["size"] > 1:
+            logits = self.tp_gather(logits)          # [rows, V/P] per rank -> [rows, V]
         if self.emb_cfg["logit_scale"] is not None or self.emb_cfg["logit_soft_cap"] is not None:
             O.logit_transform(logits, self.emb_cfg["logit_scale"] or 1.0, self.emb_cfg["logit_soft_cap"])
         self.context_length += m

@@ -49,6 +49,31 @@ def test_teacher_forced_logits(ctx, tmp_path, kind, quant):
         assert eng.context_length == ref.context_length
 
 
+@pytest.mark.parametrize("kind,n", [("qwen-hybrid", 21), ("qwen-hybrid-512", 90)])
+def test_hybrid_batched_prefill_matches_token_stepping(ctx, tmp_path, kind, n):
+    """DeltaNet layers in a multi-token pass: projections batched (tensor-core GEMM for >= 64 rows), the recurrence row by row inside
+    the pass -- the same function as one pass per token (the oracle restates the m = 1 branch, so it steps)."""
+    spec = synth.tiny(kind)
+    path = synth.write_model(spec, tmp_path / "m", seed=23)
+    rng = np.random.default_rng(6)
+    prompt = rng.integers(0, spec.vocab_size, n)
+    ref = OracleModel(path, max_context=256)
+    for t in prompt:
+        lr = ref.forward([t])
+    with B.Engine(ctx, path, max_context_length=256, use_cuda_graph=False) as eng:
+        lg = eng.forward(prompt)                      # ONE pass over the whole prompt
+        _logit_check(lg, lr, f"{kind} batched prefill")
+        assert eng.context_length == n
+        own_first = int(np.argmax(bf16_to_f32(lg[0])))
+        tok = int(np.argmax(bf16_to_f32(lr[0])))
+        for step in range(4):                         # the recurrent state left by the batched pass continues correctly
+            lr, lg = ref.forward([tok]), eng.forward([tok])
+            _logit_check(lg, lr, f"{kind} decode after batched prefill {step}")
+            tok = int(np.argmax(bf16_to_f32(lr[0])))
+        eng.reset()
+        assert eng.prefill(prompt) == own_first       # stream API: the same chunked pass + greedy sampling of its last row
+
+
 def test_stream_api_graph_and_eager_agree_with_oracle(ctx, tmp_path):
     spec = synth.tiny("llama", layers=3)
     path = synth.write_model(spec, tmp_path / "m", seed=9)

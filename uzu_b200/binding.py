@@ -118,6 +118,8 @@ ModelInfo = _struct("uzu_model_info", [
     ("num_delta_net_layers", u32), ("weight_bytes_per_token", u64), ("kv_bytes_per_token_per_ctx", u64),
     ("state_bytes_per_token", u64)])
 
+TpAllGatherArgs = _struct("uzu_tp_all_gather_args", [("src", u64), ("dst", u64), ("scratch", u64), ("rows", u32), ("cols_local", u32)])
+
 FusedLinearArgs = _struct("uzu_fused_linear_args", [
     ("matmul", MatmulArgs), ("prologue", u32), ("norm_input", u64), ("norm_shortcut_in", u64), ("norm_scales", u64), ("shortcut_out", u64),
     ("norm_epsilon", f32), ("norm_scale_offset", f32), ("norm_residual_add", u32), ("norm_full_layer", u32), ("act_operand", u64),
@@ -125,7 +127,7 @@ FusedLinearArgs = _struct("uzu_fused_linear_args", [
 
 ABI_STRUCTS = [DeltaNetFusedUpdateArgs, QkNormConfig, AttentionPrepareNormArgs, FusedLinearArgs, RingParams, TrieNode, KvCopy, MatmulArgs, NormalizationArgs, QkvNormArgs, AttentionPrepareArgs, AttentionArgs,
                AttentionTwoPass2Args, KvCacheUpdateArgs, GatedActMulArgs, QuantizedEmbeddingLookupArgs, UnifiedSamplingArgs,
-               DeltaNetConvUpdateArgs, DeltaNetUpdateArgs, EngineOptions, SamplingMethod, ModelInfo]
+               DeltaNetConvUpdateArgs, DeltaNetUpdateArgs, EngineOptions, SamplingMethod, ModelInfo, TpAllGatherArgs]
 
 # every symbol include/uzu_b200.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTS = """uzu_last_error uzu_version uzu_abi_struct_size uzu_context_create uzu_context_destroy uzu_context_synchronize
@@ -145,7 +147,8 @@ uzu_tensor_add_bias_encode uzu_tensor_add_swap_encode uzu_unified_sampling_encod
 uzu_delta_net_update_encode uzu_engine_create uzu_engine_destroy uzu_engine_info uzu_engine_reset uzu_engine_context_length
 uzu_engine_snapshot uzu_engine_restore uzu_engine_prefill uzu_engine_next uzu_engine_flush uzu_engine_decode_device
 uzu_engine_forward uzu_engine_launch_count uzu_engine_decode_timed uzu_engine_step_host
-uzu_delta_net_fused_update_supported uzu_delta_net_fused_update_encode uzu_engine_time_linears uzu_engine_time_linears_select uzu_debug_set_qmv_tuning uzu_debug_set_umma uzu_fused_linear_supported uzu_fused_linear_encode""".split()
+uzu_delta_net_fused_update_supported uzu_delta_net_fused_update_encode uzu_engine_time_linears uzu_engine_time_prefill_linears uzu_engine_time_linears_select uzu_debug_set_qmv_tuning uzu_debug_set_umma uzu_tp_get_unique_id uzu_context_tp_init uzu_context_tp_destroy uzu_context_tp_size
+uzu_context_tp_rank uzu_tp_all_reduce_encode uzu_tp_all_gather_encode uzu_fused_linear_supported uzu_fused_linear_encode""".split()
 
 _lib = None
 
@@ -244,9 +247,17 @@ def load() -> C.CDLL:
         "uzu_engine_decode_timed": (C.c_int, [vp, u32, C.POINTER(C.c_double)]),
         "uzu_engine_step_host": (C.c_int, [vp, u32, C.POINTER(u32)]),
         "uzu_engine_time_linears": (C.c_int, [vp, u32, C.POINTER(C.c_double), C.POINTER(u64)]),
+        "uzu_engine_time_prefill_linears": (C.c_int, [vp, u32, u32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "uzu_engine_time_linears_select": (C.c_int, [vp, u32, u32, C.POINTER(C.c_double), C.POINTER(u64)]),
         "uzu_debug_set_qmv_tuning": (None, [C.c_int, C.c_int, C.c_int, C.c_int]),
         "uzu_debug_set_umma": (None, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
+        "uzu_tp_get_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+        "uzu_context_tp_init": (C.c_int, [vp, u32, u32, C.POINTER(C.c_uint8)]),
+        "uzu_context_tp_destroy": (None, [vp]),
+        "uzu_context_tp_size": (u32, [vp]),
+        "uzu_context_tp_rank": (u32, [vp]),
+        "uzu_tp_all_reduce_encode": (None, [vp, u64, u32, u64]),
+        "uzu_tp_all_gather_encode": (None, [vp, C.POINTER(TpAllGatherArgs)]),
         "uzu_fused_linear_supported": (C.c_int, [vp, C.POINTER(FusedLinearArgs)]),
         "uzu_fused_linear_encode": (None, [vp, C.POINTER(FusedLinearArgs)]),
     }
@@ -256,6 +267,13 @@ def load() -> C.CDLL:
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def tp_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0); hand the 128 bytes to every rank's Context.tp_init."""
+    buf = (C.c_uint8 * 128)()
+    _check(load().uzu_tp_get_unique_id(buf))
+    return bytes(buf)
 
 
 def _check(status: int):
@@ -287,6 +305,11 @@ class Context:
 
     def synchronize(self):
         _check(self.lib.uzu_context_synchronize(self.h))
+
+    def tp_init(self, rank: int, size: int, unique_id: bytes):
+        """Join the tensor-parallel group: `unique_id` = tp_unique_id() of rank 0, distributed by the host program."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        _check(self.lib.uzu_context_tp_init(self.h, rank, size, buf))
 
     @property
     def sm_count(self):
@@ -379,10 +402,10 @@ class CommandBuffer:
 class Engine:
     """Engine + LanguageModel + LanguageModelState + stream (engine/language_model/*)."""
 
-    def __init__(self, ctx: Context, model_dir, max_context_length=8192, use_cuda_graph=True, fused_decode=True):
+    def __init__(self, ctx: Context, model_dir, max_context_length=8192, use_cuda_graph=True, fused_decode=True, tp_rank=0, tp_size=1):
         self.ctx, self.lib = ctx, ctx.lib
         opts = EngineOptions(max_context_length=max_context_length, use_cuda_graph=int(use_cuda_graph),
-                             fused_decode=int(fused_decode), tp_rank=0, tp_size=1)
+                             fused_decode=int(fused_decode), tp_rank=tp_rank, tp_size=tp_size)
         h = C.c_void_p()
         _check(self.lib.uzu_engine_create(ctx.h, str(model_dir).encode(), C.byref(opts), C.byref(h)))
         self.h = h
@@ -477,6 +500,12 @@ class Engine:
         out = u32()
         _check(self.lib.uzu_engine_step_host(self.h, int(token), C.byref(out)))
         return out.value
+
+    def time_prefill_linears(self, m: int, iters: int = 3):
+        """(seconds per pass, useful flops per pass) of every linear of one prefill pass over m rows (tensor-core GEMM for m >= 64)."""
+        t, f = C.c_double(), C.c_double()
+        _check(self.lib.uzu_engine_time_prefill_linears(self.h, m, iters, C.byref(t), C.byref(f)))
+        return t.value, f.value
 
     def time_linears(self, iters: int, select: int = 31):
         t, n = C.c_double(), u64()

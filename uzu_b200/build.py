@@ -27,6 +27,7 @@ SOURCES = {
     "runtime.cu": [],
     "matmul.cu": [],
     "prefill_gemm.cu": [],
+    "tp.cu": [],
     "attention.cu": ["-fmad=false"],
     "norm.cu": ["-fmad=false"],
     "elementwise.cu": ["-fmad=false"],

@@ -45,6 +45,9 @@ struct uzu_context {
     unsigned int* attn_counters = nullptr;
     bool vmm_supported = false;
     size_t vmm_granularity = 0;
+    // tensor parallelism (tp.cu): NCCL communicator of this process's rank, created by uzu_context_tp_init
+    void* nccl_comm = nullptr;
+    uint32_t tp_rank = 0, tp_size = 1;
 };
 
 struct uzu_command_buffer {

@@ -379,6 +379,10 @@ struct uzu_engine {
     Buf decode_state;     // device DecodeState
     Buf snapshot_token;   // next-input token at snapshot time
     uint32_t logits_rows = 16;
+    // tensor parallelism (config.json "tensor_parallel" block written by uzu_b200/tp.py; tp.cu holds the collectives)
+    uint32_t tp_rank = 0, tp_size = 1, vocab_local = 0;
+    bool tp_sharded = false;       // the checkpoint is a shard: row-parallel partials in f32 + exchange, vocab-parallel readout
+    Buf tp_partial, logits_local, tp_gather;
     // streaming
     uzu_sampling_method sampling{};
     uint32_t steps_issued = 0, steps_returned = 0;
@@ -547,14 +551,33 @@ static void load_model(uzu_engine* e, const std::string& dir) {
         throw std::runtime_error("PLE / embedding norm are outside this backend's scope (SURVEY 2.1)");
     ParameterLoader pl(dir + "/model.safetensors");
     const uint32_t H = e->model_dim, V = e->vocab;
-    const uint32_t tp = e->opts.tp_size ? e->opts.tp_size : 1;
-    if (tp != 1) throw std::runtime_error("tensor parallel loading is not implemented in this build");
+    // tensor-parallel shard (uzu_b200/tp.py): narrower heads / hidden_dim come from the shard's own config; the block says which rank
+    // this is and how many vocabulary rows the local readout holds. The context must carry the matching communicator.
+    const uint32_t want_tp = e->opts.tp_size ? e->opts.tp_size : 1;
+    uint32_t vocab_out = V;
+    if (const Json* tpj = cfg.get("tensor_parallel")) {
+        if (!tpj->is_null()) {
+            e->tp_sharded = true;
+            e->tp_rank = tpj->at("rank").u32();
+            e->tp_size = tpj->at("size").u32();
+            e->vocab_local = tpj->at("vocab_size_local").u32();
+            if (e->tp_size == 0 || e->tp_rank >= e->tp_size || (uint64_t)e->vocab_local * e->tp_size != V)
+                throw std::runtime_error("config.json: inconsistent tensor_parallel block");
+            if (e->ctx->tp_size != e->tp_size || e->ctx->tp_rank != e->tp_rank)
+                throw std::runtime_error("tensor-parallel shard " + std::to_string(e->tp_rank) + "/" + std::to_string(e->tp_size) +
+                                         " needs a context initialised with the same rank / size (uzu_context_tp_init)");
+            vocab_out = e->vocab_local;
+        }
+    }
+    if (want_tp != e->tp_size || (e->opts.tp_size && e->opts.tp_rank != e->tp_rank))
+        throw std::runtime_error("uzu_engine_options tp_rank/tp_size do not match the checkpoint (shard it with uzu_b200/tp.py)");
 
     const Json& emb = dec.at("embedding_config");
     e->tied = emb.type_tag() == "TiedEmbeddingConfig";
     if (!emb.at("input_scale").is_null()) e->input_scale = (float)emb.at("input_scale").number();
     if (!emb.at("logit_scale").is_null()) { e->has_logit_scale = true; e->logit_scale = (float)emb.at("logit_scale").number(); }
     if (!emb.at("logit_soft_cap").is_null()) { e->has_logit_soft_cap = true; e->logit_soft_cap = (float)emb.at("logit_soft_cap").number(); }
+    if (e->tied && e->tp_sharded) throw std::runtime_error("a tensor-parallel shard carries untied embeddings (uzu_b200/tp.py)");
     if (e->tied) {
         e->in_emb.in_dim = H; e->in_emb.out_dim = V;
         e->in_emb.w = load_weight_matrix(e, pl, "decoder.embedding.embedding", "input_output", V, H);
@@ -562,8 +585,8 @@ static void load_model(uzu_engine* e, const std::string& dir) {
     } else {
         e->in_emb.in_dim = H; e->in_emb.out_dim = V;
         e->in_emb.w = load_weight_matrix(e, pl, "decoder.embedding.input_embedding", "input_output", V, H);
-        e->out_emb.in_dim = H; e->out_emb.out_dim = V;
-        e->out_emb.w = load_weight_matrix(e, pl, "decoder.embedding.output_embedding", "input_output", V, H);
+        e->out_emb.in_dim = H; e->out_emb.out_dim = vocab_out;
+        e->out_emb.w = load_weight_matrix(e, pl, "decoder.embedding.output_embedding", "input_output", vocab_out, H);
     }
 
     uint64_t wbytes = e->out_emb.w.bytes, kvb = 0, stb = 0;
@@ -616,6 +639,7 @@ static void load_model(uzu_engine* e, const std::string& dir) {
             kvb += 2ull * kvd * 2;
             n_attn++;
         } else if (mty == "DeltaNetConfig") {
+            if (e->tp_sharded) throw std::runtime_error("tensor parallelism covers attention mixers only");
             L.is_attention = false;
             DeltaNetLayer& D = L.dn;
             D.num_heads = mc.at("num_heads").u32();
@@ -730,9 +754,14 @@ static void create_state_and_scratch(uzu_engine* e) {
     e->gate = dev((size_t)MAX_ROWS * max_qd * 2);
     e->fused_up = dev((size_t)MAX_ROWS * 2 * max_f * 2);
     e->gated = dev((size_t)MAX_ROWS * max_f * 2);
-    e->in_proj = dev((size_t)max_proj * 2);
-    e->delta_out = dev((size_t)max_vd * 2);
+    e->in_proj = dev((size_t)MAX_ROWS * max_proj * 2);
+    e->delta_out = dev((size_t)MAX_ROWS * max_vd * 2);
     e->logits = dev((size_t)e->logits_rows * V * 2);
+    if (e->tp_sharded) {
+        e->tp_partial = dev((size_t)MAX_ROWS * H * 4);
+        e->logits_local = dev((size_t)e->logits_rows * e->vocab_local * 2);
+        e->tp_gather = dev((size_t)e->logits_rows * V * 2);
+    }
     e->sampled = dev(MAX_ROWS * 4);
     e->seeds = dev(MAX_ROWS * 8);
     // two-pass attention scratch (only used for suffix <= 8 and context > 1024, like the reference dispatch)
@@ -813,6 +842,36 @@ static void encode_linear(uzu_command_buffer* cmd, const Linear& l, uint64_t a, 
     uzu_matmul_encode(cmd, &ma);
 }
 
+// Row-parallel projection (attention out / MLP down). Unsharded: the plain linear. Tensor-parallel shard: this rank's K slice gives an
+// f32 partial [m, H]; uzu_tp_all_reduce sums it over the ranks and rounds to bf16 once (the unsharded kernel's rounding point).
+static void encode_row_parallel(uzu_engine* e, uzu_command_buffer* cmd, const Linear& l, uint64_t a, uint32_t m, uint64_t d) {
+    if (!e->tp_sharded) {
+        encode_linear(cmd, l, a, m, d);
+        return;
+    }
+    uzu_matmul_args ma{};
+    ma.a = a;
+    ma.b = l.w.values.ptr(); ma.b_scales = l.w.scales.ptr(); ma.b_zero_points = l.w.zero_points.ptr(); ma.b_biases = l.w.biases.ptr();
+    ma.d = e->tp_partial.ptr();
+    ma.b_prologue = l.w.prologue; ma.b_mode = l.w.mode; ma.b_group_size = l.w.group_size; ma.b_transpose = 1; ma.ab_scale = 1.0f;
+    ma.m = m; ma.n = l.out_dim; ma.k = l.in_dim;
+    ma.weights_dt = ma.input_dt = UZU_DT_BF16;
+    ma.output_dt = UZU_DT_F32;
+    uzu_matmul_encode(cmd, &ma);
+    uzu_tp_all_reduce_encode(cmd, e->tp_partial.ptr(), m * l.out_dim, d);
+}
+
+// Readout (embedding.rs:374-456). Tensor-parallel shard: local vocabulary rows, then all-gather into the full logits rows.
+static void encode_readout(uzu_engine* e, uzu_command_buffer* cmd, uint64_t normed, uint32_t rows) {
+    if (!e->tp_sharded) {
+        encode_linear(cmd, e->out_emb, normed, rows, e->logits.ptr());
+        return;
+    }
+    encode_linear(cmd, e->out_emb, normed, rows, e->logits_local.ptr());
+    uzu_tp_all_gather_args ga{e->logits_local.ptr(), e->logits.ptr(), e->tp_gather.ptr(), rows, e->vocab_local};
+    uzu_tp_all_gather_encode(cmd, &ga);
+}
+
 enum ShortcutMode { ShortcutNone, ShortcutCopy, ShortcutAdd };
 
 static void encode_norm(uzu_command_buffer* cmd, const Norm& n, uint64_t input, uint64_t output, uint64_t shortcut, ShortcutMode mode, uint32_t rows) {
@@ -848,7 +907,7 @@ static uint64_t encode_attention(uzu_engine* e, uzu_command_buffer* cmd, const L
     if (A.has_gate) encode_linear(cmd, A.gate, hidden, pc.m, e->gate.ptr());
     encode_linear(cmd, A.qkv, hidden, pc.m, e->qkv.ptr());
     encode_attention_mix(e, cmd, L, S, pc, true);
-    encode_linear(cmd, A.out, e->attn_out.ptr(), pc.m, e->mixer_out.ptr());
+    encode_row_parallel(e, cmd, A.out, e->attn_out.ptr(), pc.m, e->mixer_out.ptr());
     return e->mixer_out.ptr();
 }
 
@@ -913,19 +972,31 @@ static void encode_attention_mix(uzu_engine* e, uzu_command_buffer* cmd, const L
 
 static uint64_t encode_delta_net(uzu_engine* e, uzu_command_buffer* cmd, const Layer& L, LayerState& S, uint64_t hidden, const PassCtx& pc) {
     const DeltaNetLayer& D = L.dn;
-    if (pc.m != 1) throw std::runtime_error("DeltaNet prefill (m > 1) is stepped token by token by the caller");
-    encode_linear(cmd, D.in_proj, hidden, 1, e->in_proj.ptr());
-    uzu_delta_net_conv_update_args ca{};
-    ca.conv_weight = D.conv_weight.ptr(); ca.bias = D.conv_bias.ptr(); ca.in_out = e->in_proj.ptr(); ca.state = S.conv_state.ptr();
-    ca.kernel_size = D.kernel_size; ca.conv_dim = D.conv_dim; ca.state_stride = D.kernel_size - 1; ca.has_bias = D.conv_has_bias;
-    uzu_delta_net_conv_update_encode(cmd, &ca);
-    uzu_delta_net_update_args ua{};
-    ua.in_proj = e->in_proj.ptr(); ua.a_log = D.a_log.ptr(); ua.dt_bias = D.dt_bias.ptr(); ua.norm_weight = D.norm_weight.ptr();
-    ua.state = S.ssm_state.ptr(); ua.out = e->delta_out.ptr();
-    ua.num_v_heads = D.num_heads; ua.num_k_heads = D.num_groups; ua.head_v_dim = D.value_head_dim; ua.key_dim = D.key_dim;
-    ua.value_dim = D.value_dim; ua.norm_epsilon = D.norm_epsilon; ua.head_k_dim = D.head_dim;
-    uzu_delta_net_update_encode(cmd, &ua);
-    encode_linear(cmd, D.out_proj, e->delta_out.ptr(), 1, e->mixer_out.ptr());
+    const uint32_t m = pc.m;
+    // m > 1 (prefill): the two projections run batched over the m rows (tensor-core GEMM for m >= 64); the recurrence itself -- the
+    // rolling conv state and the delta-rule state update -- is the decode branch (delta_net.rs flat m = 1 path) applied row by row in
+    // token order, so a batched prefill computes exactly what m single-token passes compute. (The reference's chunked-prefill core,
+    // Kernels::DeltaNetChunkedPrefill, evaluates the same recurrence in a different summation order; not restated here.)
+    encode_linear(cmd, D.in_proj, hidden, m, e->in_proj.ptr());
+    for (uint32_t t = 0; t < m; ++t) {
+        const uint64_t row = e->in_proj.ptr() + (size_t)t * D.total_proj_dim * 2;
+        uzu_delta_net_fused_update_args fa{};
+        uzu_delta_net_conv_update_args& ca = fa.conv;
+        ca.conv_weight = D.conv_weight.ptr(); ca.bias = D.conv_bias.ptr(); ca.in_out = row; ca.state = S.conv_state.ptr();
+        ca.kernel_size = D.kernel_size; ca.conv_dim = D.conv_dim; ca.state_stride = D.kernel_size - 1; ca.has_bias = D.conv_has_bias;
+        uzu_delta_net_update_args& ua = fa.update;
+        ua.in_proj = row; ua.a_log = D.a_log.ptr(); ua.dt_bias = D.dt_bias.ptr(); ua.norm_weight = D.norm_weight.ptr();
+        ua.state = S.ssm_state.ptr(); ua.out = e->delta_out.ptr() + (size_t)t * D.value_dim * 2;
+        ua.num_v_heads = D.num_heads; ua.num_k_heads = D.num_groups; ua.head_v_dim = D.value_head_dim; ua.key_dim = D.key_dim;
+        ua.value_dim = D.value_dim; ua.norm_epsilon = D.norm_epsilon; ua.head_k_dim = D.head_dim;
+        if (m > 1 && uzu_delta_net_fused_update_supported(&fa)) {
+            uzu_delta_net_fused_update_encode(cmd, &fa);          // conv + update in one launch per token
+        } else {
+            uzu_delta_net_conv_update_encode(cmd, &ca);
+            uzu_delta_net_update_encode(cmd, &ua);
+        }
+    }
+    encode_linear(cmd, D.out_proj, e->delta_out.ptr(), m, e->mixer_out.ptr());
     return e->mixer_out.ptr();
 }
 
@@ -959,14 +1030,14 @@ static void encode_decoder(uzu_engine* e, uzu_command_buffer* cmd, const PassCtx
         ga.act_operand = e->fused_up.ptr(); ga.fp_out = e->gated.ptr(); ga.gated_dim = L.hidden_dim; ga.batch_dim = m;
         ga.act_type = L.act; ga.interleaved = 1;
         uzu_gated_act_mul_encode(cmd, &ga);
-        encode_linear(cmd, L.down, e->gated.ptr(), m, e->hidden_a.ptr());
+        encode_row_parallel(e, cmd, L.down, e->gated.ptr(), m, e->hidden_a.ptr());
         hidden = e->hidden_a.ptr();
     }
     if (row_end <= row_begin) return;
     const uint32_t rows = row_end - row_begin;
     // output_norm over the requested rows, residual add into the same rows of the shortcut (transformer.rs:317-323)
     encode_norm(cmd, e->out_norm, hidden + (size_t)row_begin * H * 2, e->normed_out.ptr(), e->shortcut.ptr() + (size_t)row_begin * H * 2, ShortcutAdd, rows);
-    encode_linear(cmd, e->out_emb, e->normed_out.ptr(), rows, e->logits.ptr());  // readout (embedding.rs:374-456)
+    encode_readout(e, cmd, e->normed_out.ptr(), rows);
     if (e->has_logit_scale || e->has_logit_soft_cap)
         uzu_logit_transform_encode(cmd, e->logits.ptr(), rows * e->vocab, e->has_logit_scale ? e->logit_scale : 1.0f, e->logit_soft_cap, e->has_logit_soft_cap);
 }
@@ -1133,14 +1204,14 @@ static void encode_decoder_fused(uzu_engine* e, uzu_command_buffer* cmd, const P
             aa.scale = A.has_scale ? A.scale : 1.0f / sqrtf((float)D);
             aa.num_heads = Hq; aa.suffix_length = 1; aa.head_dim = D; aa.is_causal = A.is_causal; aa.dynamic_position = dyn;
             uzu_attention_single_pass_encode(cmd, &aa);
-            if (A.has_gate && fuse_sigmoid) {
+            if (A.has_gate && fuse_sigmoid && !e->tp_sharded) {
                 uzu_fused_linear_args g{};
                 g.matmul = linear_args(A.out, 0, 1, e->mixer_out.ptr());
                 g.prologue = 3; g.sg_attn = e->attn_out.ptr(); g.sg_gate = e->gate.ptr();
                 uzu_fused_linear_encode(cmd, &g);
             } else {
                 if (A.has_gate) uzu_sigmoid_gate_encode(cmd, e->gate.ptr(), e->attn_out.ptr(), Hq * D);
-                encode_linear(cmd, A.out, e->attn_out.ptr(), 1, e->mixer_out.ptr());
+                encode_row_parallel(e, cmd, A.out, e->attn_out.ptr(), 1, e->mixer_out.ptr());
             }
         } else {
             const DeltaNetLayer& Dn = L.dn;
@@ -1178,11 +1249,11 @@ static void encode_decoder_fused(uzu_engine* e, uzu_command_buffer* cmd, const P
             ga.act_type = L.act; ga.interleaved = 1;
             uzu_gated_act_mul_encode(cmd, &ga);
         }
-        encode_linear(cmd, L.down, e->gated.ptr(), 1, e->hidden_a.ptr());
+        encode_row_parallel(e, cmd, L.down, e->gated.ptr(), 1, e->hidden_a.ptr());
     }
     // output norm with the residual add in place on the current residual buffer (transformer.rs:317-323), readout, logit transform
     encode_norm(cmd, e->out_norm, e->hidden_a.ptr(), e->normed_out.ptr(), S[cur], ShortcutAdd, 1);
-    encode_linear(cmd, e->out_emb, e->normed_out.ptr(), 1, e->logits.ptr());
+    encode_readout(e, cmd, e->normed_out.ptr(), 1);
     if (e->has_logit_scale || e->has_logit_soft_cap)
         uzu_logit_transform_encode(cmd, e->logits.ptr(), e->vocab, e->has_logit_scale ? e->logit_scale : 1.0f, e->logit_soft_cap, e->has_logit_soft_cap);
     (void)pc;
@@ -1455,9 +1526,11 @@ uzu_status uzu_engine_prefill(uzu_engine* e, const uint32_t* tokens, uint32_t co
     UZU_ENGINE_TRY({
         if (!tokens || count == 0) throw std::runtime_error("prefill: empty prompt");
         if (sampling) e->sampling = *sampling;
-        // chunks of <= 1024 (stream.rs:194-195); only the last chunk's last row is sampled. Hybrid (DeltaNet) models are
-        // stepped token by token: this backend implements the DeltaNet decode branch only.
-        const uint32_t step = has_delta(e) ? 1 : MAX_ROWS;
+        // chunks of <= 1024 (stream.rs:194-195); only the last chunk's last row is sampled. Hybrid (DeltaNet) models take the same
+        // chunks: projections and MLPs batched, the DeltaNet recurrence row by row inside the pass (encode_delta_net).
+        // UZU_DELTA_PREFILL_STEPPED=1 restores one pass per token (A/B runs).
+        static const bool stepped = getenv("UZU_DELTA_PREFILL_STEPPED") != nullptr;
+        const uint32_t step = (stepped && has_delta(e)) ? 1 : MAX_ROWS;
         for (uint32_t s0 = 0; s0 < count; s0 += step) {
             const uint32_t n = std::min(step, count - s0);
             const bool last = s0 + n == count;
@@ -1514,7 +1587,6 @@ uzu_status uzu_engine_decode_device(uzu_engine* e, uint32_t steps, uint64_t out_
 uzu_status uzu_engine_forward(uzu_engine* e, const uint32_t* tokens, uint32_t count, uint32_t row_begin, uint32_t row_end, uint16_t* out_logits) {
     UZU_ENGINE_TRY({
         if (row_end > count || row_begin > row_end || row_end - row_begin > e->logits_rows) throw std::runtime_error("forward: bad row range (<= 16 rows)");
-        if (has_delta(e) && count != 1) throw std::runtime_error("forward: hybrid models take one token per pass");
         run_pass(e, tokens, count, row_begin, row_end, false);
         if (out_logits && row_end > row_begin)
             cudaMemcpy(out_logits, (void*)e->logits.ptr(), (size_t)(row_end - row_begin) * e->vocab * 2, cudaMemcpyDeviceToHost);
@@ -1629,6 +1701,50 @@ uzu_status uzu_engine_time_linears_select(uzu_engine* e, uint32_t iters, uint32_
         if (err != cudaSuccess || g.c->sticky != UZU_OK) throw std::runtime_error("time_linears failed: " + g.c->sticky_msg);
         if (out_seconds) *out_seconds = (double)ms * 1e-3;
         if (out_launches) *out_launches = g.c->launches - before;
+    });
+}
+
+uzu_status uzu_engine_time_prefill_linears(uzu_engine* e, uint32_t m, uint32_t iters, double* out_seconds, double* out_flops) {
+    UZU_ENGINE_TRY({
+        if (m == 0 || m > MAX_ROWS || iters == 0) throw std::runtime_error("time_prefill_linears: m must be in 1..1024, iters > 0");
+        cudaStream_t s = e->ctx->stream;
+        CmdGuard g(e->ctx, "prefill linears");
+        g.c->state = uzu_command_buffer::Encoding;
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        double flops = 0.0;
+        auto lin = [&](const Linear& l, uint64_t in, uint64_t out, bool count) {
+            encode_linear(g.c, l, in, m, out);
+            if (count) flops += 2.0 * m * (double)l.out_dim * (double)l.in_dim;
+        };
+        auto once = [&](bool count) {
+            for (auto& L : e->layers) {
+                if (L.is_attention) {
+                    if (L.attn.has_gate) lin(L.attn.gate, e->hidden_b.ptr(), e->gate.ptr(), count);
+                    lin(L.attn.qkv, e->hidden_b.ptr(), e->qkv.ptr(), count);
+                    lin(L.attn.out, e->attn_out.ptr(), e->mixer_out.ptr(), count);
+                } else {
+                    lin(L.dn.in_proj, e->hidden_b.ptr(), e->in_proj.ptr(), count);
+                    lin(L.dn.out_proj, e->delta_out.ptr(), e->mixer_out.ptr(), count);
+                }
+                lin(L.up, e->hidden_b.ptr(), e->fused_up.ptr(), count);
+                lin(L.down, e->gated.ptr(), e->hidden_a.ptr(), count);
+            }
+        };
+        once(false);   // warm-up
+        cudaStreamSynchronize(s);
+        cudaEventRecord(a, s);
+        for (uint32_t i = 0; i < iters; ++i) once(i == 0);
+        cudaEventRecord(b, s);
+        cudaError_t err = cudaEventSynchronize(b);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, a, b);
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        if (err != cudaSuccess || g.c->sticky != UZU_OK) throw std::runtime_error("time_prefill_linears failed: " + g.c->sticky_msg);
+        if (out_seconds) *out_seconds = (double)ms * 1e-3 / iters;
+        if (out_flops) *out_flops = flops;
     });
 }
 

@@ -51,11 +51,12 @@ struct QmmParams {
     uint32_t desc_lbo; // leading-dimension byte offset field (>> 4)
     uint32_t k_step;   // start-address increment (>> 4) per UMMA_K = 16 elements
     uint32_t idesc;    // instruction descriptor (kind::f16, bf16 x bf16 -> f32, M = 128, N = 128, both K-major)
+    uint32_t packed_path;  // 4-bit ZeroPoint / Symmetric: bf16x2 dequant, the lo plane is stored negated and its MMAs negate B (idesc bit 14)
 };
 
-constexpr int QMM_PRODUCERS = 128;
-constexpr int QMM_THREADS = 160;
 constexpr uint32_t QMM_TILE_BYTES = 128 * 64 * 2;  // one 128-row x 64-k bf16 tile
+constexpr int QMM_DEFAULT_PRODUCERS = 256;          // producer threads (B200 sweep, profiles/README.md)
+constexpr bool QMM_DEFAULT_COAL = true;             // cooperative coalesced code loads
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -128,6 +129,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 16-byte asynchronous global -> shared copy (L2 only); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // byte offset of the 16-byte chunk `ch` (8 bf16 along k) of row `row` inside a 128-row x 64-k tile
 __device__ __forceinline__ uint32_t tile_off(uint32_t row, uint32_t ch, uint32_t layout) {
     return layout == 0 ? row * 128u + ((ch ^ (row & 7u)) << 4)                     // SWIZZLE_128B: Swizzle<3,4,3> on byte addresses
@@ -139,23 +151,49 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// Two weights -> packed hi plane and lo plane words. w = fmaf(s, code, c): s*code is exact (<= 16 significant bits), so this is the
-// reference's `scale * code + corr` (kernel.rs:267-276) bit for bit.
-__device__ __forceinline__ void dequant_pair(uint32_t code0, uint32_t code1, float s, float c, uint32_t& hi, uint32_t& lo) {
-    const float f0 = __uint_as_float(0x4B000000u | code0) - 8388608.0f;   // exact int -> float
-    const float f1 = __uint_as_float(0x4B000000u | code1) - 8388608.0f;
-    const float w0 = fmaf(s, f0, c), w1 = fmaf(s, f1, c);
+// Code -> f32 without a conversion instruction: the code is shifted into the mantissa of 128.0f (4-bit) / 256.0f (8-bit), giving
+// BASE + code exactly; the BASE is folded into the per-group constant c' = corr - scale*BASE (exact for ZeroPoint / Symmetric, where
+// corr = -scale*zp: scale*(zp + BASE) has <= 17 significant bits), so w = fmaf(scale, BASE + code, c') == scale*code + corr, the
+// reference's expression (kernel.rs:267-276), bit for bit. `in_place_shift` = position of the code inside `word`.
+template <int BITS>
+__device__ __forceinline__ float code_to_f32(uint32_t word, int bit_pos) {
+    constexpr int target = BITS == 4 ? 16 : 15;                       // mantissa bit that weighs 1.0 under the BASE exponent
+    constexpr uint32_t mask = BITS == 4 ? 0x000F0000u : 0x007F8000u;
+    constexpr uint32_t base = BITS == 4 ? 0x43000000u : 0x43800000u;  // 128.0f / 256.0f
+    const uint32_t v = bit_pos <= target ? (word << (target - bit_pos)) : (word >> (bit_pos - target));
+    return __uint_as_float((v & mask) | base);
+}
+__device__ __forceinline__ __nv_bfloat162 u32_as_bf162(uint32_t v) { return *reinterpret_cast<__nv_bfloat162*>(&v); }
+__device__ __forceinline__ uint32_t bf162_as_u32(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
+// Two f32 weights -> packed hi plane word (RNE bf16) and lo plane word (the exact remainders, RNE bf16).
+__device__ __forceinline__ void split_pair(float w0, float w1, uint32_t& hi, uint32_t& lo) {
     hi = pack_bf16x2(w0, w1);
     const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
     lo = pack_bf16x2(w0 - h0, w1 - h1);
 }
 
-template <int BITS, int MT, int STAGES>
-__global__ void __launch_bounds__(QMM_THREADS, 1) qmm_umma_kernel(const QmmParams p) {
+// NP = producer threads (128 / 256 / 512): NP / 128 threads share a weight row, each dequantising 8 / (NP / 128) 16-byte chunks per
+// K block. One producer warp per scheduler (NP = 128) is latency-bound (measured: 0.29 IPC, 3000 clk per K block against 1024 clk
+// of MMA work); 4 warps per scheduler (NP = 512) hide the ALU / shared-memory latencies of the dequant chain.
+// COAL = cooperative, coalesced loading of the packed codes: measured with ncu, per-thread loads of "my row's 32 bytes" cost one
+// LSU wavefront per lane (32 rows = 32 different 128-byte lines per warp instruction, 256-512 wavefronts per K block, L1TEX 79 % busy).
+// With COAL the producers fetch a SUPER-BLOCK of 128 rows x 128 contiguous bytes (4 K blocks of 4-bit / 2 of 8-bit codes) with 8
+// consecutive lanes per row (4 lines per warp instruction, 8x fewer wavefronts) into one of two 16 KB buffers, XOR-swizzled by row
+// so that the per-row reads of the dequantising threads are bank-conflict free; a named barrier among the producer warps per
+// super-block hands the buffer from the loading threads to the consuming threads and recycles the other buffer.
+template <int BITS, int MT, int STAGES, int NP, bool COAL>
+__global__ void __launch_bounds__(NP + 32, 1) qmm_umma_kernel(const QmmParams p) {
     constexpr uint32_t A_BYTES = QMM_TILE_BYTES * MT;
     constexpr uint32_t STAGE_BYTES = A_BYTES + 2 * QMM_TILE_BYTES;
     constexpr uint32_t TMEM_COLS = 128 * MT;
-    constexpr int WORDS = BITS == 4 ? 8 : 16;   // 32-bit words of packed codes per row per K block (64 weights)
+    constexpr int TPR = NP / 128;                  // threads per weight row
+    constexpr int CPT = 8 / TPR;                   // 16-byte bf16 chunks (8 k each) per thread per K block
+    constexpr int WORDS = CPT * BITS / 4;          // 32-bit words of packed codes per thread per K block
+    constexpr int PIECE = WORDS >= 4 ? 16 : WORDS * 4;   // cp.async granule for the raw codes (16 or 8 bytes)
+    constexpr int PIECES = WORDS * 4 / PIECE;
+    constexpr int A_PER_THREAD = MT * 1024 / NP;   // activation chunks copied per thread per K block
+    static_assert(NP == 128 || NP == 256 || NP == 512, "producer threads");
+    static_assert(PIECE == 16 || PIECE == 8, "raw code granule");
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
@@ -174,7 +212,7 @@ __global__ void __launch_bounds__(QMM_THREADS, 1) qmm_umma_kernel(const QmmParam
     if (warp == 0) {
         if (lane == 0) {
             for (int s = 0; s < STAGES; ++s) {
-                mbar_init(full_bar(s), QMM_PRODUCERS);
+                mbar_init(full_bar(s), NP);
                 mbar_init(empty_bar(s), 1);
             }
             mbar_init(accum_bar, 1);
@@ -192,101 +230,245 @@ __global__ void __launch_bounds__(QMM_THREADS, 1) qmm_umma_kernel(const QmmParam
     const uint32_t nkb = p.k >> 6;
     const uint32_t layout = p.layout;
 
-    if (warp < 4) {
+    if (tid < (uint32_t)NP) {
         // ================================ producers ================================
-        const uint32_t brow = min(n0 + tid, p.n - 1);      // rows past n are computed from a clamped row and never stored
-        const uint8_t* wrow = p.w + (size_t)brow * p.row_bytes;
+        const uint32_t trow = tid & 127u, part = tid >> 7;          // `part` is warp-uniform: which CPT chunks of the row
+        const uint32_t brow = min(n0 + trow, p.n - 1);              // rows past n are computed from a clamped row and never stored
+        const uint8_t* wrow = p.w + (size_t)brow * p.row_bytes + part * (WORDS * 4);
         const __nv_bfloat16* srow = p.scales + (size_t)brow * p.groups_per_row;
         const uint8_t* zrow = p.zero_points ? p.zero_points + (size_t)brow * p.zp_stride : nullptr;
         const __nv_bfloat16* crow = p.biases ? p.biases + (size_t)brow * p.groups_per_row : nullptr;
-        pdl_wait();                                         // activations come from the previous kernel
-        for (uint32_t kb = 0; kb < nkb; ++kb) {
-            const uint32_t s = kb % STAGES, it = kb / STAGES;
-            // ---- global loads first (in flight while we wait for the stage to drain) ----
-            uint4 av[MT * 8];
+        // Software pipeline (all copies are cp.async, i.e. need no registers while in flight):
+        //   weights: raw packed codes of K block j go to a per-thread slot of a RAW-deep ring PW = RAW - 2 blocks ahead (HBM latency),
+        //   activations: the bf16 tile of K block j is copied straight into its swizzled UMMA stage PA = STAGES - 2 blocks ahead
+        //                (the stage must have been released by the MMA warp first; PA < STAGES - 1 leaves the MMA one block of slack),
+        //   scales / zero points: plain loads one block ahead (same cache line for 32+ consecutive blocks).
+        // Iteration t issues {A(t), W(t + DW)} as cp.async group t and then dequantises block t - PA.
+        constexpr int PA = STAGES - 2;
+        constexpr int RAW = BITS == 4 ? 8 : 4;
+        constexpr int PW = RAW - 2;
+        constexpr int DW = PW - PA;
+        static_assert(PA >= 1 && DW >= 0, "pipeline distances");
+        constexpr uint32_t ROW_CODE_BYTES = BITS * 8u;                          // packed bytes of one row per K block (64 weights)
+        constexpr uint32_t RAW_SLOT_BYTES = ROW_CODE_BYTES * 128u;
+        constexpr uint32_t CODE_BASE = BITS == 4 ? 128u : 256u;
+        constexpr uint32_t SB = 128u / ROW_CODE_BYTES;                          // K blocks per super-block (COAL): 4 (4-bit) / 2 (8-bit)
+        constexpr uint32_t SB_BYTES = 128u * 128u;                              // 128 rows x 128 bytes
+        constexpr int SB_PIECES = 1024 / NP;                                    // 16-byte pieces per thread per super-block
+        const uint32_t raw_base = smem_base + (uint32_t)STAGES * STAGE_BYTES;
+        const uint8_t* raw_ptr = smem + (size_t)STAGES * STAGE_BYTES;
+        auto issue_w = [&](uint32_t j) {
+            const uint32_t slot = raw_base + (j % RAW) * RAW_SLOT_BYTES + tid * PIECE;   // [piece][thread][PIECE]: conflict-free reads
 #pragma unroll
-            for (int i = 0; i < MT * 8; ++i) {
-                const uint32_t c = (uint32_t)i * QMM_PRODUCERS + tid, row = c >> 3, ch = c & 7u;
+            for (int i = 0; i < PIECES; ++i) {
+                if constexpr (PIECE == 16) cp_async16_zfill(slot + (uint32_t)i * (NP * 16u), wrow + (size_t)j * ROW_CODE_BYTES + i * 16, 16u);
+                else cp_async8(slot + (uint32_t)i * (NP * 8u), wrow + (size_t)j * ROW_CODE_BYTES + i * 8);
+            }
+        };
+        // COAL: super-block `sb` = K blocks [sb*SB, sb*SB + SB): piece (row, seg) = 16 bytes at byte seg*16 of the row's 128, stored at
+        // row*128 + ((seg ^ (row & 7)) << 4). Rows past n re-read row n-1 (never stored); a tail super-block shorter than 128 bytes
+        // zero-fills the K blocks that do not exist (never consumed).
+        const uint32_t k_bytes = p.row_bytes;
+        auto issue_sb = [&](uint32_t sb) {
+            const uint32_t buf = raw_base + (sb & 1u) * SB_BYTES;
+#pragma unroll
+            for (int i = 0; i < SB_PIECES; ++i) {
+                const uint32_t pi = (uint32_t)i * NP + tid, row = pi >> 3, seg = pi & 7u;
+                const uint32_t grow = min(n0 + row, p.n - 1);
+                const uint32_t off = sb * 128u + seg * 16u;                     // byte offset inside the weight row
+                const bool ok = off < k_bytes;
+                cp_async16_zfill(buf + row * 128u + ((seg ^ (row & 7u)) << 4), p.w + (size_t)grow * k_bytes + (ok ? off : 0u), ok ? 16u : 0u);
+            }
+        };
+        auto issue_a = [&](uint32_t j) {
+            const uint32_t st = smem_base + (j % STAGES) * STAGE_BYTES;
+#pragma unroll
+            for (int i = 0; i < A_PER_THREAD; ++i) {
+                const uint32_t c = (uint32_t)i * NP + tid, row = c >> 3, ch = c & 7u;
                 const uint32_t grow = m0 + row;
-                av[i] = make_uint4(0u, 0u, 0u, 0u);
-                if (grow < p.m) av[i] = *reinterpret_cast<const uint4*>(p.x + (size_t)grow * p.k + (size_t)kb * 64u + ch * 8u);
+                const bool ok = grow < p.m;                                            // rows past m are zero-filled (src-size 0)
+                const __nv_bfloat16* src = p.x + (size_t)(ok ? grow : 0u) * p.k + (size_t)j * 64u + ch * 8u;
+                cp_async16_zfill(st + (row >> 7) * QMM_TILE_BYTES + tile_off(row & 127u, ch, layout), src, ok ? 16u : 0u);
             }
-            uint32_t q[WORDS];
-#pragma unroll
-            for (int i = 0; i < WORDS / 4; ++i) {
-                const uint4 t = ldg_stream_u4(wrow + (size_t)kb * (WORDS * 4) + i * 16);
-                q[4 * i] = t.x ^ p.xor_mask; q[4 * i + 1] = t.y ^ p.xor_mask; q[4 * i + 2] = t.z ^ p.xor_mask; q[4 * i + 3] = t.w ^ p.xor_mask;
-            }
-            float sc[2], cc[2];
+        };
+        // the thread's CPT chunks cover k in [k0, k0 + 8*CPT) of the block; two halves so that group size 32 is handled at NP = 128
+        struct ScRaw { uint32_t s[2], c[2]; };
+        auto group_of = [&](uint32_t j, int h) { return (j * 64u + part * (CPT * 8u) + (uint32_t)h * (CPT * 4u)) / p.group_size; };
+        auto load_sc = [&](uint32_t j, ScRaw& r) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const uint32_t g = (kb * 64u + (uint32_t)h * 32u) / p.group_size;
-                const float s_ = bf2f(srow[g]);
+                const uint32_t g = group_of(j, h);
+                r.s[h] = reinterpret_cast<const uint16_t*>(srow)[g];
+                if (p.method == UZU_QMETHOD_SCALE_ZERO_POINT) r.c[h] = BITS == 4 ? zrow[g >> 1] : zrow[g];
+                else if (p.method == UZU_QMETHOD_SCALE_BIAS) r.c[h] = reinterpret_cast<const uint16_t*>(crow)[g];
+                else r.c[h] = 0u;
+            }
+        };
+        if constexpr (COAL) {
+            issue_sb(0);                                     // joins cp.async group 0; weights do not depend on the previous kernel
+        } else {
+#pragma unroll
+            for (int j = 0; j < DW; ++j)
+                if ((uint32_t)j < nkb) issue_w((uint32_t)j);
+        }
+        ScRaw nxt;
+        load_sc(0, nxt);
+        pdl_wait();                                         // activations come from the previous kernel
+        for (uint32_t t = 0; t < nkb + PA; ++t) {
+            if constexpr (COAL) {
+                // first K block of a super-block: its codes were issued SB iterations ago (group t - SB; super-block 0: before the
+                // loop) -> wait for this thread's pieces, then the named barrier publishes everyone's pieces and proves that every
+                // thread has finished the previous super-block, whose buffer the next super-block's loads may now overwrite.
+                if (t >= (uint32_t)PA && ((t - PA) % SB) == 0u) {
+                    if (t == (uint32_t)PA) cp_async_wait_group<0>();
+                    else cp_async_wait_group<(int)SB - 1>();
+                    asm volatile("bar.sync 1, %0;" ::"n"(NP) : "memory");
+                    const uint32_t nsb = (t - PA) / SB + 1u;
+                    if (nsb * SB < nkb) issue_sb(nsb);
+                }
+            }
+            if (t < nkb) {
+                mbar_wait(empty_bar(t % STAGES), ((t / STAGES) & 1u) ^ 1u);
+                issue_a(t);
+                if constexpr (!COAL) {
+                    if (t + DW < nkb) issue_w(t + DW);
+                }
+            }
+            cp_async_commit_group();
+            if (t < (uint32_t)PA) continue;
+            const uint32_t kb = t - PA, s = kb % STAGES;
+            const ScRaw cur = nxt;
+            if (kb + 1 < nkb) load_sc(kb + 1, nxt);
+            float sc[2], cc[2];
+            uint32_t sc2[2], zb2[2];                         // packed bf16x2 (scale, scale) and (128 + zp, 128 + zp)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t g = group_of(kb, h);
+                const float s_ = __uint_as_float(cur.s[h] << 16);
+                sc2[h] = cur.s[h] | (cur.s[h] << 16);
+                zb2[h] = 0u;
                 float c_;
                 if (p.method == UZU_QMETHOD_SCALE_ZERO_POINT) {
-                    uint32_t z;
-                    if (BITS == 4) {
-                        const uint32_t zb = zrow[g >> 1];
-                        z = (g & 1u) ? (zb >> 4) : (zb & 15u);
-                    } else {
-                        z = zrow[g];
-                    }
-                    c_ = -s_ * (float)z;
+                    const uint32_t z = BITS == 4 ? ((g & 1u) ? (cur.c[h] >> 4) : (cur.c[h] & 15u)) : cur.c[h];
+                    c_ = -s_ * (float)(z + CODE_BASE);              // corr - scale*BASE, exact
+                    zb2[h] = (0x4300u | z) * 0x00010001u;           // bf16 bits of 128 + z (z < 128), both halves
                 } else if (p.method == UZU_QMETHOD_SCALE_BIAS) {
-                    c_ = bf2f(crow[g]);
+                    c_ = __uint_as_float(cur.c[h] << 16);
                 } else {
-                    c_ = -s_ * (float)(1u << (BITS - 1));
+                    c_ = -s_ * (float)((1u << (BITS - 1)) + CODE_BASE);
+                    zb2[h] = (0x4300u | 8u) * 0x00010001u;
                 }
                 sc[h] = s_;
                 cc[h] = c_;
             }
-            // ---- wait for the MMA warp to release the stage, then fill it ----
-            mbar_wait(empty_bar(s), (it & 1u) ^ 1u);
-            uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+            cp_async_wait_group<PA>();                      // groups <= kb have landed: this thread's A chunks and its raw codes
+            uint32_t q[WORDS];
+            if constexpr (COAL) {
+                // this thread's WORDS*4 bytes sit at byte (kb % SB)*ROW_CODE_BYTES + part*WORDS*4 of its row's 128-byte super-block line
+                const uint8_t* line = raw_ptr + (size_t)((kb / SB) & 1u) * SB_BYTES + trow * 128u;
+                const uint32_t o = (kb % SB) * ROW_CODE_BYTES + part * (WORDS * 4u);
 #pragma unroll
-            for (int i = 0; i < MT * 8; ++i) {
-                const uint32_t c = (uint32_t)i * QMM_PRODUCERS + tid, row = c >> 3, ch = c & 7u;
-                *reinterpret_cast<uint4*>(st + (row >> 7) * QMM_TILE_BYTES + tile_off(row & 127u, ch, layout)) = av[i];
+                for (int i = 0; i < PIECES; ++i) {
+                    const uint32_t ob = o + (uint32_t)i * PIECE;
+                    const uint8_t* src = line + (((ob >> 4) ^ (trow & 7u)) << 4) + (ob & 15u);
+                    if constexpr (PIECE == 16) {
+                        const uint4 v4 = *reinterpret_cast<const uint4*>(src);
+                        q[4 * i] = v4.x ^ p.xor_mask; q[4 * i + 1] = v4.y ^ p.xor_mask; q[4 * i + 2] = v4.z ^ p.xor_mask; q[4 * i + 3] = v4.w ^ p.xor_mask;
+                    } else {
+                        const uint2 v2 = *reinterpret_cast<const uint2*>(src);
+                        q[2 * i] = v2.x ^ p.xor_mask; q[2 * i + 1] = v2.y ^ p.xor_mask;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < PIECES; ++i) {
+                    const uint8_t* src = raw_ptr + (size_t)(kb % RAW) * RAW_SLOT_BYTES + (size_t)i * (NP * PIECE) + tid * PIECE;
+                    if constexpr (PIECE == 16) {
+                        const uint4 v4 = *reinterpret_cast<const uint4*>(src);
+                        q[4 * i] = v4.x ^ p.xor_mask; q[4 * i + 1] = v4.y ^ p.xor_mask; q[4 * i + 2] = v4.z ^ p.xor_mask; q[4 * i + 3] = v4.w ^ p.xor_mask;
+                    } else {
+                        const uint2 v2 = *reinterpret_cast<const uint2*>(src);
+                        q[2 * i] = v2.x ^ p.xor_mask; q[2 * i + 1] = v2.y ^ p.xor_mask;
+                    }
+                }
             }
+            uint8_t* st = smem + (size_t)s * STAGE_BYTES;
             uint8_t* bhi = st + A_BYTES;
             uint8_t* blo = bhi + QMM_TILE_BYTES;
+            if (BITS == 4 && p.packed_path) {
+                // ---- packed bf16x2 path (4-bit ZeroPoint / Symmetric): w = s*(q - z) ----
+                // d = (128 + q) - (128 + z) is an exact small integer; hi = RNE_bf16(s*d) is ONE HMUL2; -lo = fma(-s, d, hi) is exact
+                // (s*d has <= 13 significant bits, the remainder <= 8) -> hi + lo == s*(q - z) == the reference's scale*code + corr.
+                // Nibbles p and p+4 of a word are 16 bits apart, so one shift + one LOP3 yields the pair (e_p, e_p+4); the planes are
+                // put back into k order with PRMT before the 16-byte stores. The lo plane is stored NEGATED (no separate negation);
+                // its MMAs run with the instruction descriptor's negate-B bit.
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {               // chunk = 8 consecutive k
-                const float s_ = sc[ch >> 2], c_ = cc[ch >> 2];
-                uint4 hi4, lo4;
-                if constexpr (BITS == 4) {
-                    const uint32_t w = q[ch];
-                    dequant_pair(w & 15u, (w >> 4) & 15u, s_, c_, hi4.x, lo4.x);
-                    dequant_pair((w >> 8) & 15u, (w >> 12) & 15u, s_, c_, hi4.y, lo4.y);
-                    dequant_pair((w >> 16) & 15u, (w >> 20) & 15u, s_, c_, hi4.z, lo4.z);
-                    dequant_pair((w >> 24) & 15u, w >> 28, s_, c_, hi4.w, lo4.w);
-                } else {
-                    const uint32_t w0 = q[2 * ch], w1 = q[2 * ch + 1];
-                    dequant_pair(w0 & 255u, (w0 >> 8) & 255u, s_, c_, hi4.x, lo4.x);
-                    dequant_pair((w0 >> 16) & 255u, w0 >> 24, s_, c_, hi4.y, lo4.y);
-                    dequant_pair(w1 & 255u, (w1 >> 8) & 255u, s_, c_, hi4.z, lo4.z);
-                    dequant_pair((w1 >> 16) & 255u, w1 >> 24, s_, c_, hi4.w, lo4.w);
+                for (int ch = 0; ch < CPT; ++ch) {
+                    const int h = ch / (CPT / 2);
+                    const uint32_t s2 = sc2[h], ns2 = s2 ^ 0x80008000u, z2 = zb2[h];
+                    uint32_t H[4], L[4];
+#pragma unroll
+                    for (int pr = 0; pr < 4; ++pr) {
+                        const uint32_t pq = ((q[ch] >> (4 * pr)) & 0x000F000Fu) | 0x43004300u;      // bf16x2 (128 + e_p, 128 + e_p+4)
+                        const __nv_bfloat162 d = __hsub2(u32_as_bf162(pq), u32_as_bf162(z2));
+                        const __nv_bfloat162 hh = __hmul2(u32_as_bf162(s2), d);
+                        const __nv_bfloat162 nl = __hfma2(u32_as_bf162(ns2), d, hh);
+                        H[pr] = bf162_as_u32(hh);
+                        L[pr] = bf162_as_u32(nl);
+                    }
+                    uint4 hi4, lo4;
+                    hi4.x = __byte_perm(H[0], H[1], 0x5410); hi4.y = __byte_perm(H[2], H[3], 0x5410);
+                    hi4.z = __byte_perm(H[0], H[1], 0x7632); hi4.w = __byte_perm(H[2], H[3], 0x7632);
+                    lo4.x = __byte_perm(L[0], L[1], 0x5410); lo4.y = __byte_perm(L[2], L[3], 0x5410);
+                    lo4.z = __byte_perm(L[0], L[1], 0x7632); lo4.w = __byte_perm(L[2], L[3], 0x7632);
+                    const uint32_t off = tile_off(trow, part * CPT + (uint32_t)ch, layout);
+                    *reinterpret_cast<uint4*>(bhi + off) = hi4;
+                    *reinterpret_cast<uint4*>(blo + off) = lo4;
                 }
-                const uint32_t off = tile_off(tid, (uint32_t)ch, layout);
-                *reinterpret_cast<uint4*>(bhi + off) = hi4;
-                *reinterpret_cast<uint4*>(blo + off) = lo4;
+            } else {
+                // ---- f32 path (8-bit codes, MLX scale/bias): w = fmaf(s, code, c) in f32, then the hi / lo split ----
+                const bool mlx = p.method == UZU_QMETHOD_SCALE_BIAS;
+#pragma unroll
+                for (int ch = 0; ch < CPT; ++ch) {
+                    const int h = ch / (CPT / 2);
+                    const float s_ = sc[h], c_ = cc[h];
+                    float wv[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float f;
+                        if constexpr (BITS == 4) f = code_to_f32<4>(q[ch], 4 * e);
+                        else f = code_to_f32<8>(q[(2 * ch + (e >> 2)) % WORDS], 8 * (e & 3));
+                        if (mlx) f = __fadd_rn(f, -(float)CODE_BASE);   // MLX: keep the reference's scale*code + bias rounding
+                        wv[e] = fmaf(s_, f, c_);
+                    }
+                    uint4 hi4, lo4;
+                    split_pair(wv[0], wv[1], hi4.x, lo4.x);
+                    split_pair(wv[2], wv[3], hi4.y, lo4.y);
+                    split_pair(wv[4], wv[5], hi4.z, lo4.z);
+                    split_pair(wv[6], wv[7], hi4.w, lo4.w);
+                    const uint32_t off = tile_off(trow, part * CPT + (uint32_t)ch, layout);
+                    *reinterpret_cast<uint4*>(bhi + off) = hi4;
+                    *reinterpret_cast<uint4*>(blo + off) = lo4;
+                }
             }
-            fence_proxy_async_smem();                       // generic-proxy stores -> visible to tcgen05.mma (async proxy)
+            fence_proxy_async_smem();                       // generic-proxy writes (st.shared, cp.async) -> visible to tcgen05.mma
             mbar_arrive(full_bar(s));
         }
 
         // ================================ epilogue ================================
+        // warp w reads TMEM lanes 32*(w % 4) .. +31 (token rows); with more than 4 producer warps the 32-column blocks are split by w / 4
         mbar_wait(accum_bar, 0);
         tc_fence_after();
         const bool vec_ok = p.d_is_f32 ? ((p.n & 3u) == 0 && ((uintptr_t)p.d & 15u) == 0) : ((p.n & 7u) == 0 && ((uintptr_t)p.d & 15u) == 0);
+        const uint32_t lane_grp = warp & 3u;
 #pragma unroll 1
         for (int mt = 0; mt < MT; ++mt) {
-            const uint32_t row = m0 + (uint32_t)mt * 128u + warp * 32u + lane;
+            const uint32_t row = m0 + (uint32_t)mt * 128u + lane_grp * 32u + lane;
 #pragma unroll 1
-            for (int cb = 0; cb < 4; ++cb) {
+            for (uint32_t cb = warp >> 2; cb < 4u; cb += (uint32_t)TPR) {
                 uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((warp * 32u) << 16) + (uint32_t)mt * 128u + (uint32_t)cb * 32u, v);
-                const uint32_t col0 = n0 + (uint32_t)cb * 32u;
+                tmem_ld_32x32(tmem_base + ((lane_grp * 32u) << 16) + (uint32_t)mt * 128u + cb * 32u, v);
+                const uint32_t col0 = n0 + cb * 32u;
                 if (row >= p.m || col0 >= p.n) continue;
                 const size_t obase = (size_t)row * p.n + col0;
                 float f[32];
@@ -316,11 +498,12 @@ __global__ void __launch_bounds__(QMM_THREADS, 1) qmm_umma_kernel(const QmmParam
                                               pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
                     }
                 } else {
-#pragma unroll 1
+#pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        if (col0 + (uint32_t)j >= p.n) break;
-                        if (p.d_is_f32) reinterpret_cast<float*>(p.d)[obase + j] = f[j];
-                        else reinterpret_cast<__nv_bfloat16*>(p.d)[obase + j] = f2bf(f[j]);
+                        if (col0 + (uint32_t)j < p.n) {
+                            if (p.d_is_f32) reinterpret_cast<float*>(p.d)[obase + j] = f[j];
+                            else reinterpret_cast<__nv_bfloat16*>(p.d)[obase + j] = f2bf(f[j]);
+                        }
                     }
                 }
             }
@@ -336,6 +519,7 @@ __global__ void __launch_bounds__(QMM_THREADS, 1) qmm_umma_kernel(const QmmParam
                 const uint32_t bh_addr = a_addr + A_BYTES, bl_addr = bh_addr + QMM_TILE_BYTES;
                 const uint64_t hi = (uint64_t)p.desc_hi << 32;
                 const uint32_t lbo = p.desc_lbo << 16;
+                const uint32_t idesc_lo = (BITS == 4 && p.packed_path) ? (p.idesc | (1u << 14)) : p.idesc;
 #pragma unroll
                 for (uint32_t kk = 0; kk < 4; ++kk) {
                     const uint64_t dbh = hi | (uint64_t)((((bh_addr >> 4) + kk * p.k_step) & 0x3FFFu) | lbo);
@@ -344,7 +528,7 @@ __global__ void __launch_bounds__(QMM_THREADS, 1) qmm_umma_kernel(const QmmParam
                     for (uint32_t mt = 0; mt < (uint32_t)MT; ++mt) {
                         const uint64_t da = hi | (uint64_t)(((((a_addr + mt * QMM_TILE_BYTES) >> 4) + kk * p.k_step) & 0x3FFFu) | lbo);
                         umma_bf16(tmem_base + mt * 128u, da, dbh, p.idesc, (kb | kk) != 0u ? 1u : 0u);
-                        umma_bf16(tmem_base + mt * 128u, da, dbl, p.idesc, 1u);
+                        umma_bf16(tmem_base + mt * 128u, da, dbl, idesc_lo, 1u);
                     }
                 }
                 umma_commit(empty_bar(s));                  // stage reusable once these MMAs have read it
@@ -367,6 +551,7 @@ struct UmmaTuning {
     int layout = -1;               // -1 = default (SWIZZLE_128B)
     uint32_t desc_hi = 0, desc_lbo = 0, k_step = 0, idesc = 0;
     int mt = 0;                    // 0 = heuristic
+    int np = 0;                    // producer threads, 0 = default
     bool custom = false;
 };
 static UmmaTuning g_umma;
@@ -378,15 +563,28 @@ static constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
-template <int BITS, int MT, int STAGES>
+template <int BITS, int MT, int STAGES, int NP, bool COAL>
 static void launch_qmm(uzu_command_buffer* cmd, const QmmParams& p, dim3 grid) {
-    constexpr size_t smem = (size_t)STAGES * (QMM_TILE_BYTES * MT + 2 * QMM_TILE_BYTES) + 1024;
+    // stages + raw-code ring (32 KB: 8 / 4 per-thread K-block slots, or two 16 KB super-block buffers) + alignment slack
+    constexpr size_t smem = (size_t)STAGES * (QMM_TILE_BYTES * MT + 2 * QMM_TILE_BYTES) + 32768 + 1024;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(qmm_umma_kernel<BITS, MT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(qmm_umma_kernel<BITS, MT, STAGES, NP, COAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done = true;
     }
-    launch(cmd, "matmul qmm_umma_kernel", qmm_umma_kernel<BITS, MT, STAGES>, grid, dim3(QMM_THREADS), smem, p);
+    launch(cmd, "matmul qmm_umma_kernel", qmm_umma_kernel<BITS, MT, STAGES, NP, COAL>, grid, dim3(NP + 32), smem, p);
+}
+template <int BITS, int MT, int STAGES>
+static void launch_qmm_np(uzu_command_buffer* cmd, const QmmParams& p, dim3 grid, int np, bool coal) {
+    if (coal) {
+        if (np == 128) launch_qmm<BITS, MT, STAGES, 128, true>(cmd, p, grid);
+        else if (np == 256) launch_qmm<BITS, MT, STAGES, 256, true>(cmd, p, grid);
+        else launch_qmm<BITS, MT, STAGES, 512, true>(cmd, p, grid);
+    } else {
+        if (np == 128) launch_qmm<BITS, MT, STAGES, 128, false>(cmd, p, grid);
+        else if (np == 256) launch_qmm<BITS, MT, STAGES, 256, false>(cmd, p, grid);
+        else launch_qmm<BITS, MT, STAGES, 512, false>(cmd, p, grid);
+    }
 }
 
 bool prefill_gemm_applicable(const uzu_matmul_args& a) {
@@ -438,6 +636,8 @@ void encode_prefill_gemm(uzu_command_buffer* cmd, const uzu_matmul_args& a) {
     p.desc_lbo = 1;
     p.k_step = 2;
     p.idesc = umma_idesc_bf16(128, 128);
+    static const bool packed_ok = [] { const char* e = getenv("UZU_QMM_PACKED"); return !e || atoi(e) != 0; }();   // 0: f32 dequant path for A/B runs
+    p.packed_path = (packed_ok && bits == 4 && p.method != UZU_QMETHOD_SCALE_BIAS) ? 1u : 0u;
     if (g_umma.custom) {
         p.layout = (uint32_t)g_umma.layout;
         p.desc_hi = g_umma.desc_hi; p.desc_lbo = g_umma.desc_lbo; p.k_step = g_umma.k_step;
@@ -448,10 +648,14 @@ void encode_prefill_gemm(uzu_command_buffer* cmd, const uzu_matmul_args& a) {
     if (a.m <= 128u) mt = 1;
     if (g_umma.mt == 1 || g_umma.mt == 2) mt = g_umma.mt;
     const dim3 grid(nt, (a.m + 128u * mt - 1) / (128u * mt));
+    static const int np_env = [] { const char* e = getenv("UZU_QMM_PRODUCERS"); return e ? atoi(e) : 0; }();   // 128 | 256 | 512 (A/B runs)
+    const int np = g_umma.np ? g_umma.np : ((np_env == 128 || np_env == 256 || np_env == 512) ? np_env : QMM_DEFAULT_PRODUCERS);
+    static const int coal_env = [] { const char* e = getenv("UZU_QMM_COAL"); return e ? atoi(e) : -1; }();       // 0 | 1 (A/B runs)
+    const bool coal = coal_env < 0 ? QMM_DEFAULT_COAL : coal_env != 0;
     if (bits == 4) {
-        if (mt == 2) launch_qmm<4, 2, 3>(cmd, p, grid); else launch_qmm<4, 1, 4>(cmd, p, grid);
+        if (mt == 2) launch_qmm_np<4, 2, 3>(cmd, p, grid, np, coal); else launch_qmm_np<4, 1, 4>(cmd, p, grid, np, coal);
     } else {
-        if (mt == 2) launch_qmm<8, 2, 3>(cmd, p, grid); else launch_qmm<8, 1, 4>(cmd, p, grid);
+        if (mt == 2) launch_qmm_np<8, 2, 3>(cmd, p, grid, np, coal); else launch_qmm_np<8, 1, 4>(cmd, p, grid, np, coal);
     }
 }
 
@@ -461,5 +665,7 @@ extern "C" void uzu_debug_set_umma(int layout, uint32_t desc_hi, uint32_t desc_l
     uzu::g_umma.custom = layout >= 0;
     uzu::g_umma.layout = layout;
     uzu::g_umma.desc_hi = desc_hi; uzu::g_umma.desc_lbo = desc_lbo; uzu::g_umma.k_step = k_step; uzu::g_umma.idesc = idesc;
-    uzu::g_umma.mt = mt;
+    uzu::g_umma.mt = mt & 0xff;                      // low byte: tokens-per-CTA factor; bits 8.. : producer threads (128 | 256 | 512)
+    const int np = mt >> 8;
+    uzu::g_umma.np = (np == 128 || np == 256 || np == 512) ? np : 0;
 }
