@@ -22,8 +22,9 @@ VARIANTS = [
     ("default int8", -1, 0, 0, 0, 0, 1, 8),
     ("sw128 lbo=0", 0, 0x40004040, 0, 2, 0, 1, 4),
     ("sw128 version=0", 0, 0x40000040, 1, 2, 0, 1, 4),
-    ("noswizzle lbo=128 sbo=1024", 1, 0x00004040, 8, 16, 0, 1, 4),
-    ("noswizzle lbo=1024 sbo=128", 1, 0x00004008, 64, 16, 0, 1, 4),
+    # (round-1 history: the no-swizzle core-matrix layout -- 8 rows x 16 B, LBO = 128, SBO = 1024, k step 256 B -- also matched the
+    #  reference and LBO/SBO swapped did not; the kernel now keeps the SWIZZLE_128B writer only, so those variants are gone)
+    ("sw128 wrong sbo=512 (must FAIL: proves the probe can tell)", 0, 0x40004020, 1, 2, 0, 1, 4),
 ]
 
 

@@ -46,7 +46,7 @@ struct QmmParams {
     uint32_t method, xor_mask, d_is_f32, accumulate, has_soft_cap;
     float ab_scale, soft_cap;
     // UMMA encodings, chosen by the host so that tools/umma_probe.py can sweep alternatives without recompiling
-    uint32_t layout;   // 0 = SWIZZLE_128B K-major atoms, 1 = SWIZZLE_NONE core matrices (8 rows x 16 B)
+    uint32_t gshift;   // log2(group_size): quantisation group of element k = k >> gshift
     uint32_t desc_hi;  // upper 32 bits of the shared-memory matrix descriptor (SBO, version, layout type)
     uint32_t desc_lbo; // leading-dimension byte offset field (>> 4)
     uint32_t k_step;   // start-address increment (>> 4) per UMMA_K = 16 elements
@@ -140,10 +140,11 @@ __device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void* src) {
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// byte offset of the 16-byte chunk `ch` (8 bf16 along k) of row `row` inside a 128-row x 64-k tile
-__device__ __forceinline__ uint32_t tile_off(uint32_t row, uint32_t ch, uint32_t layout) {
-    return layout == 0 ? row * 128u + ((ch ^ (row & 7u)) << 4)                     // SWIZZLE_128B: Swizzle<3,4,3> on byte addresses
-                       : (row >> 3) * 1024u + ch * 128u + (row & 7u) * 16u;         // core matrices: 8 rows x 16 B contiguous
+// byte offset of the 16-byte chunk `ch` (8 bf16 along k) of row `row` inside a 128-row x 64-k tile. (The no-swizzle core-matrix
+// layout, LBO = 128 / SBO = 1024, was also verified with tools/umma_probe.py in an earlier revision; one layout is kept so the offset
+// arithmetic is compile-time.)
+__device__ __forceinline__ uint32_t tile_off(uint32_t row, uint32_t ch) {
+    return row * 128u + ((ch ^ (row & 7u)) << 4);   // SWIZZLE_128B: Swizzle<3,4,3> on byte addresses (8-row x 128-byte atoms)
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
@@ -228,7 +229,6 @@ __global__ void __launch_bounds__(NP + 32, 1) qmm_umma_kernel(const QmmParams p)
 
     const uint32_t n0 = blockIdx.x * 128u, m0 = blockIdx.y * (128u * MT);
     const uint32_t nkb = p.k >> 6;
-    const uint32_t layout = p.layout;
 
     if (tid < (uint32_t)NP) {
         // ================================ producers ================================
@@ -280,20 +280,21 @@ __global__ void __launch_bounds__(NP + 32, 1) qmm_umma_kernel(const QmmParams p)
                 cp_async16_zfill(buf + row * 128u + ((seg ^ (row & 7u)) << 4), p.w + (size_t)grow * k_bytes + (ok ? off : 0u), ok ? 16u : 0u);
             }
         };
-        auto issue_a = [&](uint32_t j) {
-            const uint32_t st = smem_base + (j % STAGES) * STAGE_BYTES;
+        auto issue_a = [&](uint32_t j, uint32_t stage) {
+            const uint32_t st = smem_base + stage * STAGE_BYTES;
 #pragma unroll
             for (int i = 0; i < A_PER_THREAD; ++i) {
                 const uint32_t c = (uint32_t)i * NP + tid, row = c >> 3, ch = c & 7u;
                 const uint32_t grow = m0 + row;
                 const bool ok = grow < p.m;                                            // rows past m are zero-filled (src-size 0)
                 const __nv_bfloat16* src = p.x + (size_t)(ok ? grow : 0u) * p.k + (size_t)j * 64u + ch * 8u;
-                cp_async16_zfill(st + (row >> 7) * QMM_TILE_BYTES + tile_off(row & 127u, ch, layout), src, ok ? 16u : 0u);
+                cp_async16_zfill(st + (row >> 7) * QMM_TILE_BYTES + tile_off(row & 127u, ch), src, ok ? 16u : 0u);
             }
         };
         // the thread's CPT chunks cover k in [k0, k0 + 8*CPT) of the block; two halves so that group size 32 is handled at NP = 128
         struct ScRaw { uint32_t s[2], c[2]; };
-        auto group_of = [&](uint32_t j, int h) { return (j * 64u + part * (CPT * 8u) + (uint32_t)h * (CPT * 4u)) / p.group_size; };
+        const uint32_t gshift = p.gshift;
+        auto group_of = [&](uint32_t j, int h) { return (j * 64u + part * (CPT * 8u) + (uint32_t)h * (CPT * 4u)) >> gshift; };
         auto load_sc = [&](uint32_t j, ScRaw& r) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -314,29 +315,34 @@ __global__ void __launch_bounds__(NP + 32, 1) qmm_umma_kernel(const QmmParams p)
         ScRaw nxt;
         load_sc(0, nxt);
         pdl_wait();                                         // activations come from the previous kernel
+        uint32_t a_stage = 0, a_parity = 1;                 // issue side: stage of K block t, parity its `empty` wait needs
+        uint32_t c_stage = 0;                               // consume side: stage of K block t - PA
+        uint32_t c_sub = 0, c_buf = 0;                      // COAL: K block index inside its super-block, buffer of that super-block
         for (uint32_t t = 0; t < nkb + PA; ++t) {
             if constexpr (COAL) {
                 // first K block of a super-block: its codes were issued SB iterations ago (group t - SB; super-block 0: before the
                 // loop) -> wait for this thread's pieces, then the named barrier publishes everyone's pieces and proves that every
                 // thread has finished the previous super-block, whose buffer the next super-block's loads may now overwrite.
-                if (t >= (uint32_t)PA && ((t - PA) % SB) == 0u) {
+                if (t >= (uint32_t)PA && c_sub == 0u) {
                     if (t == (uint32_t)PA) cp_async_wait_group<0>();
                     else cp_async_wait_group<(int)SB - 1>();
                     asm volatile("bar.sync 1, %0;" ::"n"(NP) : "memory");
-                    const uint32_t nsb = (t - PA) / SB + 1u;
+                    const uint32_t nsb = (t - PA) / SB + 1u;            // SB is a power of two
                     if (nsb * SB < nkb) issue_sb(nsb);
                 }
             }
             if (t < nkb) {
-                mbar_wait(empty_bar(t % STAGES), ((t / STAGES) & 1u) ^ 1u);
-                issue_a(t);
+                mbar_wait(empty_bar(a_stage), a_parity);
+                issue_a(t, a_stage);
+                if (++a_stage == (uint32_t)STAGES) { a_stage = 0; a_parity ^= 1u; }
                 if constexpr (!COAL) {
                     if (t + DW < nkb) issue_w(t + DW);
                 }
             }
             cp_async_commit_group();
             if (t < (uint32_t)PA) continue;
-            const uint32_t kb = t - PA, s = kb % STAGES;
+            const uint32_t kb = t - PA, s = c_stage;
+            if (++c_stage == (uint32_t)STAGES) c_stage = 0;
             const ScRaw cur = nxt;
             if (kb + 1 < nkb) load_sc(kb + 1, nxt);
             float sc[2], cc[2];
@@ -365,8 +371,9 @@ __global__ void __launch_bounds__(NP + 32, 1) qmm_umma_kernel(const QmmParams p)
             uint32_t q[WORDS];
             if constexpr (COAL) {
                 // this thread's WORDS*4 bytes sit at byte (kb % SB)*ROW_CODE_BYTES + part*WORDS*4 of its row's 128-byte super-block line
-                const uint8_t* line = raw_ptr + (size_t)((kb / SB) & 1u) * SB_BYTES + trow * 128u;
-                const uint32_t o = (kb % SB) * ROW_CODE_BYTES + part * (WORDS * 4u);
+                const uint8_t* line = raw_ptr + (size_t)c_buf * SB_BYTES + trow * 128u;
+                const uint32_t o = c_sub * ROW_CODE_BYTES + part * (WORDS * 4u);
+                if (++c_sub == SB) { c_sub = 0; c_buf ^= 1u; }
 #pragma unroll
                 for (int i = 0; i < PIECES; ++i) {
                     const uint32_t ob = o + (uint32_t)i * PIECE;
@@ -421,7 +428,7 @@ __global__ void __launch_bounds__(NP + 32, 1) qmm_umma_kernel(const QmmParams p)
                     hi4.z = __byte_perm(H[0], H[1], 0x7632); hi4.w = __byte_perm(H[2], H[3], 0x7632);
                     lo4.x = __byte_perm(L[0], L[1], 0x5410); lo4.y = __byte_perm(L[2], L[3], 0x5410);
                     lo4.z = __byte_perm(L[0], L[1], 0x7632); lo4.w = __byte_perm(L[2], L[3], 0x7632);
-                    const uint32_t off = tile_off(trow, part * CPT + (uint32_t)ch, layout);
+                    const uint32_t off = tile_off(trow, part * CPT + (uint32_t)ch);
                     *reinterpret_cast<uint4*>(bhi + off) = hi4;
                     *reinterpret_cast<uint4*>(blo + off) = lo4;
                 }
@@ -446,7 +453,7 @@ __global__ void __launch_bounds__(NP + 32, 1) qmm_umma_kernel(const QmmParams p)
                     split_pair(wv[2], wv[3], hi4.y, lo4.y);
                     split_pair(wv[4], wv[5], hi4.z, lo4.z);
                     split_pair(wv[6], wv[7], hi4.w, lo4.w);
-                    const uint32_t off = tile_off(trow, part * CPT + (uint32_t)ch, layout);
+                    const uint32_t off = tile_off(trow, part * CPT + (uint32_t)ch);
                     *reinterpret_cast<uint4*>(bhi + off) = hi4;
                     *reinterpret_cast<uint4*>(blo + off) = lo4;
                 }
@@ -511,9 +518,9 @@ __global__ void __launch_bounds__(NP + 32, 1) qmm_umma_kernel(const QmmParams p)
     } else {
         // ================================ MMA issuer (one lane) ================================
         if (lane == 0) {
+            uint32_t s = 0, parity = 0;
             for (uint32_t kb = 0; kb < nkb; ++kb) {
-                const uint32_t s = kb % STAGES, it = kb / STAGES;
-                mbar_wait(full_bar(s), it & 1u);
+                mbar_wait(full_bar(s), parity);
                 tc_fence_after();
                 const uint32_t a_addr = smem_base + s * STAGE_BYTES;
                 const uint32_t bh_addr = a_addr + A_BYTES, bl_addr = bh_addr + QMM_TILE_BYTES;
@@ -532,6 +539,7 @@ __global__ void __launch_bounds__(NP + 32, 1) qmm_umma_kernel(const QmmParams p)
                     }
                 }
                 umma_commit(empty_bar(s));                  // stage reusable once these MMAs have read it
+                if (++s == (uint32_t)STAGES) { s = 0; parity ^= 1u; }
             }
             umma_commit(accum_bar);                         // accumulators complete
         }
@@ -599,7 +607,7 @@ bool prefill_gemm_applicable(const uzu_matmul_args& a) {
     if (a.b_mode != UZU_QMODE_U4 && a.b_mode != UZU_QMODE_U8) return false;
     if (a.k % 64u != 0) return false;
     const uint32_t gs = a.b_group_size;
-    if (gs != 32 && (gs % 64u) != 0) return false;         // a 32-k half block never straddles a group
+    if (gs < 32 || (gs & (gs - 1)) != 0) return false;      // power-of-two groups >= 32: a thread's span never straddles a group, index = k >> log2(gs)
     if (a.k % gs != 0) return false;
     if ((a.a & 15u) || (a.b & 15u)) return false;
     return true;
@@ -620,6 +628,8 @@ void encode_prefill_gemm(uzu_command_buffer* cmd, const uzu_matmul_args& a) {
     p.groups_per_row = a.k / a.b_group_size;
     p.zp_stride = bits == 4 ? (p.groups_per_row + 1) / 2 : p.groups_per_row;
     p.group_size = a.b_group_size;
+    p.gshift = 0;
+    while ((1u << p.gshift) < a.b_group_size) ++p.gshift;
     p.method = a.b_prologue == UZU_B_SCALE_BIAS_DEQUANT ? UZU_QMETHOD_SCALE_BIAS
                : a.b_prologue == UZU_B_SCALE_ZERO_POINT_DEQUANT ? UZU_QMETHOD_SCALE_ZERO_POINT : UZU_QMETHOD_SCALE_SYMMETRIC;
     p.xor_mask = a.b_signed_codes ? (bits == 4 ? 0x88888888u : 0x80808080u) : 0u;
@@ -631,7 +641,6 @@ void encode_prefill_gemm(uzu_command_buffer* cmd, const uzu_matmul_args& a) {
     // shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start address >> 4 @ [0,14), LBO >> 4 @ [16,30),
     // SBO >> 4 @ [32,46), version = 1 @ [46,48), layout type @ [61,64) (2 = SWIZZLE_128B, 0 = none).
     // SWIZZLE_128B, K-major: atoms of 8 rows x 128 B, SBO = 1024 B between 8-row groups, LBO unused (1); UMMA_K = 16 bf16 = 32 B -> +2.
-    p.layout = 0;
     p.desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     p.desc_lbo = 1;
     p.k_step = 2;
@@ -639,7 +648,6 @@ void encode_prefill_gemm(uzu_command_buffer* cmd, const uzu_matmul_args& a) {
     static const bool packed_ok = [] { const char* e = getenv("UZU_QMM_PACKED"); return !e || atoi(e) != 0; }();   // 0: f32 dequant path for A/B runs
     p.packed_path = (packed_ok && bits == 4 && p.method != UZU_QMETHOD_SCALE_BIAS) ? 1u : 0u;
     if (g_umma.custom) {
-        p.layout = (uint32_t)g_umma.layout;
         p.desc_hi = g_umma.desc_hi; p.desc_lbo = g_umma.desc_lbo; p.k_step = g_umma.k_step;
         if (g_umma.idesc) p.idesc = g_umma.idesc;
     }
