@@ -33,7 +33,6 @@ SOURCES = {
     "elementwise.cu": ["-fmad=false"],
     "sampling.cu": ["-fmad=false"],
     "deltanet.cu": ["-fmad=false"],
-    "fused.cu": [],
     "engine.cu": [],
 }
 

@@ -5,24 +5,26 @@
 // encodable_block/linear/matmul.rs:122-148, m = prefill chunk <= 1024). SURVEY 8, north_star row "prefill batched-GEMM".
 //
 // Shape of the kernel (one CTA = 128 output features x (MT x 128) tokens, K walked in blocks of 64):
-//   * warps 0-3 (128 threads) are the PRODUCERS. Per K block they
-//       - copy the activation tile (bf16, K contiguous = "K-major") into shared memory with 16 B loads/stores, and
-//       - dequantise one weight row each: 64 codes -> f32 `scale*code + corr` (exactly the reference's expression; the product
-//         is exact, so the FMA equals the reference's separate multiply and add) -> split into TWO bf16 planes
-//         hi = bf16(w), lo = bf16(w - hi). For ZeroPoint / Symmetric weights w = scale*(code - zp) has <= 16 significant bits, so
-//         hi + lo == w EXACTLY (8 + 8 bits); for MLX scale/bias the residual is < 2^-17 |w|. Feeding a single rounded bf16 plane
-//         would put a 2^-9 relative error on every weight (about 1e-3 of the output rms, i.e. the whole parity budget).
+//   * warps 0 .. NP/32-1 (NP = 256 threads by default) are the PRODUCERS. Per K block they
+//       - copy the activation tile (bf16, K contiguous = "K-major") with cp.async straight into its UMMA stage, and
+//       - dequantise their share of a weight row (NP/128 threads per row): codes -> `scale*code + corr` (the reference's
+//         expression, bit for bit) -> TWO bf16 planes hi = bf16(w), lo = w - hi. For ZeroPoint / Symmetric weights
+//         w = scale*(code - zp) has <= 16 significant bits, so hi + lo == w EXACTLY (8 + 8 bits); for MLX scale/bias the residual is
+//         < 2^-17 |w|. Feeding a single rounded bf16 plane would put a 2^-9 relative error on every weight (about 1e-3 of the output
+//         rms, i.e. the whole parity budget). 4-bit ZeroPoint / Symmetric runs in packed bf16x2 arithmetic (HADD2 / HMUL2 / HFMA2).
 //     Tiles are written in the UMMA canonical K-major SWIZZLE_128B layout (8-row x 128-byte atoms, 16-byte chunk index XORed
 //     with the row index inside the atom), made visible to the async proxy with fence.proxy.async, and handed to the MMA warp
-//     through an mbarrier ("full", 128 arrivals).
-//   * warp 4, one lane, is the MMA ISSUER: per K block 4 (K=16 steps) x MT x 2 (hi, lo plane) tcgen05.mma.cta_group::1.kind::f16
+//     through an mbarrier ("full", NP arrivals). The packed codes arrive through cooperative, coalesced cp.async "super-blocks"
+//     (128 rows x 128 contiguous bytes) two buffers deep; a named barrier per super-block hands them from loaders to consumers.
+//   * the last warp, one lane, is the MMA ISSUER: per K block 4 (K=16 steps) x MT x 2 (hi, lo plane) tcgen05.mma.cta_group::1.kind::f16
 //     128x128x16 instructions accumulate into MT x 128 TMEM columns; bf16 x bf16 products are exact in the f32 accumulator, so
 //     the result is sum_k x_k*w_k with f32 accumulation, the reference's arithmetic up to summation order. tcgen05.commit
 //     releases the shared-memory stage ("empty" mbarrier) and, after the last block, signals the epilogue.
-//   * warps 0-3 then run the EPILOGUE: tcgen05.ld (32 lanes x 32 columns per instruction; warp w owns TMEM lanes 32w..32w+31 =
-//     token rows), ab_scale / accumulate / bias / soft-cap in the reference's order, bf16 (RNE) or f32 store.
-// The weight tile is dequantised once per 128 x MT tokens; with MT = 2 the tensor pipe (2 planes x 2 sub-tiles) and the
-// dequantising ALU work per K block are about balanced (~1000 vs ~450 issue cycles), so the kernel is tensor-bound by design.
+//   * the producer warps then run the EPILOGUE: tcgen05.ld (32 lanes x 32 columns per instruction; warp w owns TMEM lanes
+//     32*(w mod 4) .. +31 = token rows, w / 4 picks the column blocks), ab_scale / accumulate / bias / soft-cap in the reference's
+//     order, bf16 (RNE) or f32 store.
+// Measured on B200 (profiles/README.md): 452 TFLOP/s useful at m = 2048 on the Llama-3-8B up projection, tensor pipe 43.5 % active;
+// the limiter is the producers' instruction issue, the ceiling 50 % useful because of the two planes (DESIGN.md 4.5 has the history).
 //
 // Bound: tensor pipe (2*m*n*k flop useful, 2x that issued because of the hi/lo planes). Algorithmic HBM bytes per launch are the
 // packed weights once per token tile + activations once per feature tile (both L2 resident for the shapes of SURVEY 8).
