@@ -148,3 +148,15 @@ def test_two_rank_gloo_processes(tmp_path):
     assert out.returncode == 0, out.stderr[-3000:]
     d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert d["shape"] == [1, spec.vocab_size] and d["err"] <= 0.02 * d["scale"] + 1e-3, d
+
+
+def test_nccl_is_resolved_at_run_time():
+    """csrc/tp.cu dlopens NCCL on first use (no link-time dependency): the unique id call works without a GPU."""
+    from uzu_b200 import binding as B
+    try:
+        a, b = B.tp_unique_id(), B.tp_unique_id()
+    except B.UzuError as ex:
+        if "cannot load NCCL" in str(ex):
+            pytest.skip("no libnccl.so.2 on this host")
+        raise
+    assert len(a) == 128 and a != b
