@@ -29,6 +29,7 @@ SOURCES = {
     "prefill_gemm.cu": [],
     "tp.cu": [],
     "attention.cu": ["-fmad=false"],
+    "attention_prefill.cu": [],
     "norm.cu": ["-fmad=false"],
     "elementwise.cu": ["-fmad=false"],
     "sampling.cu": ["-fmad=false"],

@@ -616,6 +616,7 @@ void uzu_attention_prepare_norm_encode(uzu_command_buffer* cmd, const uzu_attent
 void uzu_attention_single_pass_encode(uzu_command_buffer* cmd, const uzu_attention_args* a) {
     if (!uzu::encodable(cmd, "attention_single_pass")) return;
     if (!uzu::attn_common_checks(cmd, a, "attention_single_pass")) return;
+    if (uzu::encode_attention_prefill(cmd, *a)) return;   // opt-in tensor-core path for suffix >= 16 (attention_prefill.cu)
     uzu_context* ctx = cmd->ctx;
     const int g = uzu::pick_group(a->gqa_factor);
     const uint32_t head_groups = a->num_heads / g;

@@ -104,6 +104,9 @@ inline void launch(uzu_command_buffer* cmd, const char* what, void (*kernel)(KAr
 bool prefill_gemm_applicable(const uzu_matmul_args& a);
 void encode_prefill_gemm(uzu_command_buffer* cmd, const uzu_matmul_args& a);
 
+// tensor-core prefill attention (attention_prefill.cu, opt-in), tried first by uzu_attention_single_pass_encode
+bool encode_attention_prefill(uzu_command_buffer* cmd, const uzu_attention_args& a);
+
 inline bool encodable(uzu_command_buffer* cmd, const char* what) {
     if (!cmd) return false;
     if (cmd->state != uzu_command_buffer::Encoding) {
