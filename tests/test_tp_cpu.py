@@ -160,3 +160,32 @@ def test_nccl_is_resolved_at_run_time():
             pytest.skip("no libnccl.so.2 on this host")
         raise
     assert len(a) == 128 and a != b
+
+
+@pytest.mark.parametrize("preset,kw,sizes", [("llama3-8b", dict(bits=4), (2, 4, 8)), ("llama3-8b", dict(bits=8), (2, 4, 8)),
+                                              ("llama3-70b", dict(bits=4), (2, 4, 8))])
+def test_baseline_models_are_shardable_shape_only(preset, kw, sizes):
+    """Llama-3-8B / 70B (BASELINE configs 3-5) at TP 2 / 4 / 8: whole heads, whole groups, whole zero-point bytes on every rank --
+    checked from config + quantisation specs alone (no 35 GB of weights needed)."""
+    spec = synth.PRESETS[preset](layers=2, **kw)
+    cfg = synth.build_config(spec)
+    q = spec.quant.spec_json("output_input")
+    meta = {}
+    for i in range(spec.num_layers):
+        for name in ("mixer.qkv_projection", "mixer.out_projection", "mlp.up_projection", "mlp.down_projection"):
+            meta[f"decoder.transformer.layers.{i}.{name}.weights.spec"] = json.dumps(q)
+    for size in sizes:
+        assert tp.check_shardable(cfg, meta, size) == [], (preset, size)
+    assert tp.check_shardable(cfg, meta, 16)            # 8 kv heads cannot feed 16 ranks
+    hybrid = synth.build_config(synth.qwen35_0p8b(layers=3))      # 3 DeltaNet layers
+    assert any("DeltaNetConfig" in p for p in tp.check_shardable(hybrid, {}, 2))
+
+
+def test_bench_shard_dir_is_written_once(tmp_path, monkeypatch):
+    import bench
+    full = synth.write_model(synth.tiny("llama"), tmp_path / "tiny-llama-seed0", seed=0)
+    d0 = bench.shard_dir_for(full, 0, 2)
+    assert (d0 / ".done").exists() and json.loads((d0 / "config.json").read_text())["tensor_parallel"]["rank"] == 0
+    stamp = (d0 / "model.safetensors").stat().st_mtime_ns
+    assert bench.shard_dir_for(full, 0, 2) == d0 and (d0 / "model.safetensors").stat().st_mtime_ns == stamp
+    assert bench.shard_dir_for(full, 1, 2).name.endswith("tp2-rank1")

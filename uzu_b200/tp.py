@@ -153,6 +153,47 @@ def shard_tensors(config: dict, tensors: dict, dtypes: dict, meta: dict, rank: i
     return cfg, T, M
 
 
+def check_shardable(config: dict, meta: dict, size: int) -> list:
+    """Shape-only version of the checks shard_tensors() makes (no tensor data needed: usable on a 70B config before 35 GB of
+    weights exist). Returns the list of problems; empty = every rank of `size` gets whole heads, whole quantisation groups and
+    whole zero-point bytes."""
+    problems = []
+    dec = config["decoder_config"]
+    tr = dec["transformer_config"]
+    F, V = tr["hidden_dim"], dec["vocab_size"]
+    if V % size:
+        problems.append(f"vocab_size {V} is not divisible by {size}")
+
+    def k_shard(prefix, k_total):
+        spec = json.loads(meta[prefix + ".spec"])
+        if spec["type"] == "FullPrecisionSpec":
+            return
+        gs, bits = spec["group_size"], spec["bits"]
+        per = k_total // size
+        if per % gs:
+            problems.append(f"{prefix}: K shard of {per} is not a whole number of groups of {gs}")
+        elif bits == 4 and spec["type"] == "IntSpec" and not spec.get("is_symmetric", False) and (per // gs) % 2:
+            problems.append(f"{prefix}: {per // gs} groups per shard = half a 4-bit zero-point byte")
+
+    for i, lc in enumerate(tr["layer_configs"]):
+        p = f"decoder.transformer.layers.{i}"
+        mc = lc["mixer_config"]
+        if mc["type"] != "AttentionConfig":
+            problems.append(f"layer {i}: {mc['type']} is not sharded")
+            continue
+        Hq, Hkv, D = mc["num_heads"], mc["num_groups"], mc["head_dim"]
+        if Hq % size or Hkv % size:
+            problems.append(f"layer {i}: {Hq} query / {Hkv} kv heads are not divisible by {size}")
+        else:
+            k_shard(f"{p}.mixer.out_projection.weights", Hq * D)
+        Fi = lc["hidden_dim"] if lc.get("hidden_dim") is not None else F
+        if Fi % size:
+            problems.append(f"layer {i}: hidden_dim {Fi} is not divisible by {size}")
+        else:
+            k_shard(f"{p}.mlp.down_projection.weights", Fi)
+    return problems
+
+
 def shard_checkpoint(model_dir, out_dir, rank: int, size: int) -> Path:
     model_dir, out_dir = Path(model_dir), Path(out_dir)
     config = json.loads((model_dir / "config.json").read_text())
