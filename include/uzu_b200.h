@@ -306,7 +306,8 @@ UZU_API void uzu_attention_single_pass_encode(uzu_command_buffer* cmd, const uzu
 UZU_API void uzu_attention_two_pass1_encode(uzu_command_buffer* cmd, const uzu_attention_args* args);
 /* Opt-in tensor-core prefill attention (csrc/attention_prefill.cu; suffix >= 16, plain causal / non-causal, head_dim 64 | 128): taken by
  * uzu_attention_single_pass_encode when UZU_PREFILL_ATTN=1 or after uzu_debug_set_prefill_attention(1); -1 = follow the environment.
- * NOT validated on hardware in round 1 -- the default stays the split-KV kernel. */
+ * Round 1: probed on hardware against a float64 softmax (profiles/r1_prefill_attention_probe.txt), oracle tests pending -- the default stays
+ * the split-KV kernel. */
 UZU_API void uzu_debug_set_prefill_attention(int mode);
 /* AttentionTwoPass2Kernel: attention_two_pass.rs:139-149 */
 typedef struct uzu_attention_two_pass2_args {

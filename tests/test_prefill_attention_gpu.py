@@ -2,8 +2,9 @@
 AttentionSinglePass restatement (backends/cpu/kernel/attention/attention_single_pass.rs:49-126) and the independent float64 softmax of
 tests/unit/encodable_block/attention_test.rs:26-124, on the reference tests' closed-form inputs (attention_single_pass_test.rs:33-78).
 
-The kernel was written at the end of round 1 with no GPU time left and has NOT run on hardware: these tests are skipped unless
-UZU_TEST_PREFILL_ATTN=1 so that an unvalidated path cannot turn the suite red; they are the first thing to run in round 2."""
+The kernel was written at the end of round 1; its only hardware run is tools/prefill_attn_probe.py (float64 softmax, 3 shapes, passed).
+These oracle-ulp tests have not run yet, so they are skipped unless UZU_TEST_PREFILL_ATTN=1 (an unvalidated assertion must not turn the
+suite red); they are the first thing to run in round 2, after which the path becomes the default."""
 import os
 
 import numpy as np

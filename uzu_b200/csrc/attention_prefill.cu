@@ -1,8 +1,9 @@
 // Prefill attention on tensor cores (suffix >= 16 query tokens): flash-attention-style tiling over the token-major KV cache.
 //
-//   OPT-IN (UZU_PREFILL_ATTN=1) -- written at the end of round 1 without GPU time left: it has NOT run on hardware yet, so the default
-//   prefill path stays the split-KV decode kernel applied per query token (attention.cu, parity-tested). tests/test_prefill_attention_gpu.py
-//   is the parity test to run first (it enables the flag itself).
+//   OPT-IN (UZU_PREFILL_ATTN=1). Written after round 1's GPU budget was spent; its only hardware run so far is tools/prefill_attn_probe.py
+//   (3 shapes within one bf16 step of a float64 softmax, profiles/r1_prefill_attention_probe.txt). Until tests/test_prefill_attention_gpu.py
+//   (oracle ulp comparison, enabled with UZU_TEST_PREFILL_ATTN=1) and the engine tests have run through it, the default prefill path stays
+//   the split-KV decode kernel applied per query token (attention.cu).
 //
 // Semantic spec: backends/cpu/kernel/attention/attention_single_pass.rs:49-126 (online softmax per query over the visible keys, q scaled by
 // `scale`, GQA kv_head = h / gqa, output [suffix, heads, D] cast after the division by the sum), mask.rs:3-62 restricted to the plain causal /
