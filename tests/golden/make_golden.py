@@ -33,7 +33,9 @@ def main():
     cases = {}
     for name, (seed, m, n, k, bits, gs, method) in {
         "int4_gs64_zp": (1, 1, 96, 1024, 4, 64, O.QM_ZERO_POINT), "int8_gs64_zp": (2, 3, 64, 512, 8, 64, O.QM_ZERO_POINT),
-        "mlx4_gs32": (3, 2, 80, 512, 4, 32, O.QM_SCALE_BIAS), "sym4_gs128": (4, 1, 48, 1024, 4, 128, O.QM_SYMMETRIC)}.items():
+        "mlx4_gs32": (3, 2, 80, 512, 4, 32, O.QM_SCALE_BIAS), "sym4_gs128": (4, 1, 48, 1024, 4, 128, O.QM_SYMMETRIC),
+        # prefill row counts (m >= 64: the tcgen05 GEMM with the in-kernel dequant stage on the GPU side)
+        "prefill_int4_gs64_zp": (5, 96, 136, 320, 4, 64, O.QM_ZERO_POINT), "prefill_int8_gs32_mlx": (6, 70, 96, 256, 8, 32, O.QM_SCALE_BIAS)}.items():
         x, w, sc, zp, bi = quant_case(seed, m, n, k, bits, gs, method)
         d = O.matmul(x, w, m=m, n=n, k=k, scales=sc, zero_points=zp, biases=bi, method=method, bits=bits, group_size=gs, d_f32=True)
         cases[f"matmul_{name}_seed"] = np.array([seed, m, n, k, bits, gs, method])
