@@ -263,6 +263,14 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.broadcast(idt, 0)
         ctx.tp_init(rank, world, bytes(idt.cpu().tolist()))
         mdir = shard_dir_for(mdir, rank, world)
+        if os.environ.get("UZU_TP_P2P"):
+            # opt-in: decode-sized all-reduces through the one-kernel peer-memory exchange (CUDA IPC handles travel over torch.distributed)
+            model_dim = json.loads((mdir / "config.json").read_text())["decoder_config"]["transformer_config"]["model_dim"]
+            mine = torch.tensor(list(ctx.tp_p2p_export(16 * model_dim)), dtype=torch.uint8, device="cuda")
+            allh = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            ctx.tp_p2p_import([bytes(h.cpu().tolist()) for h in allh])
+            dist.barrier()
     eng = B.Engine(ctx, mdir, max_context_length=max_ctx, use_cuda_graph=not args.no_graph, fused_decode=not args.no_fused,
                    tp_rank=rank if tp > 1 else 0, tp_size=tp)
     replicas = 1 if tp > 1 else world

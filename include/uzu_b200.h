@@ -216,6 +216,12 @@ UZU_API uzu_status uzu_context_tp_init(uzu_context* ctx, uint32_t rank, uint32_t
 UZU_API void uzu_context_tp_destroy(uzu_context* ctx);
 UZU_API uint32_t uzu_context_tp_size(const uzu_context* ctx);
 UZU_API uint32_t uzu_context_tp_rank(const uzu_context* ctx);
+/* Optional peer-memory exchange for small (decode) messages -- one kernel pushes the partials to every peer over NVLink, waits, reduces in
+ * rank order and rounds (csrc/tp.cu: tp_p2p_all_reduce_kernel). Every rank: export (allocates the exchange buffer, returns a 64-byte CUDA IPC
+ * handle), all-gather the handles with the host program, import (handles of all ranks, rank order), then a host-side barrier. After that
+ * uzu_tp_all_reduce_encode uses the peer path for count <= capacity_f32 and NCCL otherwise. NOT yet run on hardware (round 1). */
+UZU_API uzu_status uzu_tp_p2p_export(uzu_context* ctx, uint32_t capacity_f32, uint8_t* handle_out64);
+UZU_API uzu_status uzu_tp_p2p_import(uzu_context* ctx, const uint8_t* handles_size_x_64);
 /* Row-parallel projection epilogue: sum the f32 partials [count] over the ranks in place (ncclAllReduce on the context stream),
  * then round to bf16 once into out_bf16. With a 1-rank context only the rounding runs. */
 UZU_API void uzu_tp_all_reduce_encode(uzu_command_buffer* cmd, uint64_t partial_f32, uint32_t count, uint64_t out_bf16);

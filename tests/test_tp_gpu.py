@@ -69,7 +69,8 @@ def _gpu_count():
 
 @pytest.mark.skipif(_gpu_count() < 2 or not os.environ.get("UZU_TEST_TP_NCCL"),
                     reason="needs two GPUs and UZU_TEST_TP_NCCL=1 (gpurun --gpus 2): the NCCL path has not run on hardware yet (DESIGN.md 5)")
-def test_two_rank_nccl_engine_matches_unsharded_oracle(tmp_path):
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
+def test_two_rank_nccl_engine_matches_unsharded_oracle(tmp_path, exchange):
     spec = synth.tiny("llama-512")
     full = synth.write_model(spec, tmp_path / "full", seed=22)
     for r in range(2):
@@ -89,6 +90,12 @@ def test_two_rank_nccl_engine_matches_unsharded_oracle(tmp_path):
         dist.broadcast(idt, 0)
         ctx = B.Context(lr)
         ctx.tp_init(rank, world, bytes(idt.cpu().tolist()))
+        if os.environ.get("UZU_TP_P2P"):          # second run of this test: decode all-reduces over peer memory instead of NCCL
+            mine = torch.tensor(list(ctx.tp_p2p_export(16 * {spec.model_dim})), dtype=torch.uint8, device="cuda")
+            allh = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            ctx.tp_p2p_import([bytes(h.cpu().tolist()) for h in allh])
+            dist.barrier()
         out = {{}}
         for graph in (False, True):
             with B.Engine(ctx, {str(tmp_path)!r} + f"/rank{{rank}}", max_context_length=256, use_cuda_graph=graph, tp_rank=rank, tp_size=world) as eng:
@@ -113,6 +120,9 @@ def test_two_rank_nccl_engine_matches_unsharded_oracle(tmp_path):
         dist.barrier(); dist.destroy_process_group()
     """))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29621")
+    env.pop("UZU_TP_P2P", None)
+    if exchange == "p2p":
+        env["UZU_TP_P2P"] = "1"
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                           "--master-port", "29621", str(script)], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-4000:])

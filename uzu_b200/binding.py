@@ -148,7 +148,7 @@ uzu_delta_net_update_encode uzu_engine_create uzu_engine_destroy uzu_engine_info
 uzu_engine_snapshot uzu_engine_restore uzu_engine_prefill uzu_engine_next uzu_engine_flush uzu_engine_decode_device
 uzu_engine_forward uzu_engine_launch_count uzu_engine_decode_timed uzu_engine_step_host
 uzu_delta_net_fused_update_supported uzu_delta_net_fused_update_encode uzu_engine_time_linears uzu_engine_time_prefill_linears uzu_engine_time_linears_select uzu_debug_set_qmv_tuning uzu_debug_set_prefill_attention uzu_debug_set_umma uzu_tp_get_unique_id uzu_context_tp_init uzu_context_tp_destroy uzu_context_tp_size
-uzu_context_tp_rank uzu_tp_all_reduce_encode uzu_tp_all_gather_encode uzu_fused_linear_supported uzu_fused_linear_encode""".split()
+uzu_context_tp_rank uzu_tp_p2p_export uzu_tp_p2p_import uzu_tp_all_reduce_encode uzu_tp_all_gather_encode uzu_fused_linear_supported uzu_fused_linear_encode""".split()
 
 _lib = None
 
@@ -257,6 +257,8 @@ def load() -> C.CDLL:
         "uzu_context_tp_destroy": (None, [vp]),
         "uzu_context_tp_size": (u32, [vp]),
         "uzu_context_tp_rank": (u32, [vp]),
+        "uzu_tp_p2p_export": (C.c_int, [vp, u32, C.POINTER(C.c_uint8)]),
+        "uzu_tp_p2p_import": (C.c_int, [vp, C.POINTER(C.c_uint8)]),
         "uzu_tp_all_reduce_encode": (None, [vp, u64, u32, u64]),
         "uzu_tp_all_gather_encode": (None, [vp, C.POINTER(TpAllGatherArgs)]),
         "uzu_fused_linear_supported": (C.c_int, [vp, C.POINTER(FusedLinearArgs)]),
@@ -306,6 +308,18 @@ class Context:
 
     def synchronize(self):
         _check(self.lib.uzu_context_synchronize(self.h))
+
+    def tp_p2p_export(self, capacity_f32: int) -> bytes:
+        """Allocate this rank's peer-memory exchange buffer; returns its 64-byte CUDA IPC handle (all-gather it, then tp_p2p_import)."""
+        buf = (C.c_uint8 * 64)()
+        _check(self.lib.uzu_tp_p2p_export(self.h, capacity_f32, buf))
+        return bytes(buf)
+
+    def tp_p2p_import(self, handles: list):
+        """`handles` = the 64-byte handles of all ranks in rank order. Barrier all ranks afterwards, before the first exchange."""
+        blob = b"".join(bytes(h) for h in handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        _check(self.lib.uzu_tp_p2p_import(self.h, buf))
 
     def tp_init(self, rank: int, size: int, unique_id: bytes):
         """Join the tensor-parallel group: `unique_id` = tp_unique_id() of rank 0, distributed by the host program."""

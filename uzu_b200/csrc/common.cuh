@@ -48,6 +48,7 @@ struct uzu_context {
     // tensor parallelism (tp.cu): NCCL communicator of this process's rank, created by uzu_context_tp_init
     void* nccl_comm = nullptr;
     uint32_t tp_rank = 0, tp_size = 1;
+    void* tp_p2p = nullptr;   // peer-memory exchange state (tp.cu, opt-in)
 };
 
 struct uzu_command_buffer {

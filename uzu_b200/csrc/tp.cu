@@ -97,6 +97,108 @@ __global__ void __launch_bounds__(256) tp_interleave_rows_kernel(const uint16_t*
     }
 }
 
+
+// ---- one-shot all-reduce over peer memory (NVLink / NVSwitch P2P), for the 8-32 KB decode messages ----------------------------------
+// NOT yet run on hardware (round 1 had no multi-GPU time): enabled only after uzu_tp_p2p_export / uzu_tp_p2p_import succeeded, and
+// the 2-rank test that covers it is opt-in. NCCL stays the default exchange and the fallback for large (prefill) messages.
+//
+// Every rank owns an exchange buffer (cudaMalloc, opened by the peers through CUDA IPC):
+//     data [2 slot sets][P ranks][capacity] f32      partials the peers push into this rank
+//     flags[2 slot sets][P ranks][CTAS]     u32      "chunk c of rank r, call number e, has landed"
+//     epoch[CTAS]                           u32      this rank's call counter per CTA (device resident: the call is captured in a CUDA
+//                                                    graph, so nothing that changes per call may be a kernel argument)
+// CTA c of every rank owns the same slice of the vector. Per call e = epoch[c] + 1, slot set = e & 1:
+//   1. push my slice of my partial into data[set][me][slice] of every peer (16-byte P2P stores), __threadfence_system, then publish
+//      flags[set][me][c] = e on every peer (release, system scope);
+//   2. spin (acquire, system scope) until flags[set][r][c] == e for every peer r in my own buffer;
+//   3. out[i] = bf16( sum over ranks IN RANK ORDER of the f32 partials ) -- the same value on every rank, rounded once;
+//   4. epoch[c] = e.
+// Two slot sets are enough: a peer publishes call e only after it finished its own call e - 1, so when some rank overwrites set
+// (e + 1) & 1 nobody can still be reading call e - 1 from it. No CTA waits for another CTA of its own rank: no grid barrier.
+constexpr int TP_P2P_CTAS = 8;
+constexpr int TP_P2P_MAX_RANKS = 8;
+
+struct TpP2pView {
+    float* data[TP_P2P_MAX_RANKS];            // data region of rank r's exchange buffer (peer-mapped; [me] = local)
+    unsigned int* flags[TP_P2P_MAX_RANKS];    // flags region of rank r's exchange buffer
+    unsigned int* epoch;                      // local
+    uint32_t rank, size, capacity;            // capacity = f32 elements per (slot set, rank)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) tp_p2p_all_reduce_kernel(const TpP2pView v, const float* __restrict__ partial, __nv_bfloat16* __restrict__ out,
+                                                                uint32_t count) {
+    pdl_wait();
+    const uint32_t c = blockIdx.x, me = v.rank, P = v.size;
+    __shared__ unsigned int s_e;
+    if (threadIdx.x == 0) s_e = v.epoch[c] + 1u;
+    __syncthreads();
+    const unsigned int e = s_e;
+    const uint32_t set = e & 1u;
+    // slice of this CTA in units of float4 (count is a multiple of 4: model_dim rows)
+    const uint32_t vec = count / 4u, per = (vec + TP_P2P_CTAS - 1) / TP_P2P_CTAS;
+    const uint32_t v0 = min(vec, c * per), v1 = min(vec, v0 + per);
+    const size_t slot_me = ((size_t)set * P + me) * v.capacity;
+    // 1. push
+    for (uint32_t r = 0; r < P; ++r) {
+        if (r == me) continue;
+        float4* dst = reinterpret_cast<float4*>(v.data[r] + slot_me);
+        for (uint32_t i = v0 + threadIdx.x; i < v1; i += blockDim.x) dst[i] = reinterpret_cast<const float4*>(partial)[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < P && threadIdx.x != me) st_release_sys(v.flags[threadIdx.x] + ((size_t)set * P + me) * TP_P2P_CTAS + c, e);
+    // 2. wait for the peers' pushes into MY buffer
+    if (threadIdx.x < P && threadIdx.x != me) {
+        const unsigned int* f = v.flags[me] + ((size_t)set * P + threadIdx.x) * TP_P2P_CTAS + c;
+        unsigned long long t0 = 0;
+        unsigned int spins = 0;
+        while ((int)(ld_acquire_sys(f) - e) < 0) {
+            if ((++spins & 4095u) == 0) {     // a peer that never arrives (crashed rank) must not hang this GPU forever
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t0 == 0) t0 = t1;
+                else if (t1 - t0 > 20000000000ull) __trap();
+            }
+        }
+    }
+    __syncthreads();
+    // 3. reduce in rank order (peer slots are read with L1 bypass: the same addresses are reused every second call)
+    for (uint32_t i = v0 + threadIdx.x; i < v1; i += blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t r = 0; r < P; ++r) {
+            const float4 x = r == me ? reinterpret_cast<const float4*>(partial)[i]
+                                     : __ldcg(reinterpret_cast<const float4*>(v.data[me] + ((size_t)set * P + r) * v.capacity) + i);
+            acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+        }
+        __nv_bfloat162 a = __floats2bfloat162_rn(acc.x, acc.y), b = __floats2bfloat162_rn(acc.z, acc.w);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&a);
+        o.y = *reinterpret_cast<uint32_t*>(&b);
+        reinterpret_cast<uint2*>(out)[i] = o;
+    }
+    // 4.
+    if (threadIdx.x == 0) v.epoch[c] = e;
+}
+
+struct TpP2pState {
+    void* local = nullptr;                      // this rank's exchange buffer
+    void* peer[TP_P2P_MAX_RANKS] = {};          // opened peer buffers ([me] = local)
+    uint32_t capacity = 0;                      // f32 elements per (slot set, rank)
+    bool ready = false;
+};
+static size_t tp_p2p_bytes(uint32_t size, uint32_t capacity) {
+    return (size_t)2 * size * capacity * 4 + (size_t)2 * size * TP_P2P_CTAS * 4 + TP_P2P_CTAS * 4;
+}
+
 }  // namespace uzu
 
 using namespace uzu;
@@ -132,12 +234,57 @@ uzu_status uzu_context_tp_init(uzu_context* ctx, uint32_t rank, uint32_t size, c
 }
 
 void uzu_context_tp_destroy(uzu_context* ctx) {
+    if (ctx && ctx->tp_p2p) {
+        TpP2pState* st = static_cast<TpP2pState*>(ctx->tp_p2p);
+        for (uint32_t r = 0; r < ctx->tp_size && r < (uint32_t)TP_P2P_MAX_RANKS; ++r)
+            if (st->peer[r] && st->peer[r] != st->local) cudaIpcCloseMemHandle(st->peer[r]);
+        cudaFree(st->local);
+        delete st;
+        ctx->tp_p2p = nullptr;
+    }
     if (!ctx || !ctx->nccl_comm) return;
     NcclApi& n = nccl();
     if (n.CommDestroy) n.CommDestroy(ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
     ctx->tp_rank = 0;
     ctx->tp_size = 1;
+}
+
+
+uzu_status uzu_tp_p2p_export(uzu_context* ctx, uint32_t capacity_f32, uint8_t* handle_out64) {
+    if (!ctx || !handle_out64 || capacity_f32 == 0 || (capacity_f32 & 3u)) return fail(UZU_ERROR_INVALID_ARGUMENT, "tp_p2p_export: bad arguments");
+    if (ctx->tp_size < 2 || ctx->tp_size > (uint32_t)TP_P2P_MAX_RANKS) return fail(UZU_ERROR_INVALID_ARGUMENT, "tp_p2p_export: needs a 2..8 rank context");
+    if (ctx->tp_p2p) return fail(UZU_ERROR_INVALID_ARGUMENT, "tp_p2p_export: already exported");
+    UZU_CUDA_TRY(cudaSetDevice(ctx->device));
+    TpP2pState* st = new TpP2pState();
+    const size_t bytes = tp_p2p_bytes(ctx->tp_size, capacity_f32);
+    cudaError_t e = cudaMalloc(&st->local, bytes);
+    if (e != cudaSuccess) { delete st; return fail(UZU_ERROR_OUT_OF_MEMORY, std::string("tp_p2p_export: ") + cudaGetErrorString(e)); }
+    cudaMemset(st->local, 0, bytes);
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, st->local);
+    if (e != cudaSuccess) { cudaFree(st->local); delete st; return fail(UZU_ERROR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    memcpy(handle_out64, &h, 64);
+    st->capacity = capacity_f32;
+    ctx->tp_p2p = st;
+    return UZU_OK;
+}
+
+uzu_status uzu_tp_p2p_import(uzu_context* ctx, const uint8_t* handles_size_x_64) {
+    if (!ctx || !handles_size_x_64 || !ctx->tp_p2p) return fail(UZU_ERROR_INVALID_ARGUMENT, "tp_p2p_import: export first");
+    TpP2pState* st = static_cast<TpP2pState*>(ctx->tp_p2p);
+    UZU_CUDA_TRY(cudaSetDevice(ctx->device));
+    for (uint32_t r = 0; r < ctx->tp_size; ++r) {
+        if (r == ctx->tp_rank) { st->peer[r] = st->local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles_size_x_64 + (size_t)r * 64, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(&st->peer[r], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(UZU_ERROR_CUDA, "cudaIpcOpenMemHandle(rank " + std::to_string(r) + "): " + cudaGetErrorString(e));
+    }
+    UZU_CUDA_TRY(cudaDeviceSynchronize());
+    st->ready = true;       // the host program must barrier all ranks after this call and before the first exchange
+    return UZU_OK;
 }
 
 uint32_t uzu_context_tp_size(const uzu_context* ctx) { return ctx ? ctx->tp_size : 0; }
@@ -148,6 +295,22 @@ void uzu_tp_all_reduce_encode(uzu_command_buffer* cmd, uint64_t partial_f32, uin
     uzu_context* ctx = cmd->ctx;
     if (!partial_f32 || !out_bf16 || count == 0) {
         cmd->record_error(UZU_ERROR_INVALID_ARGUMENT, "tp_all_reduce: null operand / empty");
+        return;
+    }
+    if (ctx->tp_size > 1 && ctx->tp_p2p && static_cast<TpP2pState*>(ctx->tp_p2p)->ready && (count & 3u) == 0 &&
+        count <= static_cast<TpP2pState*>(ctx->tp_p2p)->capacity && !((partial_f32 | out_bf16) & 15u)) {
+        // one kernel: push to the peers over NVLink, wait, reduce in rank order, round (see tp_p2p_all_reduce_kernel)
+        TpP2pState* st = static_cast<TpP2pState*>(ctx->tp_p2p);
+        TpP2pView v{};
+        const size_t data_bytes = (size_t)2 * ctx->tp_size * st->capacity * 4, flag_bytes = (size_t)2 * ctx->tp_size * TP_P2P_CTAS * 4;
+        for (uint32_t r = 0; r < ctx->tp_size; ++r) {
+            v.data[r] = reinterpret_cast<float*>(st->peer[r]);
+            v.flags[r] = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(st->peer[r]) + data_bytes);
+        }
+        v.epoch = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(st->local) + data_bytes + flag_bytes);
+        v.rank = ctx->tp_rank; v.size = ctx->tp_size; v.capacity = st->capacity;
+        launch(cmd, "tp_p2p_all_reduce_kernel", tp_p2p_all_reduce_kernel, dim3(TP_P2P_CTAS), dim3(256), 0, v, (const float*)partial_f32,
+               (__nv_bfloat16*)out_bf16, count);
         return;
     }
     if (ctx->tp_size > 1) {
