@@ -54,3 +54,28 @@ def test_sass_uses_tensor_pipe_and_vector_loads(lib):
     sass = subprocess.run(["cuobjdump", "-sass", str(binding.LIB_PATH)], capture_output=True, text=True).stdout
     assert "HMMA.16816.F32.BF16" in sass
     assert "LDG.E.128" in sass
+
+
+def test_sass_of_the_prefill_gemm_uses_tcgen05(lib):
+    """The prefill GEMM runs on the 5th-generation tensor cores: tcgen05.mma (UTCHMMA), TMEM loads (LDTM), tcgen05.commit (UTCBAR),
+    TMEM allocation (UTCATOMSWS) and cp.async staging (LDGSTS) must be in the sm_100a SASS (B200_PROFILING.md mnemonics)."""
+    import shutil, subprocess
+    from uzu_b200 import binding
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3uzu15qmm_umma_kernelILi4ELi2ELi3ELi256ELb1EEEvNS_9QmmParamsE", str(binding.LIB_PATH)],
+                          capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "UTCBAR", "UTCATOMSWS", "LDGSTS", "HFMA2.BF16"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/uzu_b200.h is the drop-in boundary: it must compile as C11 for cgo / bindgen / ctypes-style consumers."""
+    import shutil, subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    src = tmp_path / "h.c"
+    src.write_text('#include "uzu_b200.h"\nint main(void) { return sizeof(uzu_matmul_args) + sizeof(uzu_tp_all_gather_args) > 0 ? 0 : 1; }\n')
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", str(ROOT / "include"), "-c", str(src), "-o", str(tmp_path / "h.o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
