@@ -413,6 +413,10 @@ typedef struct uzu_delta_net_fused_update_args {
 } uzu_delta_net_fused_update_args;
 UZU_API int uzu_delta_net_fused_update_supported(const uzu_delta_net_fused_update_args* args);
 UZU_API void uzu_delta_net_fused_update_encode(uzu_command_buffer* cmd, const uzu_delta_net_fused_update_args* args);
+/* Opt-in (UZU_DELTA_PREFILL_KERNEL=1 or uzu_debug_set_delta_prefill(1); -1 = follow the environment): the engine's batched hybrid prefill runs
+ * the m-token DeltaNet recurrence of a layer in ONE launch (csrc/deltanet_prefill.cu: one CTA per v-head, state resident in shared memory)
+ * instead of one decode-kernel launch per token. NOT yet run on hardware (round 1). */
+UZU_API void uzu_debug_set_delta_prefill(int mode);
 
 /* ---- Host engine (C++ mirror of the reference's backend-agnostic Rust host code) ---------- *
  * No Rust toolchain exists in the build image, so the layer above the kernels -- Engine /

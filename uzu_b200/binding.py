@@ -147,7 +147,7 @@ uzu_tensor_add_bias_encode uzu_tensor_add_swap_encode uzu_unified_sampling_encod
 uzu_delta_net_update_encode uzu_engine_create uzu_engine_destroy uzu_engine_info uzu_engine_reset uzu_engine_context_length
 uzu_engine_snapshot uzu_engine_restore uzu_engine_prefill uzu_engine_next uzu_engine_flush uzu_engine_decode_device
 uzu_engine_forward uzu_engine_launch_count uzu_engine_decode_timed uzu_engine_step_host
-uzu_delta_net_fused_update_supported uzu_delta_net_fused_update_encode uzu_engine_time_linears uzu_engine_time_prefill_linears uzu_engine_time_linears_select uzu_debug_set_qmv_tuning uzu_debug_set_prefill_attention uzu_debug_set_umma uzu_tp_get_unique_id uzu_context_tp_init uzu_context_tp_destroy uzu_context_tp_size
+uzu_delta_net_fused_update_supported uzu_delta_net_fused_update_encode uzu_engine_time_linears uzu_engine_time_prefill_linears uzu_engine_time_linears_select uzu_debug_set_qmv_tuning uzu_debug_set_delta_prefill uzu_debug_set_prefill_attention uzu_debug_set_umma uzu_tp_get_unique_id uzu_context_tp_init uzu_context_tp_destroy uzu_context_tp_size
 uzu_context_tp_rank uzu_tp_p2p_export uzu_tp_p2p_import uzu_tp_all_reduce_encode uzu_tp_all_gather_encode uzu_fused_linear_supported uzu_fused_linear_encode""".split()
 
 _lib = None
@@ -251,6 +251,7 @@ def load() -> C.CDLL:
         "uzu_engine_time_linears_select": (C.c_int, [vp, u32, u32, C.POINTER(C.c_double), C.POINTER(u64)]),
         "uzu_debug_set_qmv_tuning": (None, [C.c_int, C.c_int, C.c_int, C.c_int]),
         "uzu_debug_set_prefill_attention": (None, [C.c_int]),
+        "uzu_debug_set_delta_prefill": (None, [C.c_int]),
         "uzu_debug_set_umma": (None, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
         "uzu_tp_get_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
         "uzu_context_tp_init": (C.c_int, [vp, u32, u32, C.POINTER(C.c_uint8)]),

@@ -34,6 +34,7 @@ SOURCES = {
     "elementwise.cu": ["-fmad=false"],
     "sampling.cu": ["-fmad=false"],
     "deltanet.cu": ["-fmad=false"],
+    "deltanet_prefill.cu": ["-fmad=false"],
     "engine.cu": [],
 }
 

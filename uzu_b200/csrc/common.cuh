@@ -108,6 +108,9 @@ void encode_prefill_gemm(uzu_command_buffer* cmd, const uzu_matmul_args& a);
 // tensor-core prefill attention (attention_prefill.cu, opt-in), tried first by uzu_attention_single_pass_encode
 bool encode_attention_prefill(uzu_command_buffer* cmd, const uzu_attention_args& a);
 
+// multi-token DeltaNet recurrence in one launch (deltanet_prefill.cu, opt-in), tried by the engine's batched hybrid prefill
+bool encode_delta_net_prefill(uzu_command_buffer* cmd, const uzu_delta_net_fused_update_args& f, uint32_t rows, uint32_t in_stride, uint32_t out_stride);
+
 inline bool encodable(uzu_command_buffer* cmd, const char* what) {
     if (!cmd) return false;
     if (cmd->state != uzu_command_buffer::Encoding) {

@@ -978,7 +978,18 @@ static uint64_t encode_delta_net(uzu_engine* e, uzu_command_buffer* cmd, const L
     // token order, so a batched prefill computes exactly what m single-token passes compute. (The reference's chunked-prefill core,
     // Kernels::DeltaNetChunkedPrefill, evaluates the same recurrence in a different summation order; not restated here.)
     encode_linear(cmd, D.in_proj, hidden, m, e->in_proj.ptr());
-    for (uint32_t t = 0; t < m; ++t) {
+    bool whole_pass = false;
+    if (m > 1) {   // opt-in: the m-token recurrence of this layer in ONE launch (deltanet_prefill.cu), state kept on chip across tokens
+        uzu_delta_net_fused_update_args f0{};
+        f0.conv.conv_weight = D.conv_weight.ptr(); f0.conv.bias = D.conv_bias.ptr(); f0.conv.in_out = e->in_proj.ptr(); f0.conv.state = S.conv_state.ptr();
+        f0.conv.kernel_size = D.kernel_size; f0.conv.conv_dim = D.conv_dim; f0.conv.state_stride = D.kernel_size - 1; f0.conv.has_bias = D.conv_has_bias;
+        f0.update.in_proj = e->in_proj.ptr(); f0.update.a_log = D.a_log.ptr(); f0.update.dt_bias = D.dt_bias.ptr(); f0.update.norm_weight = D.norm_weight.ptr();
+        f0.update.state = S.ssm_state.ptr(); f0.update.out = e->delta_out.ptr();
+        f0.update.num_v_heads = D.num_heads; f0.update.num_k_heads = D.num_groups; f0.update.head_v_dim = D.value_head_dim; f0.update.key_dim = D.key_dim;
+        f0.update.value_dim = D.value_dim; f0.update.norm_epsilon = D.norm_epsilon; f0.update.head_k_dim = D.head_dim;
+        whole_pass = encode_delta_net_prefill(cmd, f0, m, D.total_proj_dim, D.value_dim);
+    }
+    for (uint32_t t = 0; t < m && !whole_pass; ++t) {
         const uint64_t row = e->in_proj.ptr() + (size_t)t * D.total_proj_dim * 2;
         uzu_delta_net_fused_update_args fa{};
         uzu_delta_net_conv_update_args& ca = fa.conv;
