@@ -274,6 +274,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     eng = B.Engine(ctx, mdir, max_context_length=max_ctx, use_cuda_graph=not args.no_graph, fused_decode=not args.no_fused,
                    tp_rank=rank if tp > 1 else 0, tp_size=tp)
     replicas = 1 if tp > 1 else world
+    if args.batch > 1:
+        run_batched(args, eng, ctx, dist, rank, world, local_rank, workload, prefill, K, W)
+        return
     info = eng.info
     rng = np.random.default_rng(0)
     prompt = rng.integers(0, info.vocab_size, prefill).astype(np.uint32)
@@ -384,6 +387,61 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.destroy_process_group()
 
 
+def run_batched(args, eng, ctx, dist, rank, world, local_rank, workload, prefill, K, W):
+    """--batch B: B independent sequences decoded together (uzu_engine_batch_*: one pass over the weights per step for all of them).
+    value = tokens/s summed over the B sequences (and over replicas); a "step" is one batched step = B tokens."""
+    nseq = args.batch
+    info = eng.info
+    rng = np.random.default_rng(0)
+    eng.batch_begin(nseq)
+    firsts = [eng.batch_prefill(b, rng.integers(0, info.vocab_size, prefill).astype(np.uint32)) for b in range(nseq)]
+    eng.batch_decode_timed(firsts, max(W, 3))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if dist:
+        import torch
+        dist.barrier()
+        torch.cuda.synchronize()
+    launches0 = eng.launch_count
+    seconds = eng.batch_decode_timed(firsts, K)
+    launches = eng.launch_count - launches0
+    seconds = max_over_ranks(dist, seconds, "cuda")
+    clocks = sampler.stop()
+    value = whole_job_value(world, K * nseq, seconds)
+    toks = list(firsts)
+    for _ in range(3):
+        toks = eng.batch_step(toks)
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        toks = eng.batch_step(toks)              # H2D of the B input tokens, the step, D2H of the B sampled tokens
+    e2e_s = max_over_ranks(dist, time.perf_counter() - t0, "cuda")
+    peak, peak_src = hbm_peak()
+    line = {
+        "metric": "decode tokens/sec/GPU (int4)" if "int4" in workload else "decode tokens/sec/GPU",
+        "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1000.0 * seconds / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 activations x int4 weights, f32 accumulate" if "int4" in workload else "bf16 activations x int8 weights, f32 accumulate",
+        "data": "synthetic",
+        "config": {"workload": f"{workload}: prefill {prefill}, decode {K}, batch {nseq} (independent sequences, one weight pass per step), greedy",
+                   "parallelism": "replicas" if world > 1 else "single", "batch": nseq, "weight_bytes_per_token": info.weight_bytes_per_token,
+                   "cache_policy": f"inputs larger than L2: {info.weight_bytes_per_token / 1e6:.0f} MB of weights streamed every step vs 126 MB L2",
+                   "cuda_graph": False},
+        "roofline": {"bound": "hbm", "achieved": info.weight_bytes_per_token * (K / seconds) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": info.weight_bytes_per_token * (K / seconds) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel": "whole batched step (weights streamed once per step for all sequences)"},
+        "e2e": {"value": whole_job_value(world, K * nseq, e2e_s), "unit": "tokens/s", "h2d_bytes_per_step": 4 * nseq, "d2h_bytes_per_step": 4 * nseq},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    eng.close()
+    ctx.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -396,6 +454,7 @@ def main():
     ap.add_argument("--fused", action="store_true", help="(default) fold norm / gated-act / sigmoid-gate launches into the neighbouring GEMV")
     ap.add_argument("--no-fused", action="store_true", help="encode the reference's kernel sequence one launch per kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=1, help="decode this many independent sequences together (<= 16), one weight pass per step")
     ap.add_argument("--tp", type=int, default=1, help="tensor-parallel size: shard ONE model over this many ranks (= --gpus) instead of replicas")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -475,6 +475,21 @@ UZU_API uzu_status uzu_engine_decode_device(uzu_engine* e, uint32_t steps, uint6
  * state, copy bf16 logits of rows [row_begin,row_end) to `out_logits` (HOST, u16 bits) and synchronize. */
 UZU_API uzu_status uzu_engine_forward(uzu_engine* e, const uint32_t* tokens, uint32_t count, uint32_t row_begin,
                                       uint32_t row_end, uint16_t* out_logits);
+/* Multi-sequence batched decode (extension -- the reference decodes ONE sequence; BASELINE config 4 "batch = 8"): `sequences` (<= 16)
+ * independent sequence states (own KV caches / DeltaNet states / positions) advance by one token per step and share one pass over the
+ * weights (every linear runs with m = sequences rows); attention and the DeltaNet recurrence run per sequence. Greedy sampling.
+ *   batch_begin        allocate / reset the sequence states (the engine's own single-sequence state is untouched)
+ *   batch_prefill      ordinary chunked prefill of `tokens` (HOST) into sequence `sequence`; returns its first sampled token
+ *   batch_step         tokens_in[sequences] (HOST) -> one step for all sequences -> tokens_out[sequences] (HOST)
+ *   batch_decode_timed `steps` device-chained steps from first_tokens[sequences] between two CUDA events; seconds for all of them
+ *   batch_logits       bf16 logits [sequences, vocab] of the last step (parity tests)
+ * NOT yet run on hardware (round 1): orchestration of the parity-tested kernels, plain stream-ordered launches (no CUDA graph yet). */
+UZU_API uzu_status uzu_engine_batch_begin(uzu_engine* e, uint32_t sequences);
+UZU_API uzu_status uzu_engine_batch_prefill(uzu_engine* e, uint32_t sequence, const uint32_t* tokens, uint32_t count, uint32_t* out_token);
+UZU_API uzu_status uzu_engine_batch_step(uzu_engine* e, const uint32_t* tokens_in, uint32_t* tokens_out);
+UZU_API uzu_status uzu_engine_batch_decode_timed(uzu_engine* e, const uint32_t* first_tokens, uint32_t steps, double* out_seconds);
+UZU_API uzu_status uzu_engine_batch_logits(uzu_engine* e, uint16_t* out_logits);
+UZU_API uint32_t uzu_engine_batch_context_length(const uzu_engine* e, uint32_t sequence);
 UZU_API uint64_t uzu_engine_launch_count(const uzu_engine* e);   /* kernels launched (incl. graph nodes replayed) */
 /* Measurement helpers (bench.py). All time with CUDA events recorded on the engine's stream.
  *  decode_timed: `steps` device-chained decode passes between two events; returns seconds.

@@ -146,7 +146,8 @@ uzu_full_precision_embedding_lookup_encode uzu_logit_transform_encode uzu_tensor
 uzu_tensor_add_bias_encode uzu_tensor_add_swap_encode uzu_unified_sampling_encode uzu_delta_net_conv_update_encode
 uzu_delta_net_update_encode uzu_engine_create uzu_engine_destroy uzu_engine_info uzu_engine_reset uzu_engine_context_length
 uzu_engine_snapshot uzu_engine_restore uzu_engine_prefill uzu_engine_next uzu_engine_flush uzu_engine_decode_device
-uzu_engine_forward uzu_engine_launch_count uzu_engine_decode_timed uzu_engine_step_host
+uzu_engine_forward uzu_engine_batch_begin uzu_engine_batch_prefill uzu_engine_batch_step uzu_engine_batch_decode_timed
+uzu_engine_batch_logits uzu_engine_batch_context_length uzu_engine_launch_count uzu_engine_decode_timed uzu_engine_step_host
 uzu_delta_net_fused_update_supported uzu_delta_net_fused_update_encode uzu_engine_time_linears uzu_engine_time_prefill_linears uzu_engine_time_linears_select uzu_debug_set_qmv_tuning uzu_debug_set_delta_prefill uzu_debug_set_prefill_attention uzu_debug_set_umma uzu_tp_get_unique_id uzu_context_tp_init uzu_context_tp_destroy uzu_context_tp_size
 uzu_context_tp_rank uzu_tp_p2p_export uzu_tp_p2p_import uzu_tp_all_reduce_encode uzu_tp_all_gather_encode uzu_fused_linear_supported uzu_fused_linear_encode""".split()
 
@@ -244,6 +245,12 @@ def load() -> C.CDLL:
         "uzu_engine_decode_device": (C.c_int, [vp, u32, u64]),
         "uzu_engine_forward": (C.c_int, [vp, C.POINTER(u32), u32, u32, u32, C.POINTER(C.c_uint16)]),
         "uzu_engine_launch_count": (u64, [vp]),
+        "uzu_engine_batch_begin": (C.c_int, [vp, u32]),
+        "uzu_engine_batch_prefill": (C.c_int, [vp, u32, C.POINTER(u32), u32, C.POINTER(u32)]),
+        "uzu_engine_batch_step": (C.c_int, [vp, C.POINTER(u32), C.POINTER(u32)]),
+        "uzu_engine_batch_decode_timed": (C.c_int, [vp, C.POINTER(u32), u32, C.POINTER(C.c_double)]),
+        "uzu_engine_batch_logits": (C.c_int, [vp, C.POINTER(C.c_uint16)]),
+        "uzu_engine_batch_context_length": (u32, [vp, u32]),
         "uzu_engine_decode_timed": (C.c_int, [vp, u32, C.POINTER(C.c_double)]),
         "uzu_engine_step_host": (C.c_int, [vp, u32, C.POINTER(u32)]),
         "uzu_engine_time_linears": (C.c_int, [vp, u32, C.POINTER(C.c_double), C.POINTER(u64)]),
@@ -516,6 +523,35 @@ class Engine:
         out = u32()
         _check(self.lib.uzu_engine_step_host(self.h, int(token), C.byref(out)))
         return out.value
+
+    # ---- multi-sequence batched decode (extension, see include/uzu_b200.h) ----
+    def batch_begin(self, sequences: int):
+        _check(self.lib.uzu_engine_batch_begin(self.h, sequences))
+        self._batch = sequences
+
+    def batch_prefill(self, sequence: int, tokens) -> int:
+        arr = np.ascontiguousarray(tokens, dtype=np.uint32)
+        out = u32()
+        _check(self.lib.uzu_engine_batch_prefill(self.h, sequence, arr.ctypes.data_as(C.POINTER(u32)), len(arr), C.byref(out)))
+        return out.value
+
+    def batch_step(self, tokens_in) -> list:
+        arr = np.ascontiguousarray(tokens_in, dtype=np.uint32)
+        assert len(arr) == self._batch
+        out = np.zeros(self._batch, np.uint32)
+        _check(self.lib.uzu_engine_batch_step(self.h, arr.ctypes.data_as(C.POINTER(u32)), out.ctypes.data_as(C.POINTER(u32))))
+        return [int(t) for t in out]
+
+    def batch_decode_timed(self, first_tokens, steps: int) -> float:
+        arr = np.ascontiguousarray(first_tokens, dtype=np.uint32)
+        t = C.c_double()
+        _check(self.lib.uzu_engine_batch_decode_timed(self.h, arr.ctypes.data_as(C.POINTER(u32)), steps, C.byref(t)))
+        return t.value
+
+    def batch_logits(self) -> np.ndarray:
+        out = np.zeros((self._batch, self.info.vocab_size), np.uint16)
+        _check(self.lib.uzu_engine_batch_logits(self.h, out.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return out
 
     def time_prefill_linears(self, m: int, iters: int = 3):
         """(seconds per pass, useful flops per pass) of every linear of one prefill pass over m rows (tensor-core GEMM for m >= 64)."""

@@ -383,6 +383,9 @@ struct uzu_engine {
     uint32_t tp_rank = 0, tp_size = 1, vocab_local = 0;
     bool tp_sharded = false;       // the checkpoint is a shard: row-parallel partials in f32 + exchange, vocab-parallel readout
     Buf tp_partial, logits_local, tp_gather;
+    // multi-sequence batched decode (extension, BASELINE config 4 "batch=8"): independent sequence states sharing one weight pass per step
+    struct Sequence { std::vector<LayerState> layers; uint32_t context_length = 0; };
+    std::vector<Sequence> seqs;
     // streaming
     uzu_sampling_method sampling{};
     uint32_t steps_issued = 0, steps_returned = 0;
@@ -785,6 +788,42 @@ static void create_state_and_scratch(uzu_engine* e) {
     }
     cudaEventCreateWithFlags(&e->step_events[0], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->step_events[1], cudaEventDisableTiming);
+}
+
+// One more independent sequence state (KV caches, DeltaNet states) with the same geometry as e->state: multi-sequence batched decode.
+static void alloc_sequence_state(uzu_engine* e, std::vector<LayerState>& st) {
+    const uint32_t rows_total = e->max_context + MAX_ROWS;
+    const bool sparse = (uzu_context_device_capabilities(e->ctx) & UZU_CAP_SPARSE_BUFFERS) != 0;
+    st.assign(e->layers.size(), LayerState{});
+    for (size_t i = 0; i < e->layers.size(); ++i) {
+        const Layer& L = e->layers[i];
+        LayerState& S = st[i];
+        if (L.is_attention) {
+            S.row_bytes = (size_t)L.attn.num_groups * L.attn.head_dim * 2;
+            const size_t bytes = (size_t)rows_total * S.row_bytes;
+            if (sparse) {
+                check(uzu_sparse_buffer_create(e->ctx, bytes, &S.k_sparse));
+                check(uzu_sparse_buffer_create(e->ctx, bytes, &S.v_sparse));
+                S.keys = uzu_sparse_buffer_gpu_ptr(S.k_sparse);
+                S.values = uzu_sparse_buffer_gpu_ptr(S.v_sparse);
+            } else {
+                S.k_dense = make_buf(e, bytes, UZU_BUFFER_DEVICE);
+                S.v_dense = make_buf(e, bytes, UZU_BUFFER_DEVICE);
+                S.keys = S.k_dense.ptr();
+                S.values = S.v_dense.ptr();
+            }
+        } else {
+            const DeltaNetLayer& D = L.dn;
+            S.conv_bytes = (size_t)D.conv_dim * (D.kernel_size - 1) * 4;
+            S.ssm_bytes = (size_t)D.num_heads * D.value_head_dim * D.head_dim * 4;
+            S.conv_state = make_buf(e, S.conv_bytes, UZU_BUFFER_DEVICE);
+            S.ssm_state = make_buf(e, S.ssm_bytes, UZU_BUFFER_DEVICE);
+            S.conv_snapshot = make_buf(e, S.conv_bytes, UZU_BUFFER_DEVICE);
+            S.ssm_snapshot = make_buf(e, S.ssm_bytes, UZU_BUFFER_DEVICE);
+            cudaMemsetAsync((void*)S.conv_state.ptr(), 0, S.conv_bytes, e->ctx->stream);
+            cudaMemsetAsync((void*)S.ssm_state.ptr(), 0, S.ssm_bytes, e->ctx->stream);
+        }
+    }
 }
 
 // TransformerState::prepare (state.rs:141-172): make sure KV pages for rows [0, rows) are mapped
@@ -1482,6 +1521,11 @@ void uzu_engine_destroy(uzu_engine* e) {
         if (S.k_sparse) uzu_sparse_buffer_destroy(S.k_sparse);
         if (S.v_sparse) uzu_sparse_buffer_destroy(S.v_sparse);
     }
+    for (auto& q : e->seqs)
+        for (auto& S : q.layers) {
+            if (S.k_sparse) uzu_sparse_buffer_destroy(S.k_sparse);
+            if (S.v_sparse) uzu_sparse_buffer_destroy(S.v_sparse);
+        }
     for (auto* b : e->owned) uzu_buffer_destroy(b);
     if (e->step_events[0]) cudaEventDestroy(e->step_events[0]);
     if (e->step_events[1]) cudaEventDestroy(e->step_events[1]);
@@ -1642,6 +1686,241 @@ uzu_status uzu_engine_step_host(uzu_engine* e, uint32_t token_in, uint32_t* toke
         e->steps_returned = e->steps_issued;
         if (token_out) *token_out = tok;
     });
+}
+
+// ---- multi-sequence batched decode (extension; the reference is single-sequence: batch_dim = tokens of ONE sequence, SURVEY 7 hard part 5) ----
+// B independent sequences (own KV caches / DeltaNet states / positions) advance by one token per step and share ONE pass over the weights:
+// every linear runs with m = B rows (the m <= 16 GEMV streams the matrix once for all rows), norms / activations / embedding / sampling take
+// B rows, only attention and the DeltaNet recurrence run per sequence (their state is per sequence). Plain stream-ordered launches (no CUDA
+// graph yet). NOT yet run on hardware (written after round 1's GPU budget was spent); orchestration of parity-tested kernels only.
+namespace uzu {
+
+struct SeqSwap {   // RAII: make sequence b the engine's current state for code written against e->state / e->context_length
+    uzu_engine* e; uint32_t b;
+    SeqSwap(uzu_engine* e_, uint32_t b_) : e(e_), b(b_) { std::swap(e->state, e->seqs[b].layers); std::swap(e->context_length, e->seqs[b].context_length); }
+    ~SeqSwap() { std::swap(e->state, e->seqs[b].layers); std::swap(e->context_length, e->seqs[b].context_length); }
+};
+
+static void encode_batch_step(uzu_engine* e, uzu_command_buffer* cmd) {
+    const uint32_t B = (uint32_t)e->seqs.size(), H = e->model_dim;
+    if (e->in_emb.w.prologue == UZU_B_FULL_PRECISION) {
+        uzu_full_precision_embedding_lookup_encode(cmd, e->token_ids.ptr(), e->in_emb.w.values.ptr(), e->hidden_a.ptr(), B, e->vocab, H, e->input_scale);
+    } else {
+        uzu_quantized_embedding_lookup_args la{};
+        la.token_ids = e->token_ids.ptr(); la.weights = e->in_emb.w.values.ptr(); la.scales = e->in_emb.w.scales.ptr();
+        la.zero_points = e->in_emb.w.zero_points.ptr(); la.biases = e->in_emb.w.biases.ptr(); la.output = e->hidden_a.ptr();
+        la.batch_size = B; la.vocab_size = e->vocab; la.model_dim = H; la.input_scale = e->input_scale;
+        la.group_size = e->in_emb.w.group_size; la.quantization_mode = e->in_emb.w.mode;
+        la.quantization_method = e->in_emb.w.prologue == UZU_B_SCALE_BIAS_DEQUANT ? UZU_QMETHOD_SCALE_BIAS
+                                 : e->in_emb.w.prologue == UZU_B_SCALE_ZERO_POINT_DEQUANT ? UZU_QMETHOD_SCALE_ZERO_POINT : UZU_QMETHOD_SCALE_SYMMETRIC;
+        uzu_quantized_embedding_lookup_encode(cmd, &la);
+    }
+    uint64_t hidden = e->hidden_a.ptr();
+    for (size_t i = 0; i < e->layers.size(); ++i) {
+        Layer& L = e->layers[i];
+        encode_norm(cmd, L.pre_mixer, hidden, e->hidden_b.ptr(), e->shortcut.ptr(), i == 0 ? ShortcutCopy : ShortcutAdd, B);
+        if (L.is_attention) {
+            const AttentionLayer& A = L.attn;
+            const uint32_t D = A.head_dim, Hq = A.num_heads, Hkv = A.num_groups, total_heads = Hq + 2 * Hkv;
+            const size_t qkv_row = (size_t)total_heads * D * 2, q_row = (size_t)Hq * D * 2;
+            if (A.has_gate) encode_linear(cmd, A.gate, e->hidden_b.ptr(), B, e->gate.ptr());
+            encode_linear(cmd, A.qkv, e->hidden_b.ptr(), B, e->qkv.ptr());
+            for (uint32_t b = 0; b < B; ++b) {     // per sequence: q/k norm, RoPE at its own position + KV append, attention over its own cache
+                LayerState& S = e->seqs[b].layers[i];
+                const uint32_t pos = e->seqs[b].context_length;
+                const uint64_t qkv_b = e->qkv.ptr() + b * qkv_row;
+                auto qkn = [&](const Norm& n, uint32_t off, uint32_t cnt) {
+                    if (!n.present || cnt == 0) return;
+                    uzu_qkv_norm_args qa{};
+                    qa.scales = n.scales.ptr(); qa.qkv_output = qkv_b;
+                    qa.batch_size = 1; qa.total_heads = total_heads; qa.head_dim = D;
+                    qa.epsilon = n.cfg.epsilon; qa.scale_offset = n.cfg.scale_offset;
+                    qa.head_offset = off; qa.head_count = cnt; qa.full_layer = n.cfg.full_layer;
+                    qa.in_place = 1; qa.has_scales = n.cfg.has_scale;
+                    uzu_qkv_norm_encode(cmd, &qa);
+                };
+                qkn(A.qnorm, 0, Hq);
+                qkn(A.knorm, Hq, Hkv);
+                uzu_attention_prepare_args pa{};
+                pa.qkv = qkv_b; pa.queries = e->queries.ptr() + b * q_row;
+                pa.keys = S.keys; pa.values = S.values;
+                pa.num_q_heads = Hq; pa.num_kv_heads = Hkv; pa.head_dim = D;
+                pa.kv_token_offset = S.length; pa.batch_dim = 1; pa.has_kv = 1;
+                if (A.rope_index >= 0) {
+                    const RopeCfg& rc = e->ropes[A.rope_index];
+                    pa.has_rope = 1; pa.rope_dim = rc.head_dim;
+                    pa.cosines = e->rope_cos[A.rope_index].ptr() + (size_t)pos * rc.head_dim * 4;
+                    pa.sines = e->rope_sin[A.rope_index].ptr() + (size_t)pos * rc.head_dim * 4;
+                }
+                uzu_attention_prepare_encode(cmd, &pa);
+                uzu_attention_args aa{};
+                aa.queries = pa.queries; aa.keys = S.keys; aa.values = S.values; aa.out = e->attn_out.ptr() + b * q_row;
+                aa.gqa_factor = Hq / Hkv; aa.sequence_length = S.length + 1;
+                aa.k_head_stride = D; aa.k_seq_stride = Hkv * D; aa.v_head_stride = D; aa.v_seq_stride = Hkv * D;
+                aa.scale = A.has_scale ? A.scale : 1.0f / sqrtf((float)D);
+                aa.num_heads = Hq; aa.suffix_length = 1; aa.head_dim = D; aa.is_causal = A.is_causal;
+                uzu_attention_single_pass_encode(cmd, &aa);
+            }
+            if (A.has_gate) uzu_sigmoid_gate_encode(cmd, e->gate.ptr(), e->attn_out.ptr(), B * Hq * D);
+            encode_linear(cmd, A.out, e->attn_out.ptr(), B, e->mixer_out.ptr());
+        } else {
+            const DeltaNetLayer& D = L.dn;
+            encode_linear(cmd, D.in_proj, e->hidden_b.ptr(), B, e->in_proj.ptr());
+            for (uint32_t b = 0; b < B; ++b) {     // per sequence: its own rolling conv state and recurrent state
+                LayerState& S = e->seqs[b].layers[i];
+                const uint64_t row = e->in_proj.ptr() + (size_t)b * D.total_proj_dim * 2;
+                uzu_delta_net_conv_update_args ca{};
+                ca.conv_weight = D.conv_weight.ptr(); ca.bias = D.conv_bias.ptr(); ca.in_out = row; ca.state = S.conv_state.ptr();
+                ca.kernel_size = D.kernel_size; ca.conv_dim = D.conv_dim; ca.state_stride = D.kernel_size - 1; ca.has_bias = D.conv_has_bias;
+                uzu_delta_net_conv_update_encode(cmd, &ca);
+                uzu_delta_net_update_args ua{};
+                ua.in_proj = row; ua.a_log = D.a_log.ptr(); ua.dt_bias = D.dt_bias.ptr(); ua.norm_weight = D.norm_weight.ptr();
+                ua.state = S.ssm_state.ptr(); ua.out = e->delta_out.ptr() + (size_t)b * D.value_dim * 2;
+                ua.num_v_heads = D.num_heads; ua.num_k_heads = D.num_groups; ua.head_v_dim = D.value_head_dim; ua.key_dim = D.key_dim;
+                ua.value_dim = D.value_dim; ua.norm_epsilon = D.norm_epsilon; ua.head_k_dim = D.head_dim;
+                uzu_delta_net_update_encode(cmd, &ua);
+            }
+            encode_linear(cmd, D.out_proj, e->delta_out.ptr(), B, e->mixer_out.ptr());
+        }
+        encode_norm(cmd, L.pre_mlp, e->mixer_out.ptr(), e->hidden_b.ptr(), e->shortcut.ptr(), ShortcutAdd, B);
+        encode_linear(cmd, L.up, e->hidden_b.ptr(), B, e->fused_up.ptr());
+        uzu_gated_act_mul_args ga{};
+        ga.act_operand = e->fused_up.ptr(); ga.fp_out = e->gated.ptr(); ga.gated_dim = L.hidden_dim; ga.batch_dim = B;
+        ga.act_type = L.act; ga.interleaved = 1;
+        uzu_gated_act_mul_encode(cmd, &ga);
+        encode_linear(cmd, L.down, e->gated.ptr(), B, e->hidden_a.ptr());
+        hidden = e->hidden_a.ptr();
+    }
+    encode_norm(cmd, e->out_norm, hidden, e->normed_out.ptr(), e->shortcut.ptr(), ShortcutAdd, B);
+    encode_linear(cmd, e->out_emb, e->normed_out.ptr(), B, e->logits.ptr());
+    if (e->has_logit_scale || e->has_logit_soft_cap)
+        uzu_logit_transform_encode(cmd, e->logits.ptr(), B * e->vocab, e->has_logit_scale ? e->logit_scale : 1.0f, e->logit_soft_cap, e->has_logit_soft_cap);
+    encode_sampling(e, cmd, B);
+}
+
+// one step for all sequences; `chain` copies the sampled tokens into token_ids on the device (next step's inputs)
+static void run_batch_step(uzu_engine* e, bool chain) {
+    const uint32_t B = (uint32_t)e->seqs.size();
+    for (uint32_t b = 0; b < B; ++b) {
+        if (e->seqs[b].context_length + 1 > e->max_context + MAX_ROWS || e->seqs[b].context_length + 1 > e->rope_positions)
+            throw std::runtime_error("batch step: context overflow in sequence " + std::to_string(b));
+        SeqSwap sw(e, b);
+        state_prepare(e, e->context_length + 1);
+    }
+    CmdGuard g(e->ctx, "batch step");
+    g.c->state = uzu_command_buffer::Encoding;
+    encode_batch_step(e, g.c);
+    if (g.c->sticky != UZU_OK) throw std::runtime_error(g.c->sticky_msg);
+    e->launches += g.c->launches;
+    if (chain) cudaMemcpyAsync((void*)e->token_ids.ptr(), (void*)e->sampled.ptr(), B * 4, cudaMemcpyDeviceToDevice, e->ctx->stream);
+    for (uint32_t b = 0; b < B; ++b) {
+        for (size_t i = 0; i < e->layers.size(); ++i)
+            if (e->layers[i].is_attention) e->seqs[b].layers[i].length += 1;
+        e->seqs[b].context_length += 1;
+    }
+}
+
+}  // namespace uzu
+
+uzu_status uzu_engine_batch_begin(uzu_engine* e, uint32_t sequences) {
+    UZU_ENGINE_TRY({
+        if (sequences == 0 || sequences > 16) throw std::runtime_error("batch_begin: 1..16 sequences (the m <= 16 GEMV rows)");
+        if (e->tp_sharded) throw std::runtime_error("batch_begin: not combined with tensor parallelism yet");
+        if (e->sampling.kind == UZU_SAMPLING_STOCHASTIC) throw std::runtime_error("batch decode samples greedily (per-row seeds are not wired yet)");
+        if (e->logits_rows < sequences) throw std::runtime_error("batch_begin: logits scratch too small");
+        cudaStreamSynchronize(e->ctx->stream);
+        while (e->seqs.size() < sequences) {
+            e->seqs.emplace_back();
+            alloc_sequence_state(e, e->seqs.back().layers);
+        }
+        while (e->seqs.size() > sequences) {
+            for (auto& S : e->seqs.back().layers) {
+                if (S.k_sparse) uzu_sparse_buffer_destroy(S.k_sparse);
+                if (S.v_sparse) uzu_sparse_buffer_destroy(S.v_sparse);
+            }
+            e->seqs.pop_back();
+        }
+        for (auto& q : e->seqs) {       // reset every sequence
+            q.context_length = 0;
+            for (auto& S : q.layers) {
+                S.length = 0;
+                if (S.conv_state.b) {
+                    cudaMemsetAsync((void*)S.conv_state.ptr(), 0, S.conv_bytes, e->ctx->stream);
+                    cudaMemsetAsync((void*)S.ssm_state.ptr(), 0, S.ssm_bytes, e->ctx->stream);
+                }
+            }
+        }
+        cudaStreamSynchronize(e->ctx->stream);
+    });
+}
+
+uzu_status uzu_engine_batch_prefill(uzu_engine* e, uint32_t sequence, const uint32_t* tokens, uint32_t count, uint32_t* out_token) {
+    UZU_ENGINE_TRY({
+        if (sequence >= e->seqs.size()) throw std::runtime_error("batch_prefill: no such sequence (batch_begin first)");
+        if (!tokens || count == 0) throw std::runtime_error("batch_prefill: empty prompt");
+        uint32_t tok = 0;
+        {
+            SeqSwap sw(e, sequence);    // the ordinary chunked prefill, against this sequence's state
+            for (uint32_t s0 = 0; s0 < count; s0 += MAX_ROWS) {
+                const uint32_t n = std::min(MAX_ROWS, count - s0);
+                const bool last = s0 + n == count;
+                run_pass(e, tokens + s0, n, last ? n - 1 : 0, last ? n : 0, last);
+            }
+            cudaMemcpy(&tok, (void*)e->sampled.ptr(), 4, cudaMemcpyDeviceToHost);
+        }
+        if (out_token) *out_token = tok;
+    });
+}
+
+uzu_status uzu_engine_batch_step(uzu_engine* e, const uint32_t* tokens_in, uint32_t* tokens_out) {
+    UZU_ENGINE_TRY({
+        const uint32_t B = (uint32_t)e->seqs.size();
+        if (B == 0 || !tokens_in) throw std::runtime_error("batch_step: batch_begin first / null tokens");
+        uint32_t* staging = (uint32_t*)uzu_buffer_cpu_ptr(e->host_tokens.b);
+        memcpy(staging, tokens_in, B * 4);
+        cudaMemcpyAsync((void*)e->token_ids.ptr(), staging, B * 4, cudaMemcpyHostToDevice, e->ctx->stream);
+        run_batch_step(e, false);
+        cudaMemcpyAsync(staging + 16, (void*)e->sampled.ptr(), B * 4, cudaMemcpyDeviceToHost, e->ctx->stream);
+        cudaError_t err = cudaStreamSynchronize(e->ctx->stream);
+        if (err != cudaSuccess) throw std::runtime_error(std::string("batch_step: ") + cudaGetErrorString(err));
+        if (tokens_out) memcpy(tokens_out, staging + 16, B * 4);
+    });
+}
+
+uzu_status uzu_engine_batch_decode_timed(uzu_engine* e, const uint32_t* first_tokens, uint32_t steps, double* out_seconds) {
+    UZU_ENGINE_TRY({
+        const uint32_t B = (uint32_t)e->seqs.size();
+        if (B == 0 || !first_tokens || steps == 0) throw std::runtime_error("batch_decode_timed: batch_begin first / null tokens / zero steps");
+        cudaStream_t s = e->ctx->stream;
+        uint32_t* staging = (uint32_t*)uzu_buffer_cpu_ptr(e->host_tokens.b);
+        memcpy(staging, first_tokens, B * 4);
+        cudaMemcpyAsync((void*)e->token_ids.ptr(), staging, B * 4, cudaMemcpyHostToDevice, s);
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, s);
+        for (uint32_t i = 0; i < steps; ++i) run_batch_step(e, true);     // sampled tokens chained on the device, no host round trip
+        cudaEventRecord(b, s);
+        cudaError_t err = cudaEventSynchronize(b);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, a, b);
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        if (err != cudaSuccess) throw std::runtime_error(std::string("batch_decode_timed: ") + cudaGetErrorString(err));
+        if (out_seconds) *out_seconds = (double)ms * 1e-3;
+    });
+}
+
+uzu_status uzu_engine_batch_logits(uzu_engine* e, uint16_t* out_logits) {
+    UZU_ENGINE_TRY({
+        if (e->seqs.empty() || !out_logits) throw std::runtime_error("batch_logits: batch_begin first / null output");
+        cudaStreamSynchronize(e->ctx->stream);
+        cudaMemcpy(out_logits, (void*)e->logits.ptr(), e->seqs.size() * (size_t)e->vocab * 2, cudaMemcpyDeviceToHost);
+    });
+}
+
+uint32_t uzu_engine_batch_context_length(const uzu_engine* e, uint32_t sequence) {
+    return e && sequence < e->seqs.size() ? e->seqs[sequence].context_length : 0;
 }
 
 uzu_status uzu_engine_time_linears_select(uzu_engine* e, uint32_t iters, uint32_t select, double* out_seconds, uint64_t* out_launches) {
