@@ -2,8 +2,7 @@
 over the weights per step, against B independent oracle models (the reference decodes one sequence at a time: N independent reference runs
 are the oracle for an N-sequence batch).
 
-Written after round 1's GPU budget was spent -- orchestration of parity-tested kernels, but it has NOT run on hardware: skipped unless
-UZU_TEST_BATCH_DECODE=1 (an unvalidated assertion must not turn the suite red)."""
+First hardware run: round 2 (3 passed, profiles/r2_first_hardware_run.txt)."""
 import os
 
 import numpy as np
@@ -15,8 +14,7 @@ from tests.util import bf16_to_f32
 from uzu_b200 import binding as B
 from uzu_b200 import synth
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("UZU_TEST_BATCH_DECODE"), reason="opt-in: multi-sequence batched decode is not validated on hardware yet")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("kind,nseq", [("llama", 3), ("qwen-hybrid", 2), ("llama-512", 8)])

@@ -1,9 +1,9 @@
-"""Opt-in multi-token DeltaNet prefill kernel (uzu_b200/csrc/deltanet_prefill.cu: the m-token recurrence of a layer in ONE launch, state
+"""Multi-token DeltaNet prefill kernel (uzu_b200/csrc/deltanet_prefill.cu: the m-token recurrence of a layer in ONE launch, state
 resident in shared memory) against the oracle's token-by-token DeltaNet (backends/cpu/kernel/gdn/{conv_update,update}.rs restated in C) and
 against the default path (the parity-tested decode kernel launched once per token inside the batched pass).
 
-Written after round 1's GPU budget was spent: it has NOT run on hardware, so these tests are skipped unless UZU_TEST_DELTA_PREFILL=1
-(an unvalidated assertion must not turn the suite red). First thing to run in round 2 together with the prefill-attention tests."""
+First hardware run: round 2 (3 passed, profiles/r2_first_hardware_run.txt); the kernel is now the default hybrid prefill recurrence
+(UZU_DELTA_PREFILL_KERNEL=0 restores one decode-kernel launch per token)."""
 import os
 
 import numpy as np
@@ -15,8 +15,7 @@ from tests.util import bf16_to_f32
 from uzu_b200 import binding as B
 from uzu_b200 import synth
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("UZU_TEST_DELTA_PREFILL"), reason="opt-in: the one-launch DeltaNet prefill kernel is not validated on hardware yet")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("n", [2, 21, 90])

@@ -1,10 +1,9 @@
-"""Parity of the opt-in tensor-core prefill attention (uzu_b200/csrc/attention_prefill.cu) against the CPU oracle's
+"""Parity of the tensor-core prefill attention (uzu_b200/csrc/attention_prefill.cu) against the CPU oracle's
 AttentionSinglePass restatement (backends/cpu/kernel/attention/attention_single_pass.rs:49-126) and the independent float64 softmax of
 tests/unit/encodable_block/attention_test.rs:26-124, on the reference tests' closed-form inputs (attention_single_pass_test.rs:33-78).
 
-The kernel was written at the end of round 1; its only hardware run is tools/prefill_attn_probe.py (float64 softmax, 3 shapes, passed).
-These oracle-ulp tests have not run yet, so they are skipped unless UZU_TEST_PREFILL_ATTN=1 (an unvalidated assertion must not turn the
-suite red); they are the first thing to run in round 2, after which the path becomes the default."""
+First hardware run of these tests: round 2 (7 passed, profiles/r2_first_hardware_run.txt); since then the kernel is the default prefill
+attention for head_dim 64 / 128 (UZU_PREFILL_ATTN=0 restores the split-KV kernel applied per query token)."""
 import os
 
 import numpy as np
@@ -15,8 +14,7 @@ from tests import gpu_ops as G
 from tests.test_oracle_pins import attention_inputs, softmax_reference
 from tests.util import assert_bf16_close, bf16_to_f32, f32_to_bf16
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("UZU_TEST_PREFILL_ATTN"), reason="opt-in: tensor-core prefill attention is not validated on hardware yet")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture

@@ -67,8 +67,7 @@ def _gpu_count():
         return 0
 
 
-@pytest.mark.skipif(_gpu_count() < 2 or not os.environ.get("UZU_TEST_TP_NCCL"),
-                    reason="needs two GPUs and UZU_TEST_TP_NCCL=1 (gpurun --gpus 2): the NCCL path has not run on hardware yet (DESIGN.md 5)")
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
 @pytest.mark.parametrize("exchange", ["nccl", "p2p"])
 def test_two_rank_nccl_engine_matches_unsharded_oracle(tmp_path, exchange):
     spec = synth.tiny("llama-512")

@@ -201,11 +201,8 @@ __global__ void __launch_bounds__(G * 32) attn_prefill_kernel(const uzu_attentio
 template <int D, int G>
 static void launch_attn_prefill(uzu_command_buffer* cmd, const uzu_attention_args& a) {
     constexpr size_t smem = (size_t)4 * PA_BN * (D + 8) * sizeof(__nv_bfloat16);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(attn_prefill_kernel<D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
-    }
+    static std::atomic<uint64_t> smem_opt_in{0};
+    opt_in_dynamic_smem(cmd, attn_prefill_kernel<D, G>, (int)((int)smem), smem_opt_in);
     const dim3 grid((a.suffix_length + PA_BM - 1) / PA_BM, a.num_heads / G);
     attn_prefill_kernel<D, G><<<grid, G * 32, smem, cmd->ctx->stream>>>(a);
     after_launch(cmd, "attn_prefill_kernel");
@@ -215,7 +212,7 @@ static void launch_attn_prefill(uzu_command_buffer* cmd, const uzu_attention_arg
 static int g_prefill_attn = -1;   // -1: follow UZU_PREFILL_ATTN, 0 / 1: forced by uzu_debug_set_prefill_attention
 
 bool encode_attention_prefill(uzu_command_buffer* cmd, const uzu_attention_args& a) {
-    static const bool env_enabled = [] { const char* e = getenv("UZU_PREFILL_ATTN"); return e && atoi(e) != 0; }();
+    static const bool env_enabled = [] { const char* e = getenv("UZU_PREFILL_ATTN"); return !e || atoi(e) != 0; }();   // default on (validated on B200, round 2); =0 keeps the split-KV kernel
     if (!(g_prefill_attn < 0 ? env_enabled : g_prefill_attn != 0)) return false;
     if (a.suffix_length < 16 || a.dynamic_position || a.has_sinks || a.is_kv_cache_ring || a.is_trie || a.is_sliding_window) return false;
     if (a.head_dim != 64 && a.head_dim != 128) return false;

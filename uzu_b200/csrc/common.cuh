@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <string>
 
 #include "../../include/uzu_b200.h"
@@ -111,12 +112,36 @@ bool encode_attention_prefill(uzu_command_buffer* cmd, const uzu_attention_args&
 // multi-token DeltaNet recurrence in one launch (deltanet_prefill.cu, opt-in), tried by the engine's batched hybrid prefill
 bool encode_delta_net_prefill(uzu_command_buffer* cmd, const uzu_delta_net_fused_update_args& f, uint32_t rows, uint32_t in_stride, uint32_t out_stride);
 
+// The launch stream belongs to the context's device: make that device current on the calling thread (another context, or the
+// host program, may have switched it since start_encoding).
+inline void make_current(const uzu_context* ctx) {
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess || d != ctx->device) cudaSetDevice(ctx->device);
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (function, device), not of the process: opt in once per device.
+// `done` is a per-call-site (per template instance) bit mask of device ordinals; setting the attribute twice is harmless, so a
+// race between two threads only repeats the call.
+template <typename K>
+inline void opt_in_dynamic_smem(uzu_command_buffer* cmd, K kernel, int bytes, std::atomic<uint64_t>& done) {
+    const uint64_t bit = 1ull << (cmd->ctx->device & 63);
+    if (done.load(std::memory_order_acquire) & bit) return;
+    make_current(cmd->ctx);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+        cmd->record_error(UZU_ERROR_CUDA, std::string("cudaFuncSetAttribute(MaxDynamicSharedMemorySize): ") + cudaGetErrorString(e));
+        return;
+    }
+    done.fetch_or(bit, std::memory_order_release);
+}
+
 inline bool encodable(uzu_command_buffer* cmd, const char* what) {
     if (!cmd) return false;
     if (cmd->state != uzu_command_buffer::Encoding) {
         cmd->record_error(UZU_ERROR_INVALID_ARGUMENT, std::string(what) + ": command buffer is not in the Encoding state");
         return false;
     }
+    make_current(cmd->ctx);
     return true;
 }
 

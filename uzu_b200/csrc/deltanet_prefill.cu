@@ -198,7 +198,7 @@ static int g_delta_prefill = -1;   // -1: follow UZU_DELTA_PREFILL_KERNEL, 0 / 1
 
 // true = handled: the whole m-token recurrence of one DeltaNet layer in one launch
 bool encode_delta_net_prefill(uzu_command_buffer* cmd, const uzu_delta_net_fused_update_args& f, uint32_t rows, uint32_t in_stride, uint32_t out_stride) {
-    static const bool env_enabled = [] { const char* e = getenv("UZU_DELTA_PREFILL_KERNEL"); return e && atoi(e) != 0; }();
+    static const bool env_enabled = [] { const char* e = getenv("UZU_DELTA_PREFILL_KERNEL"); return !e || atoi(e) != 0; }();   // default on (validated on B200, round 2)
     if (!(g_delta_prefill < 0 ? env_enabled : g_delta_prefill != 0)) return false;
     const uzu_delta_net_update_args& a = f.update;
     const uzu_delta_net_conv_update_args& c = f.conv;
@@ -208,11 +208,8 @@ bool encode_delta_net_prefill(uzu_command_buffer* cmd, const uzu_delta_net_fused
     if (!a.in_proj || !a.a_log || !a.dt_bias || !a.norm_weight || !a.state || !a.out || !c.conv_weight || !c.state || (c.has_bias && !c.bias)) return false;
     if ((a.state & 15u)) return false;
     const size_t smem = ((size_t)a.head_v_dim * DP_DK + 4 * DP_DK + 8) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(delta_net_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)128 * DP_DK + 4 * DP_DK + 8) * sizeof(float)));
-        attr_done = true;
-    }
+    static std::atomic<uint64_t> smem_opt_in{0};
+    opt_in_dynamic_smem(cmd, delta_net_prefill_kernel, (int)((int)(((size_t)128 * DP_DK + 4 * DP_DK + 8) * sizeof(float))), smem_opt_in);
     DeltaPrefillParams p{f, rows, in_stride, out_stride};
     delta_net_prefill_kernel<<<a.num_v_heads, DP_THREADS, smem, cmd->ctx->stream>>>(p);
     after_launch(cmd, "delta_net_prefill_kernel");

@@ -175,12 +175,25 @@ struct ParameterLoader {
     std::map<std::string, TensorInfo> tensors;
     std::map<std::string, std::string> metadata;
     std::set<std::string> validated;
+    uint64_t file_size = 0;
+
+    static uint64_t dtype_size(const std::string& dt) {   // parameters/safetensors_metadata.rs:93-108
+        if (dt == "F32" || dt == "I32" || dt == "U32") return 4;
+        if (dt == "F16" || dt == "BF16") return 2;
+        if (dt == "I8" || dt == "U8") return 1;
+        if (dt == "I64" || dt == "U64") return 8;
+        return 0;
+    }
 
     explicit ParameterLoader(const std::string& path) {
         fd = open(path.c_str(), O_RDONLY);
         if (fd < 0) throw std::runtime_error("cannot open " + path);
+        struct stat st{};
+        if (fstat(fd, &st) != 0) throw std::runtime_error("cannot stat " + path);
+        file_size = (uint64_t)st.st_size;
         uint64_t hlen = 0;
         if (pread(fd, &hlen, 8, 0) != 8) throw std::runtime_error("safetensors: short header");
+        if (hlen > (100ull << 20) || 8 + hlen > file_size) throw std::runtime_error("safetensors: implausible header length");
         std::string header(hlen, '\0');
         if ((uint64_t)pread(fd, &header[0], hlen, 8) != hlen) throw std::runtime_error("safetensors: short header");
         data_offset = 8 + hlen;
@@ -214,6 +227,12 @@ struct ParameterLoader {
             throw std::runtime_error(os.str());
         }
         if (it->second.dtype != dtype) throw std::runtime_error("tensor '" + name + "' has dtype " + it->second.dtype + ", expected " + dtype);
+        // the buffer is sized from the offsets while kernels index by shape: a truncated / corrupt file must be a load error
+        uint64_t numel = 1;
+        for (auto d : shape) numel *= d;
+        const TensorInfo& t = it->second;
+        if (t.end < t.begin || data_offset + t.end > file_size || t.end - t.begin != numel * dtype_size(dtype))
+            throw std::runtime_error("tensor '" + name + "': data_offsets do not match shape x dtype or exceed the file");
         validated.insert(name);
         return it->second;
     }
@@ -394,6 +413,7 @@ struct uzu_engine {
     cudaGraphExec_t graph_exec = nullptr;
     uint32_t graph_bucket = 0;
     bool graph_stochastic = false;
+    uzu_sampling_method graph_sampling{};   // the method baked into the captured sampling launch (seed excluded: it lives in DecodeState)
     uint64_t graph_launches_per_step = 0;
     bool use_pdl = true;   // programmatic dependent launch between the kernels of a decode step (UZU_NO_PDL=1 disables)
     uint64_t launches = 0;
@@ -1427,6 +1447,15 @@ static void capture_decode_graph(uzu_engine* e) {
     e->graph_launches_per_step = g.c->launches;
     e->graph_bucket = attention_bucket(e->context_length + 1);
     e->graph_stochastic = e->sampling.kind == UZU_SAMPLING_STOCHASTIC;
+    e->graph_sampling = e->sampling;
+}
+
+// The captured graph passes temperature / top-k / top-p / min-p by value: it is only valid for the method it was captured with.
+static bool graph_sampling_matches(const uzu_engine* e) {
+    const uzu_sampling_method &a = e->graph_sampling, &b = e->sampling;
+    return a.kind == b.kind && a.has_temperature == b.has_temperature && (!a.has_temperature || a.temperature == b.temperature) &&
+           a.has_top_k == b.has_top_k && (!a.has_top_k || a.top_k == b.top_k) && a.has_top_p == b.has_top_p && (!a.has_top_p || a.top_p == b.top_p) &&
+           a.has_min_p == b.has_min_p && (!a.has_min_p || a.min_p == b.min_p);
 }
 
 // enqueue one decode step (no host wait)
@@ -1436,8 +1465,7 @@ static void issue_decode_step(uzu_engine* e, uint64_t dev_out, uint32_t dev_out_
     state_prepare(e, e->context_length + 1);
     cudaStream_t s = e->ctx->stream;
     if (e->opts.use_cuda_graph && !dev_out) {
-        if (!e->graph_exec || e->graph_bucket != attention_bucket(e->context_length + 1) ||
-            e->graph_stochastic != (e->sampling.kind == UZU_SAMPLING_STOCHASTIC))
+        if (!e->graph_exec || e->graph_bucket != attention_bucket(e->context_length + 1) || !graph_sampling_matches(e))
             capture_decode_graph(e);
         cudaError_t err = cudaGraphLaunch(e->graph_exec, s);
         if (err != cudaSuccess) throw std::runtime_error(std::string("cudaGraphLaunch: ") + cudaGetErrorString(err));
@@ -1479,8 +1507,9 @@ static void upload_decode_state(uzu_engine* e) {
 }  // namespace uzu
 
 #define UZU_ENGINE_TRY(...)                                            \
+    if (!e) return uzu::fail(UZU_ERROR_INVALID_ARGUMENT, "null engine"); \
     try {                                                              \
-        cudaSetDevice(e ? e->ctx->device : 0);                         \
+        cudaSetDevice(e->ctx->device);                                 \
         __VA_ARGS__;                                                   \
         return UZU_OK;                                                 \
     } catch (const std::exception& ex) {                               \
@@ -1540,7 +1569,7 @@ uzu_status uzu_engine_info(const uzu_engine* e, uzu_model_info* out) {
 
 uzu_status uzu_engine_reset(uzu_engine* e) { UZU_ENGINE_TRY(reset_state(e)); }
 
-uint32_t uzu_engine_context_length(const uzu_engine* e) { return e->context_length; }
+uint32_t uzu_engine_context_length(const uzu_engine* e) { return e ? e->context_length : 0; }
 
 uzu_status uzu_engine_snapshot(uzu_engine* e) {
     UZU_ENGINE_TRY({

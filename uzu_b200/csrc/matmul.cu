@@ -1772,32 +1772,23 @@ static void launch_qmv(uzu_command_buffer* cmd, const QmvParams& p, uint32_t til
     const uint32_t ngl = (nc * 128u + NPG - 1) / NPG + 1;
     (void)MROWS;
     size_t smem = qmv_smem_bytes(p.m, nc, ngl, MT);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(qmv_kernel<NPG, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    static std::atomic<uint64_t> smem_opt_in{0};
+    opt_in_dynamic_smem(cmd, qmv_kernel<NPG, MT>, (int)(200 * 1024), smem_opt_in);
     qmv_kernel<NPG, MT><<<tiles * p.kslices, QMV_WARPS * 32, smem, cmd->ctx->stream>>>(p);
     after_launch(cmd, "qmv_kernel");
 }
 
 template <int NPG>
 static void launch_qmv_decode(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(qmv_decode_kernel<NPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    static std::atomic<uint64_t> smem_opt_in{0};
+    opt_in_dynamic_smem(cmd, qmv_decode_kernel<NPG>, (int)(200 * 1024), smem_opt_in);
     launch(cmd, "qmv_decode_kernel", qmv_decode_kernel<NPG>, dim3(grid), dim3(QS_WARPS * 32), smem, p);
 }
 
 template <int NPG, int STAGES, int METHOD, int BITS, int PRO, bool EPI>
 static void launch_qmv_decode_async_s(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(qmv_decode_async_kernel<NPG, STAGES, METHOD, BITS, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    static std::atomic<uint64_t> smem_opt_in{0};
+    opt_in_dynamic_smem(cmd, qmv_decode_async_kernel<NPG, STAGES, METHOD, BITS, PRO, EPI>, (int)(200 * 1024), smem_opt_in);
     launch(cmd, "qmv_decode_async_kernel", qmv_decode_async_kernel<NPG, STAGES, METHOD, BITS, PRO, EPI>, dim3(grid), dim3(QS_WARPS * 32), smem, p);
 }
 template <int NPG, int METHOD, int BITS, int PRO, bool EPI>
@@ -1844,11 +1835,8 @@ static QmvTuning g_tune;
 
 template <int NPG, int MT>
 static void launch_qmv_stream(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(qmv_stream_kernel<NPG, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    static std::atomic<uint64_t> smem_opt_in{0};
+    opt_in_dynamic_smem(cmd, qmv_stream_kernel<NPG, MT>, (int)(200 * 1024), smem_opt_in);
     launch(cmd, "qmv_stream_kernel", qmv_stream_kernel<NPG, MT>, dim3(grid), dim3(QS_WARPS * 32), smem, p);
 }
 

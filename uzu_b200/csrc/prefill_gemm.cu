@@ -577,11 +577,8 @@ template <int BITS, int MT, int STAGES, int NP, bool COAL>
 static void launch_qmm(uzu_command_buffer* cmd, const QmmParams& p, dim3 grid) {
     // stages + raw-code ring (32 KB: 8 / 4 per-thread K-block slots, or two 16 KB super-block buffers) + alignment slack
     constexpr size_t smem = (size_t)STAGES * (QMM_TILE_BYTES * MT + 2 * QMM_TILE_BYTES) + 32768 + 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(qmm_umma_kernel<BITS, MT, STAGES, NP, COAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
-    }
+    static std::atomic<uint64_t> smem_opt_in{0};
+    opt_in_dynamic_smem(cmd, qmm_umma_kernel<BITS, MT, STAGES, NP, COAL>, (int)((int)smem), smem_opt_in);
     launch(cmd, "matmul qmm_umma_kernel", qmm_umma_kernel<BITS, MT, STAGES, NP, COAL>, grid, dim3(NP + 32), smem, p);
 }
 template <int BITS, int MT, int STAGES>
