@@ -1,25 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- decode tokens/s of the uzu transformer decode hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference] [--tp P]
 
-A "step" is one decoded token: one full forward pass (all layers + readout + sampling) at batch 1 over the
-synthetic uzu-format checkpoint of the workload, starting right after a `prefill`-token prompt. Default (N = 1)
-workload = BASELINE.json configs[1]: Qwen3.5-0.8B int4, prefill 512, decode 128.
+A "step" is one decoded token: one full forward pass (all layers + readout + sampling) at batch 1 over the synthetic uzu-format
+checkpoint of the workload, starting right after a `prefill`-token prompt. Default workload = the configuration the "at 1/2/4/8 B200"
+metric is quoted on: BASELINE.json configs[2], Llama-3-8B int4, prefill 2048, decode 256. The N = 1 run adds configs[1]
+(Qwen3.5-0.8B int4, prefill 512, decode 128) as `config.secondary` with its own value / e2e / roofline / parity.
 
-  value      decode tokens/s with everything resident in HBM: K device-chained steps (CUDA-graph replay, sampled token fed
-             back on the device) between two CUDA events on the engine's stream; max over ranks; whole-job (sum of replicas).
-  e2e        the same metric through the host-facing call: every step copies the input token host->device from pinned
-             memory, runs the pass, and reads the sampled token device->host (uzu_engine_step_host), wall-clock timed.
-  roofline   the weight-streaming fused dequant+GEMV (the dominant kernel): all GEMV launches of one token replayed back
-             to back between CUDA events; achieved = algorithmic weight bytes per token / that time.
-  cpu_baseline  the CPU oracle (C restatement of the reference CPU backend) decoding a few tokens of the same model on
-             this box's host cores, single worker thread like the reference (rank 0, N = 1 only).
-  --impl reference   times the same CPU restatement with all host threads (the reference itself is Rust and cannot be
-             built here: no rustc/cargo in the image).
-Multi-GPU: the BASELINE models that fit one GPU run as independent replicas (weak scaling, no collective on the path).
-`--tp P` (with --gpus P) runs ONE model sharded over the P ranks instead (uzu_b200/tp.py shards by attention head / FFN column /
-vocabulary row; two NCCL all-reduces per layer + one all-gather of the logits): value = tokens/s of that single replica, "strong".
+  value      decode tokens/s with everything resident in HBM: K device-chained steps (the sampled token is fed back on the device)
+             between two CUDA events on the engine's stream; max over ranks; WHOLE JOB = summed over the N replicas
+             (`config.per_gpu_value` = value / N).
+  e2e        the same metric through the host-facing call: every step copies the input token host->device from pinned memory, runs
+             the pass, and reads the sampled token device->host (uzu_engine_step_host), wall-clock timed.
+  roofline   the dominant kernel. Default decode path = the persistent whole-token kernel (decode_mega_kernel, ONE launch per step):
+             achieved = algorithmic bytes of a step (quantised weights + KV rows at the mid context + recurrent state) / the
+             CUDA-event duration of a launch. Per-kernel path (--no-persistent, or models the persistent kernel does not cover): all
+             fused dequant+GEMV launches of one token replayed back to back.
+  parity     the timed engine against the CPU oracle on the same checkpoint (short prompt, 3 teacher-forced decode steps):
+             greedy token ids and the last-row logit error (rank 0, N = 1).
+  cpu_baseline  the CPU oracle (C restatement of the reference CPU backend) decoding a few tokens of the same model on this box's
+             host cores, single worker thread like the reference (rank 0, N = 1 only).
+  --impl reference   times the same CPU restatement on the host threads the cgroup really grants (the reference itself is Rust and
+             cannot be built here: no rustc/cargo in the image).
+Multi-GPU: the BASELINE models that fit one GPU run as independent replicas (weak scaling, no collective on the path). At N >= 2 the
+run also shards ONE copy of the model over the N ranks (uzu_b200/tp.py: attention head / FFN column / vocabulary row; two all-reduces
+per layer + one all-gather of the logits) and reports it under `config.tp` for both exchanges (NCCL, one-kernel peer memory).
+`--tp P` (with --gpus P) makes that sharded model the headline instead: value = tokens/s of the single replica, "strong".
 """
 from __future__ import annotations
 
@@ -173,6 +180,28 @@ def tensor_peak():
     return 1500.0, "fallback (B200_PROFILING.md)"
 
 
+def effective_cpus() -> int:
+    """Host threads this process may really use: the affinity mask capped by the cgroup CPU quota (a 128-way OpenMP team on an
+    8-CPU cgroup runs slower than one thread)."""
+    n = len(os.sched_getaffinity(0))
+    quota = None
+    try:
+        txt = Path("/sys/fs/cgroup/cpu.max").read_text().split()
+        if txt[0] != "max":
+            quota = float(txt[0]) / float(txt[1])
+    except Exception:
+        try:
+            q = float(Path("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read_text())
+            per = float(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            quota = None
+    if quota:
+        n = min(n, max(1, int(quota + 0.999)))
+    return max(1, min(n, 64))
+
+
 def cpu_baseline(model_dir: Path, threads: int, tokens: int, prompt_len: int = 4):
     """Decode `tokens` tokens with the CPU oracle; returns (tokens/s, description)."""
     from oracle.model import OracleModel
@@ -183,19 +212,59 @@ def cpu_baseline(model_dir: Path, threads: int, tokens: int, prompt_len: int = 4
     tok = 1                         # any valid token id; the arithmetic per token does not depend on it
     t0 = time.perf_counter()
     for _ in range(tokens):
-        logits = m.forward([tok])
+        m.forward([tok])
     dt = time.perf_counter() - t0
     return tokens / dt, f"{tokens} decode tokens of the full model at context ~{prompt_len + tokens} (prompt {prompt_len} tokens untimed)"
 
 
+def bf16_to_f32(a):
+    return (np.asarray(a, np.uint16).astype(np.uint32) << 16).view(np.float32)
+
+
+def parity_check(eng, model_dir: Path, threads: int, prompt_len: int = 6, steps: int = 3, budget_s: float = 90.0):
+    """The timed engine against the CPU oracle on the same checkpoint: a short prompt, then `steps` decode steps under teacher forcing
+    (oracle tokens fed to both). Reports greedy token ids (GPU vs oracle) and the last-row logit error. Bounded: gives up after budget_s."""
+    from oracle.model import OracleModel
+    t0 = time.perf_counter()
+    ref = OracleModel(model_dir, threads=threads, max_context=64)
+    rng = np.random.default_rng(1)
+    prompt = rng.integers(0, ref.V, prompt_len).astype(np.uint32)
+    lr = ref.prefill(prompt)
+    eng.reset()
+    first = eng.prefill(prompt)
+    want = int(np.argmax(bf16_to_f32(lr[0])))
+    ids_gpu, ids_ref, worst, gaps = [int(first)], [want], 0.0, []
+    tok = want
+    done = 0
+    for _ in range(steps):
+        if time.perf_counter() - t0 > budget_s:
+            break
+        lr = ref.forward([tok])
+        got = eng.step_host(tok)
+        lg = eng.last_logits()
+        r, g = bf16_to_f32(lr[0]), bf16_to_f32(lg[0])
+        scale = float(np.abs(r).max())
+        worst = max(worst, float(np.abs(g - r).max()) / max(scale, 1e-30))
+        top = np.sort(r)[::-1]
+        gaps.append(float((top[0] - top[1]) / max(abs(top[0]), 1e-30)))
+        tok = int(np.argmax(r))
+        ids_gpu.append(int(got)); ids_ref.append(tok)
+        done += 1
+    eng.reset()
+    return {"prompt_tokens": prompt_len, "decode_steps_checked": done, "token_ids_gpu": ids_gpu, "token_ids_oracle": ids_ref,
+            "token_ids_equal": ids_gpu == ids_ref, "max_logit_err_over_range": worst, "top2_gap_over_range": gaps,
+            "persistent_kernel": bool(eng.persistent_decode), "seconds": time.perf_counter() - t0,
+            "note": "teacher-forced with the oracle's tokens; logits are bf16, error is max|gpu - oracle| / max|oracle| over the vocabulary"}
+
+
 def run_reference(args, rank: int):
-    """--impl reference: the reference's CPU path (C restatement; no Rust toolchain here) on all host threads."""
+    """--impl reference: the reference's CPU path (C restatement; no Rust toolchain here) on the host threads this process may use."""
     if rank != 0:
         return
-    from oracle import oracle as O
     workload = args.workload
+    _, _, prefill_default, decode_default = WORKLOADS[workload]
     mdir = model_dir_for(workload)
-    threads = O.lib().oracle_max_threads()
+    threads = effective_cpus()
     from oracle.model import OracleModel
     m = OracleModel(mdir, threads=threads, max_context=256)
     rng = np.random.default_rng(0)
@@ -205,10 +274,10 @@ def run_reference(args, rank: int):
     t_probe0 = time.perf_counter()
     m.forward([tok])
     t_tok = time.perf_counter() - t_probe0
-    budget = 150.0
+    budget = 120.0
     total = args.warmup + args.steps
-    timed = args.steps if total * t_tok <= budget else max(1, int(budget / t_tok) - args.warmup)
-    warm = args.warmup if total * t_tok <= budget else max(0, min(args.warmup, 1))
+    timed = args.steps if total * t_tok <= budget else max(1, int(budget / t_tok) - 1)
+    warm = args.warmup if total * t_tok <= budget else 1
     for _ in range(warm):
         m.forward([tok])
     t0 = time.perf_counter()
@@ -216,18 +285,142 @@ def run_reference(args, rank: int):
         m.forward([tok])
     dt = time.perf_counter() - t0
     value = timed / dt
-    sample = f"{timed} of {args.steps} decode steps timed (bounded to ~{budget:.0f}s of CPU work), context ~{4 + warm + timed}, prompt 4 tokens"
+    sample = (f"{timed} of {args.steps} decode steps timed (bounded to ~{budget:.0f}s of CPU work) at context ~{5 + warm + timed} after a 4-token prompt: "
+              f"the CPU path cannot prefill {args.prefill or prefill_default} tokens of this model in minutes; per-token arithmetic over the weights is "
+              f"context-independent, only the (small) attention term is shorter than in the GPU arm")
     line = {
-        "impl": "reference", "metric": "decode tokens/sec/GPU (int4)", "value": value, "unit": "tokens/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(workload), "value": value, "unit": "tokens/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16 activations x int4 weights, f32 accumulate", "data": "synthetic",
-        "config": {"workload": workload, "note": "reference CPU backend arithmetic restated in C (oracle/uzu_oracle.c); the Rust reference "
-                   "cannot be built here (no rustc/cargo). OpenMP over output columns = not the reference's single-thread execution model."},
+        "vs_baseline": None, "dtype": dtype_name(workload), "data": "synthetic",
+        "config": {"workload": workload_name(workload, args.prefill or prefill_default, args.steps, 1),
+                   "note": "reference CPU backend arithmetic restated in C (oracle/uzu_oracle.c); the Rust reference cannot be built here "
+                           "(no rustc/cargo). OpenMP over output columns = not the reference's single-thread execution model."},
         "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def metric_name(workload: str) -> str:
+    return "decode tokens/sec (int4), summed over the N GPUs" if "int4" in workload else "decode tokens/sec (int8), summed over the N GPUs"
+
+
+def dtype_name(workload: str) -> str:
+    return "bf16 activations x int4 weights, f32 accumulate" if "int4" in workload else "bf16 activations x int8 weights, f32 accumulate"
+
+
+def workload_name(workload: str, prefill: int, decode: int, batch: int) -> str:
+    return f"{workload}: prefill {prefill}, decode {decode}, batch {batch}, greedy"
+
+
+def tp_setup(ctx, dist, rank: int, world: int, full_dir: Path, p2p: bool):
+    """One tensor-parallel group over all ranks: rank 0's NCCL unique id travels over torch.distributed; every rank loads its shard."""
+    import torch
+    from uzu_b200 import binding as B
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.tensor(list(B.tp_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    ctx.tp_init(rank, world, bytes(idt.cpu().tolist()))
+    sdir = shard_dir_for(full_dir, rank, world)
+    if p2p:
+        model_dim = json.loads((sdir / "config.json").read_text())["decoder_config"]["transformer_config"]["model_dim"]
+        mine = torch.tensor(list(ctx.tp_p2p_export(16 * model_dim)), dtype=torch.uint8, device="cuda")
+        allh = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        ctx.tp_p2p_import([bytes(h.cpu().tolist()) for h in allh])
+        dist.barrier()
+    return sdir
+
+
+def measure_decode(eng, dist, world: int, replicas: int, local_rank: int, prompt, K: int, W: int):
+    """Device-resident value, end-to-end value and launches of K decode steps after `prompt`; max over ranks."""
+    t0 = time.perf_counter()
+    first = eng.prefill(prompt)
+    prefill_s = time.perf_counter() - t0
+    eng.snapshot()
+    eng.decode_timed(max(W, 3))
+    eng.restore()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if dist:
+        import torch
+        dist.barrier()
+        torch.cuda.synchronize()
+    launches0 = eng.launch_count
+    seconds = eng.decode_timed(K)
+    launches = eng.launch_count - launches0
+    if dist:
+        import torch
+        torch.cuda.synchronize()
+        seconds = max_over_ranks(dist, seconds, "cuda")
+        dist.barrier()
+    clocks = sampler.stop()
+    # ---- end to end through host buffers: H2D of the input token, the step, D2H of the sampled token, every step ----
+    eng.restore()
+    tok = first
+    for _ in range(max(W, 3)):
+        tok = eng.step_host(tok)
+    eng.restore()
+    tok = first
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        tok = eng.step_host(tok)
+    e2e_s = max_over_ranks(dist, time.perf_counter() - t0, "cuda")
+    eng.restore()
+    return {"seconds": seconds, "launches": int(launches), "clocks": clocks, "prefill_s": prefill_s, "e2e_seconds": e2e_s,
+            "value": whole_job_value(replicas, K, seconds), "e2e_value": whole_job_value(replicas, K, e2e_s)}
+
+
+def roofline_of(eng, workload: str, prefill: int, K: int, seconds: float):
+    """Dominant kernel of a decode step. Persistent mode: the step IS one kernel (decode_mega_kernel): algorithmic bytes per launch =
+    quantised weights + KV rows read at the mid context + recurrent state read/write; duration = the CUDA-event time of the K launches / K.
+    Per-kernel mode: all fused dequant+GEMV launches of one token replayed back to back."""
+    info = eng.info
+    peak, peak_src = hbm_peak()
+    traffic = None
+    tfile = ROOT / "profiles" / "roofline_traffic.json"
+    if tfile.exists():
+        try:
+            traffic = json.loads(tfile.read_text()).get(workload)
+        except Exception:
+            traffic = None
+    ctx_mid = prefill + K / 2
+    step_bytes = info.weight_bytes_per_token + info.kv_bytes_per_token_per_ctx * ctx_mid + info.state_bytes_per_token
+    if eng.persistent_decode:
+        achieved = step_bytes / (seconds / K) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "decode_mega_kernel (persistent whole-token kernel: every linear + attention + state update + argmax of one token in ONE launch)",
+                "algorithmic_bytes_per_launch": int(step_bytes), "launch_us": 1e6 * seconds / K, "peak_source": peak_src}
+        extra = {"gemv_launches_per_token": 0, "gemv_ms_per_token": None}
+    else:
+        iters = 10
+        lin_s, lin_launches = eng.time_linears(iters)
+        per_tok = lin_s / iters
+        achieved = info.weight_bytes_per_token / per_tok / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "qmv_decode_async_kernel (fused dequant + GEMV, all linears + readout of one token replayed back to back)",
+                "algorithmic_bytes_per_launch": int(info.weight_bytes_per_token // max(1, lin_launches // iters)), "peak_source": peak_src}
+        extra = {"gemv_launches_per_token": lin_launches // iters, "gemv_ms_per_token": 1000.0 * per_tok}
+    extra["whole_step_hbm_frac"] = step_bytes * (K / seconds) / 1e9 / peak
+    return roof, extra
+
+
+def prefill_gemm_of(eng, prefill: int):
+    try:
+        pm = min(prefill, 1024)
+        if pm < 64:
+            return None
+        p_s, p_flops = eng.time_prefill_linears(pm, 3)
+        tpeak, tsrc = tensor_peak()
+        return {"rows": pm, "ms_per_pass": 1000.0 * p_s, "useful_tflops": p_flops / p_s / 1e12, "peak_tflops": tpeak,
+                "frac": p_flops / p_s / 1e12 / tpeak, "peak_source": tsrc,
+                "note": "useful flops = 2*m*N*K; the kernel issues 2x that (exact hi/lo bf16 weight planes)"}
+    except Exception as ex:  # must not take the decode measurement down
+        return {"error": str(ex)[:200]}
 
 
 def run_ours(args, rank: int, world: int, local_rank: int):
@@ -247,32 +440,20 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     _, _, prefill_default, decode_default = WORKLOADS[workload]
     prefill = args.prefill or prefill_default
     K, W = args.steps or decode_default, args.warmup
-    mdir = model_dir_for(workload)
+    full_dir = model_dir_for(workload)
     max_ctx = max(1024, prefill + K + W + 64)
 
     ctx = B.Context(local_rank)
     tp = args.tp if args.tp > 1 else 1
+    mdir = full_dir
     if tp > 1:
-        # one tensor-parallel group over all ranks: rank 0's NCCL unique id travels over torch.distributed, every rank loads its shard
         if world != tp:
             raise SystemExit(f"--tp {tp} needs exactly {tp} ranks (torchrun --nproc-per-node {tp}); got WORLD_SIZE={world}")
-        import torch
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.tensor(list(B.tp_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        ctx.tp_init(rank, world, bytes(idt.cpu().tolist()))
-        mdir = shard_dir_for(mdir, rank, world)
-        if os.environ.get("UZU_TP_P2P"):
-            # opt-in: decode-sized all-reduces through the one-kernel peer-memory exchange (CUDA IPC handles travel over torch.distributed)
-            model_dim = json.loads((mdir / "config.json").read_text())["decoder_config"]["transformer_config"]["model_dim"]
-            mine = torch.tensor(list(ctx.tp_p2p_export(16 * model_dim)), dtype=torch.uint8, device="cuda")
-            allh = [torch.zeros_like(mine) for _ in range(world)]
-            dist.all_gather(allh, mine)
-            ctx.tp_p2p_import([bytes(h.cpu().tolist()) for h in allh])
-            dist.barrier()
+        mdir = tp_setup(ctx, dist, rank, world, full_dir, bool(os.environ.get("UZU_TP_P2P")))
     eng = B.Engine(ctx, mdir, max_context_length=max_ctx, use_cuda_graph=not args.no_graph, fused_decode=not args.no_fused,
                    tp_rank=rank if tp > 1 else 0, tp_size=tp)
+    if args.no_persistent and eng.persistent_decode:
+        eng.set_persistent_decode(False)
     replicas = 1 if tp > 1 else world
     if args.batch > 1:
         run_batched(args, eng, ctx, dist, rank, world, local_rank, workload, prefill, K, W)
@@ -280,111 +461,116 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     info = eng.info
     rng = np.random.default_rng(0)
     prompt = rng.integers(0, info.vocab_size, prefill).astype(np.uint32)
-
-    t0 = time.perf_counter()
-    first = eng.prefill(prompt)
-    prefill_s = time.perf_counter() - t0
-    eng.snapshot()
-
-    # ---- device-resident decode (value) ----
-    eng.decode_timed(max(W, 3))
-    eng.restore()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    if dist:
-        import torch
-        dist.barrier()
-        torch.cuda.synchronize()
-    launches0 = eng.launch_count
-    seconds = eng.decode_timed(K)
-    launches = eng.launch_count - launches0
-    if dist:
-        import torch
-        torch.cuda.synchronize()
-        seconds = max_over_ranks(dist, seconds, "cuda")
-        dist.barrier()
-    clocks = sampler.stop()
-    value = whole_job_value(replicas, K, seconds)
-
-    # ---- end to end through host buffers ----
-    eng.restore()
-    tok = first
-    for _ in range(max(W, 3)):
-        tok = eng.step_host(tok)
-    eng.restore()
-    tok = first
-    if dist:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        tok = eng.step_host(tok)
-    e2e_s = time.perf_counter() - t0
-    e2e_s = max_over_ranks(dist, e2e_s, "cuda")
-    e2e_value = whole_job_value(replicas, K, e2e_s)
-
-    # ---- roofline of the dominant kernel (fused dequant + GEMV) ----
-    iters = 10
-    lin_s, lin_launches = eng.time_linears(iters)
-    gemv_s_per_token = lin_s / iters
-    peak, peak_src = hbm_peak()
-    achieved = info.weight_bytes_per_token / gemv_s_per_token / 1e9
-    traffic = None
-    tfile = ROOT / "profiles" / "roofline_traffic.json"
-    if tfile.exists():
-        try:
-            traffic = json.loads(tfile.read_text()).get(workload)
-        except Exception:
-            traffic = None
-    # ---- prefill GEMM (tcgen05 tensor cores, in-kernel dequant): every linear of one prefill pass, useful TFLOP/s ----
-    prefill_gemm = None
-    try:
-        pm = min(prefill, 1024)
-        if pm >= 64:
-            p_s, p_flops = eng.time_prefill_linears(pm, 3)
-            tpeak, tsrc = tensor_peak()
-            prefill_gemm = {"rows": pm, "ms_per_pass": 1000.0 * p_s, "useful_tflops": p_flops / p_s / 1e12, "peak_tflops": tpeak,
-                            "frac": p_flops / p_s / 1e12 / tpeak, "peak_source": tsrc,
-                            "note": "useful flops = 2*m*N*K; the kernel issues 2x that (exact hi/lo bf16 weight planes)"}
-    except Exception as ex:  # must not take the decode measurement down
-        prefill_gemm = {"error": str(ex)[:200]}
+    m = measure_decode(eng, dist, world, replicas, local_rank, prompt, K, W)
+    roof, extra = roofline_of(eng, workload, prefill, K, m["seconds"])
     ctx_mid = prefill + K / 2
-    bytes_per_token = info.weight_bytes_per_token + info.kv_bytes_per_token_per_ctx * ctx_mid + info.state_bytes_per_token
-
     line = {
-        "metric": "decode tokens/sec/GPU (int4)" if "int4" in workload else "decode tokens/sec/GPU",
-        "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1000.0 * seconds / K,
-        "higher_is_better": True, "scaling": "strong" if tp > 1 else "weak", "vs_baseline": None,
-        "dtype": "bf16 activations x int4 weights, f32 accumulate" if "int4" in workload else "bf16 activations x int8 weights, f32 accumulate",
-        "data": "synthetic",
+        "metric": metric_name(workload), "value": m["value"], "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": 1000.0 * m["seconds"] / K, "higher_is_better": True, "scaling": "strong" if tp > 1 else "weak", "vs_baseline": None,
+        "dtype": dtype_name(workload), "data": "synthetic",
         "config": {
-            "workload": f"{workload}: prefill {prefill}, decode {K}, batch 1, greedy", "parallelism": f"tp{tp}" if tp > 1 else ("replicas" if world > 1 else "single"),
+            "workload": workload_name(workload, prefill, K, 1), "parallelism": f"tp{tp}" if tp > 1 else ("replicas" if world > 1 else "single"),
+            "per_gpu_value": m["value"] / world,
             "layers": info.num_layers, "attention_layers": info.num_attention_layers, "delta_net_layers": info.num_delta_net_layers,
             "model_dim": info.model_dim, "vocab": info.vocab_size, "weight_bytes_per_token": info.weight_bytes_per_token,
             "kv_bytes_per_token_at_mid_ctx": int(info.kv_bytes_per_token_per_ctx * ctx_mid), "state_bytes_per_token": info.state_bytes_per_token,
             "cache_policy": f"inputs larger than L2: {info.weight_bytes_per_token / 1e6:.0f} MB of weights streamed every step vs 126 MB L2",
-            "cuda_graph": not args.no_graph, "fused_decode": not args.no_fused, "prefill_tokens_per_s": prefill / prefill_s,
-            "whole_step_hbm_frac": bytes_per_token * (K / seconds) / 1e9 / peak,
-            "gemv_launches_per_token": lin_launches // iters, "gemv_ms_per_token": 1000.0 * gemv_s_per_token,
-            "prefill_gemm": prefill_gemm,
+            "decode_path": "persistent kernel (1 launch per token)" if eng.persistent_decode else
+                           f"per-kernel path ({'CUDA graph' if not args.no_graph else 'eager'}): {eng.persistent_decode_reason or 'persistent kernel disabled'}",
+            "cuda_graph": not args.no_graph, "fused_decode": not args.no_fused, "prefill_tokens_per_s": prefill / m["prefill_s"],
+            "prefill_gemm": prefill_gemm_of(eng, prefill), **extra,
         },
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "qmv_kernel (fused int4 dequant + GEMV, all linears + readout of one token)", "peak_source": peak_src},
-        "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
+        "roofline": roof,
+        "e2e": {"value": m["e2e_value"], "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 4},
+        "gpu_launches": m["launches"],
+        "clocks": m["clocks"],
     }
+    threads = effective_cpus()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            v, sample = cpu_baseline(mdir, threads=1, tokens=3 if workload.startswith("qwen") else 1)
+            v, sample = cpu_baseline(full_dir, threads=1, tokens=3 if workload.startswith("qwen") else 1)
             line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": 1, "kind": "port", "sample": sample}
         except Exception as ex:  # the baseline must not take the measurement down
             line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": 1, "kind": "port", "sample": f"failed: {ex}"}
+        try:
+            line["parity"] = parity_check(eng, full_dir, threads)
+        except Exception as ex:
+            line["parity"] = {"error": str(ex)[:300]}
     eng.close()
+    # ---- secondary line (N = 1): BASELINE.json configs[1], Qwen3.5-0.8B int4 prefill 512 / decode 128 ----
+    if world == 1 and tp == 1 and not args.no_secondary and workload != SECONDARY:
+        try:
+            line["config"]["secondary"] = secondary_line(B, ctx, args, local_rank)
+        except Exception as ex:
+            line["config"]["secondary"] = {"error": str(ex)[:300]}
+    # ---- tensor-parallel sub-measurement (N >= 2): the same model sharded over the N ranks ----
+    if world > 1 and tp == 1 and not args.no_tp_sub:
+        sub = {}
+        for mode in ("nccl", "p2p"):
+            try:
+                sub[mode] = tp_line(B, dist, args, rank, world, local_rank, full_dir, workload, prefill, max_ctx, mode == "p2p")
+            except Exception as ex:
+                sub[mode] = {"error": str(ex)[:300]}
+        if rank == 0:
+            line["config"]["tp"] = sub
     ctx.close()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()
+
+
+SECONDARY = "qwen3.5-0.8b-int4"
+
+
+def secondary_line(B, ctx, args, local_rank: int):
+    _, _, prefill, K = WORKLOADS[SECONDARY]
+    mdir = model_dir_for(SECONDARY)
+    eng = B.Engine(ctx, mdir, max_context_length=max(1024, prefill + K + 96), use_cuda_graph=not args.no_graph, fused_decode=not args.no_fused)
+    try:
+        if args.no_persistent and eng.persistent_decode:
+            eng.set_persistent_decode(False)
+        rng = np.random.default_rng(0)
+        prompt = rng.integers(0, eng.info.vocab_size, prefill).astype(np.uint32)
+        m = measure_decode(eng, None, 1, 1, local_rank, prompt, K, max(args.warmup, 3))
+        roof, extra = roofline_of(eng, SECONDARY, prefill, K, m["seconds"])
+        out = {"workload": workload_name(SECONDARY, prefill, K, 1), "value": m["value"], "unit": "tokens/s", "ms_per_step": 1000.0 * m["seconds"] / K,
+               "e2e": m["e2e_value"], "gpu_launches": m["launches"], "roofline": roof, "prefill_tokens_per_s": prefill / m["prefill_s"],
+               "decode_path": "persistent kernel (1 launch per token)" if eng.persistent_decode else "per-kernel path", **extra}
+        if not args.no_cpu_baseline:
+            try:
+                out["parity"] = parity_check(eng, mdir, effective_cpus())
+            except Exception as ex:
+                out["parity"] = {"error": str(ex)[:300]}
+        return out
+    finally:
+        eng.close()
+
+
+def tp_line(B, dist, args, rank: int, world: int, local_rank: int, full_dir: Path, workload: str, prefill: int, max_ctx: int, p2p: bool):
+    """ONE model sharded by attention head / FFN column / vocabulary row over all ranks; two all-reduces per layer + one all-gather."""
+    ctx = B.Context(local_rank)
+    try:
+        sdir = tp_setup(ctx, dist, rank, world, full_dir, p2p)
+        eng = B.Engine(ctx, sdir, max_context_length=max_ctx, use_cuda_graph=not args.no_graph, fused_decode=not args.no_fused, tp_rank=rank, tp_size=world)
+        try:
+            K = min(args.steps or 64, 64)
+            rng = np.random.default_rng(0)
+            prompt = rng.integers(0, eng.info.vocab_size, prefill).astype(np.uint32)
+            eng.prefill(prompt)
+            eng.snapshot()
+            eng.decode_timed(3)
+            eng.restore()
+            dist.barrier()
+            seconds = max_over_ranks(dist, eng.decode_timed(K), "cuda")
+            layers = eng.info.num_layers
+            return {"tokens_per_s": K / seconds, "ms_per_step": 1000.0 * seconds / K, "steps": K, "exchange": "one-kernel peer-memory all-reduce (CUDA IPC over NVLink)" if p2p else "ncclAllReduce",
+                    "collectives_per_step": 2 * layers + 1, "comm_nranks": world,
+                    "limiting_collective": f"{2 * layers} latency-bound all-reduces of [1, model_dim] f32 per step (2 per layer) + 1 all-gather of the logits"}
+        finally:
+            eng.close()
+    finally:
+        ctx.close()
 
 
 def run_batched(args, eng, ctx, dist, rank, world, local_rank, workload, prefill, K, W):
@@ -419,13 +605,13 @@ def run_batched(args, eng, ctx, dist, rank, world, local_rank, workload, prefill
     e2e_s = max_over_ranks(dist, time.perf_counter() - t0, "cuda")
     peak, peak_src = hbm_peak()
     line = {
-        "metric": "decode tokens/sec/GPU (int4)" if "int4" in workload else "decode tokens/sec/GPU",
+        "metric": metric_name(workload),
         "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1000.0 * seconds / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16 activations x int4 weights, f32 accumulate" if "int4" in workload else "bf16 activations x int8 weights, f32 accumulate",
+        "dtype": dtype_name(workload),
         "data": "synthetic",
         "config": {"workload": f"{workload}: prefill {prefill}, decode {K}, batch {nseq} (independent sequences, one weight pass per step), greedy",
-                   "parallelism": "replicas" if world > 1 else "single", "batch": nseq, "weight_bytes_per_token": info.weight_bytes_per_token,
+                   "parallelism": "replicas" if world > 1 else "single", "batch": nseq, "per_gpu_value": value / world, "weight_bytes_per_token": info.weight_bytes_per_token,
                    "cache_policy": f"inputs larger than L2: {info.weight_bytes_per_token / 1e6:.0f} MB of weights streamed every step vs 126 MB L2",
                    "cuda_graph": False},
         "roofline": {"bound": "hbm", "achieved": info.weight_bytes_per_token * (K / seconds) / 1e9, "peak": peak, "unit": "GB/s",
@@ -448,7 +634,10 @@ def main():
     ap.add_argument("--steps", type=int, default=0, help="timed decode steps (default: the workload's decode length)")
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", default="qwen3.5-0.8b-int4", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="llama3-8b-int4", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-secondary", action="store_true", help="skip the Qwen3.5-0.8B int4 line (BASELINE configs[1]) that the default N = 1 run adds under config.secondary")
+    ap.add_argument("--no-tp-sub", action="store_true", help="N >= 2: skip the tensor-parallel sub-measurement reported under config.tp")
+    ap.add_argument("--no-persistent", action="store_true", help="use the per-kernel decode path instead of the persistent whole-token kernel (A/B)")
     ap.add_argument("--prefill", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--fused", action="store_true", help="(default) fold norm / gated-act / sigmoid-gate launches into the neighbouring GEMV")

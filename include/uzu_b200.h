@@ -499,6 +499,14 @@ UZU_API uint64_t uzu_engine_launch_count(const uzu_engine* e);   /* kernels laun
  *                `iters` times between two events; returns seconds and the number of kernel launches. */
 UZU_API uzu_status uzu_engine_decode_timed(uzu_engine* e, uint32_t steps, double* out_seconds);
 UZU_API uzu_status uzu_engine_step_host(uzu_engine* e, uint32_t token_in, uint32_t* token_out);
+/* Persistent decode kernel (extension; uzu_b200/csrc/decode_mega.cu): when the model is covered (uniform int4 / int8 block quantisation,
+ * greedy sampling, one GPU) a decode step is ONE cooperative launch that runs the whole per-token pass (stream.rs:363-782) with the weight
+ * stream fed by TMA bulk copies across phase boundaries. decode_mode: 1 = persistent kernel, 0 = per-kernel path (reason says why).
+ * set_decode_mode(0) forces the per-kernel path (A/B runs, parity tests); last_logits copies the [vocab] bf16 logits of the latest step. */
+UZU_API int uzu_engine_decode_mode(const uzu_engine* e);
+UZU_API const char* uzu_engine_decode_mode_reason(const uzu_engine* e);
+UZU_API uzu_status uzu_engine_set_decode_mode(uzu_engine* e, int persistent);
+UZU_API uzu_status uzu_engine_last_logits(uzu_engine* e, uint16_t* out_logits);
 UZU_API uzu_status uzu_engine_time_linears(uzu_engine* e, uint32_t iters, double* out_seconds, uint64_t* out_launches);
 /*  time_prefill_linears: every linear of one PREFILL pass over m rows (all layers, no readout) back to back; returns seconds per pass
  *                and the useful flops of one pass (2*m*N*K summed): the tensor-core GEMM's achieved TFLOP/s = flops / seconds. */

@@ -1,0 +1,107 @@
+"""Persistent whole-token decode kernel (uzu_b200/csrc/decode_mega.cu) against the CPU oracle model and against the per-kernel decode
+path of the same engine: one cooperative launch per token must be the same function as the reference's op sequence
+(encodable_block/{decoder.rs:138-203, transformer.rs:226-329, transformer_layer.rs:194-238}) on the same synthetic checkpoint."""
+import numpy as np
+import pytest
+
+from oracle.model import OracleModel
+from tests.test_engine_gpu import _logit_check
+from tests.util import bf16_to_f32
+from uzu_b200 import binding as B
+from uzu_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("llama", None), ("llama-512", None), ("qwen-dense", None), ("qwen-hybrid", None), ("qwen-hybrid-512", None),
+         ("llama", synth.QuantSpec("int", 8, 64, False)), ("qwen-dense", synth.QuantSpec("int", 4, 128, True)),
+         ("llama-512", synth.QuantSpec("mlx", 4, 64)), ("llama", synth.QuantSpec("int", 4, 64, True))]
+
+
+@pytest.mark.parametrize("kind,quant", CASES)
+def test_persistent_decode_matches_oracle_and_per_kernel_path(ctx, tmp_path, kind, quant):
+    spec = synth.tiny(kind, quant=quant)
+    path = synth.write_model(spec, tmp_path / "m", seed=31)
+    rng = np.random.default_rng(3)
+    prompt = rng.integers(0, spec.vocab_size, 19)
+    ref = OracleModel(path, max_context=128)
+    lr = ref.prefill(prompt)
+    with B.Engine(ctx, path, max_context_length=128, use_cuda_graph=True) as eng:
+        assert eng.persistent_decode, f"persistent decode kernel does not cover {kind}: {eng.persistent_decode_reason}"
+        eng.prefill(prompt)
+        eng.snapshot()
+        tok = int(np.argmax(bf16_to_f32(lr[0])))
+        toks, mega_logits, mega_out = [], [], []
+        launches0 = eng.launch_count
+        for step in range(7):
+            lr = ref.forward([tok])
+            got = eng.step_host(tok)
+            lg = eng.last_logits()
+            _logit_check(lg, lr, f"{kind} persistent decode step {step}")
+            # greedy token id == argmax of the kernel's own logits, lowest index on ties (unified_sampling.rs:34-98, no filters)
+            f = bf16_to_f32(lg[0])
+            assert got == int(np.flatnonzero(f == f.max())[0]), (step, got)
+            toks.append(tok); mega_logits.append(lg.copy()); mega_out.append(got)
+            tok = int(np.argmax(bf16_to_f32(lr[0])))
+        assert eng.launch_count - launches0 == 7, "one launch per decoded token"
+        assert eng.context_length == ref.context_length
+        # the per-kernel path on the same engine / same state: logits agree to bf16 rounding noise, greedy ids identical unless a near-tie
+        eng.restore()
+        eng.set_persistent_decode(False)
+        assert not eng.persistent_decode
+        for step, t in enumerate(toks):
+            got = eng.step_host(t)
+            lg = eng.last_logits()
+            a, b = bf16_to_f32(lg[0]), bf16_to_f32(mega_logits[step][0])
+            scale = float(np.abs(a).max())
+            assert float(np.abs(a - b).max()) <= 0.02 * scale + 1e-3, f"{kind} step {step}: persistent vs per-kernel logits"
+            top = np.sort(a)[::-1]
+            if top[0] - top[1] > 0.05 * abs(top[0]):
+                assert got == mega_out[step], (step, got, mega_out[step])
+        eng.set_persistent_decode(True)
+        assert eng.persistent_decode
+
+
+def test_persistent_decode_device_chained_generation(ctx, tmp_path):
+    """Device-chained greedy generation (next()/flush(), decode_timed) through the persistent kernel == token-by-token host stepping."""
+    spec = synth.tiny("qwen-hybrid-512")
+    path = synth.write_model(spec, tmp_path / "m", seed=32)
+    prompt = (np.arange(40) * 53) % spec.vocab_size
+    with B.Engine(ctx, path, max_context_length=256) as eng:
+        assert eng.persistent_decode, eng.persistent_decode_reason
+        a = eng.generate(prompt, 24)
+        eng.reset()
+        first = eng.prefill(prompt)
+        b = [first]
+        for _ in range(23):
+            b.append(eng.step_host(b[-1]))
+        assert a == b
+        eng.reset()
+        eng.set_persistent_decode(False)
+        c = eng.generate(prompt, 24)
+        # identical unless a near-tie flips one argmax: require a long common prefix
+        common = next((i for i, (x, y) in enumerate(zip(a, c)) if x != y), len(a))
+        assert common >= 8, (a, c)
+        eng.set_persistent_decode(True)
+        eng.reset()
+        eng.prefill(prompt)
+        assert eng.decode_timed(16) > 0.0
+        assert eng.context_length == len(prompt) + 16
+
+
+def test_persistent_decode_long_context(ctx, tmp_path):
+    """Attention over a few hundred cached keys (several CTA parts per kv head, in-kernel merge) against the oracle."""
+    spec = synth.tiny("llama-512")
+    path = synth.write_model(spec, tmp_path / "m", seed=33)
+    rng = np.random.default_rng(4)
+    prompt = rng.integers(0, spec.vocab_size, 700)
+    ref = OracleModel(path, max_context=1024)
+    lr = ref.prefill(prompt)
+    with B.Engine(ctx, path, max_context_length=1024) as eng:
+        assert eng.persistent_decode, eng.persistent_decode_reason
+        eng.prefill(prompt)
+        tok = int(np.argmax(bf16_to_f32(lr[0])))
+        for step in range(3):
+            lr = ref.forward([tok])
+            eng.step_host(tok)
+            _logit_check(eng.last_logits(), lr, f"long-context persistent decode step {step}")
+            tok = int(np.argmax(bf16_to_f32(lr[0])))

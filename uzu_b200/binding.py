@@ -149,7 +149,8 @@ uzu_engine_snapshot uzu_engine_restore uzu_engine_prefill uzu_engine_next uzu_en
 uzu_engine_forward uzu_engine_batch_begin uzu_engine_batch_prefill uzu_engine_batch_step uzu_engine_batch_decode_timed
 uzu_engine_batch_logits uzu_engine_batch_context_length uzu_engine_launch_count uzu_engine_decode_timed uzu_engine_step_host
 uzu_delta_net_fused_update_supported uzu_delta_net_fused_update_encode uzu_engine_time_linears uzu_engine_time_prefill_linears uzu_engine_time_linears_select uzu_debug_set_qmv_tuning uzu_debug_set_delta_prefill uzu_debug_set_prefill_attention uzu_debug_set_umma uzu_tp_get_unique_id uzu_context_tp_init uzu_context_tp_destroy uzu_context_tp_size
-uzu_context_tp_rank uzu_tp_p2p_export uzu_tp_p2p_import uzu_tp_all_reduce_encode uzu_tp_all_gather_encode uzu_fused_linear_supported uzu_fused_linear_encode""".split()
+uzu_context_tp_rank uzu_tp_p2p_export uzu_tp_p2p_import uzu_tp_all_reduce_encode uzu_tp_all_gather_encode uzu_fused_linear_supported uzu_fused_linear_encode
+uzu_engine_decode_mode uzu_engine_decode_mode_reason uzu_engine_set_decode_mode uzu_engine_last_logits""".split()
 
 _lib = None
 
@@ -253,6 +254,10 @@ def load() -> C.CDLL:
         "uzu_engine_batch_context_length": (u32, [vp, u32]),
         "uzu_engine_decode_timed": (C.c_int, [vp, u32, C.POINTER(C.c_double)]),
         "uzu_engine_step_host": (C.c_int, [vp, u32, C.POINTER(u32)]),
+        "uzu_engine_decode_mode": (C.c_int, [vp]),
+        "uzu_engine_decode_mode_reason": (C.c_char_p, [vp]),
+        "uzu_engine_set_decode_mode": (C.c_int, [vp, C.c_int]),
+        "uzu_engine_last_logits": (C.c_int, [vp, C.POINTER(C.c_uint16)]),
         "uzu_engine_time_linears": (C.c_int, [vp, u32, C.POINTER(C.c_double), C.POINTER(u64)]),
         "uzu_engine_time_prefill_linears": (C.c_int, [vp, u32, u32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "uzu_engine_time_linears_select": (C.c_int, [vp, u32, u32, C.POINTER(C.c_double), C.POINTER(u64)]),
@@ -523,6 +528,23 @@ class Engine:
         out = u32()
         _check(self.lib.uzu_engine_step_host(self.h, int(token), C.byref(out)))
         return out.value
+
+    # ---- persistent decode kernel (extension, see include/uzu_b200.h) ----
+    @property
+    def persistent_decode(self) -> bool:
+        return bool(self.lib.uzu_engine_decode_mode(self.h))
+
+    @property
+    def persistent_decode_reason(self) -> str:
+        return (self.lib.uzu_engine_decode_mode_reason(self.h) or b"").decode(errors="replace")
+
+    def set_persistent_decode(self, on: bool):
+        _check(self.lib.uzu_engine_set_decode_mode(self.h, int(on)))
+
+    def last_logits(self) -> np.ndarray:
+        out = np.zeros((1, self.info.vocab_size), dtype=np.uint16)
+        _check(self.lib.uzu_engine_last_logits(self.h, out.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return out
 
     # ---- multi-sequence batched decode (extension, see include/uzu_b200.h) ----
     def batch_begin(self, sequences: int):

@@ -35,6 +35,7 @@ SOURCES = {
     "sampling.cu": ["-fmad=false"],
     "deltanet.cu": ["-fmad=false"],
     "deltanet_prefill.cu": ["-fmad=false"],
+    "decode_mega.cu": [],
     "engine.cu": [],
 }
 

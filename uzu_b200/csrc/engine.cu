@@ -34,6 +34,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "decode_mega.cuh"
 
 namespace uzu {
 
@@ -418,6 +419,15 @@ struct uzu_engine {
     bool use_pdl = true;   // programmatic dependent launch between the kernels of a decode step (UZU_NO_PDL=1 disables)
     uint64_t launches = 0;
     uzu_model_info info{};
+    // persistent whole-token decode kernel (decode_mega.cu): program + buffers, built at load when the model is covered
+    struct Mega {
+        bool ok = false;
+        std::string why;                 // why the model is not covered (diagnostics)
+        uzu::MegaConfig cfg{};
+        std::vector<uzu::MkOp> ops;
+        Buf ops_dev, barrier, error_flag, argmax_keys, attn_part, attn_tickets, dn_qk, dn_kq, dn_v, dn_raw;
+        uint64_t stream_bytes = 0;
+    } mega;
 };
 
 namespace uzu {
@@ -1329,6 +1339,379 @@ static void encode_decoder_fused(uzu_engine* e, uzu_command_buffer* cmd, const P
     (void)pc;
 }
 
+
+// =====================================================================================================
+// persistent decode kernel: compile the model into a phase program (decode_mega.cu runs it, one launch per token)
+// =====================================================================================================
+namespace {
+
+struct MegaBuilder {
+    uzu_engine* e;
+    uzu_engine::Mega& mg;
+    uint32_t W;              // consumer warps of the whole grid
+    uint32_t bits = 0, group_size = 0;
+    size_t scratch = 0;
+    std::map<uint64_t, Buf> streams;   // original values pointer -> decode-stream copy
+
+    explicit MegaBuilder(uzu_engine* e_) : e(e_), mg(e_->mega), W(0) {}
+
+    void need(bool cond, const char* why) {
+        if (!cond) throw std::runtime_error(why);
+    }
+    Buf dev_zero(size_t bytes) {
+        Buf b = make_buf(e, std::max<size_t>(bytes, 256), UZU_BUFFER_DEVICE);
+        cudaMemsetAsync((void*)b.ptr(), 0, std::max<size_t>(bytes, 256), e->ctx->stream);
+        return b;
+    }
+    void check_linear(const Linear& l) {
+        const WeightMatrix& w = l.w;
+        need(w.prologue != UZU_B_FULL_PRECISION, "full-precision linear");
+        need(w.mode == UZU_QMODE_U4 || w.mode == UZU_QMODE_U8, "signed codes");
+        if (!bits) { bits = w.bits; group_size = w.group_size; }
+        need(w.bits == bits && w.group_size == group_size, "mixed quantisation geometry");
+        need(l.in_dim <= 16384 && (l.in_dim % 64) == 0 && (l.in_dim * bits / 8) % 16 == 0, "input dimension");
+        need((l.out_dim % 4) == 0, "output dimension");
+    }
+    const uint8_t* stream_of(const Linear& l) {
+        const uint64_t key = l.w.values.ptr();
+        auto it = streams.find(key);
+        if (it == streams.end()) {
+            const size_t bytes = mega_stream_bytes(l.out_dim, l.in_dim, bits);
+            Buf b = make_buf(e, bytes, UZU_BUFFER_DEVICE);
+            const uint32_t method = l.w.prologue == UZU_B_SCALE_BIAS_DEQUANT ? UZU_QMETHOD_SCALE_BIAS
+                                    : l.w.prologue == UZU_B_SCALE_ZERO_POINT_DEQUANT ? UZU_QMETHOD_SCALE_ZERO_POINT : UZU_QMETHOD_SCALE_SYMMETRIC;
+            mega_repack(e->ctx, (const uint8_t*)l.w.values.ptr(), (const __nv_bfloat16*)l.w.scales.ptr(), (const uint8_t*)l.w.zero_points.ptr(),
+                        (const __nv_bfloat16*)l.w.biases.ptr(), l.out_dim, l.in_dim, bits, group_size, method, (uint8_t*)b.ptr());
+            mg.stream_bytes += bytes;
+            it = streams.emplace(key, b).first;
+        }
+        return (const uint8_t*)it->second.ptr();
+    }
+    static uint32_t range_of(uint64_t u, uint64_t U, uint64_t Weff) { return (uint32_t)(((u + 1) * Weff - 1) / U); }
+
+    // one GEMV phase over 1..2 matrices sharing the input row; returns the op index
+    size_t gemv(std::initializer_list<const Linear*> mats) {
+        MkOp op{};
+        op.kind = MK_GEMV;
+        uint32_t unit0 = 0, nm = 0;
+        for (const Linear* l : mats) {
+            MkMat& M = op.mat[nm++];
+            M.n = l->out_dim; M.k = l->in_dim;
+            M.tiles = (l->out_dim + 15) / 16;
+            M.C = (l->in_dim * bits / 4 + 511) / 512;
+            M.bias_form = l->w.prologue == UZU_B_SCALE_BIAS_DEQUANT;
+            M.unit0 = unit0;
+            M.stream = stream_of(*l);
+            unit0 += M.tiles * M.C;
+            op.k = l->in_dim;
+        }
+        op.nmat = nm;
+        op.units = unit0;
+        const uint64_t U = unit0, Weff = std::min<uint64_t>(W, U);
+        for (uint32_t i = 0; i < nm; ++i) {
+            MkMat& M = op.mat[i];
+            need(M.k == op.k, "matrices of a phase must share the input row");
+            std::vector<uint8_t> cnt(M.tiles);
+            uint32_t P = 1;
+            for (uint32_t t = 0; t < M.tiles; ++t) {
+                const uint32_t a = range_of((uint64_t)M.unit0 + (uint64_t)t * M.C, U, Weff), b = range_of((uint64_t)M.unit0 + (uint64_t)(t + 1) * M.C - 1, U, Weff);
+                cnt[t] = (uint8_t)(b - a + 1);
+                P = std::max(P, b - a + 1);
+            }
+            need(P <= 255, "too many pieces per tile");
+            M.P = P;
+            Buf pieces = dev_zero((size_t)M.tiles * P * 16 * 4);
+            Buf counts = make_buf(e, std::max<size_t>(M.tiles, 256), UZU_BUFFER_DEVICE);
+            cudaMemcpyAsync((void*)counts.ptr(), cnt.data(), M.tiles, cudaMemcpyHostToDevice, e->ctx->stream);
+            cudaStreamSynchronize(e->ctx->stream);     // cnt is a local
+            M.pieces = (float*)pieces.ptr();
+            piece_tables.push_back(counts);
+        }
+        const uint32_t C = op.mat[0].C, gps = 512 / (group_size * bits / 4);
+        scratch = std::max(scratch, (size_t)(C * 64 + 4) * 16 + (size_t)C * gps * 4 + 64);
+        mg.ops.push_back(op);
+        return mg.ops.size() - 1;
+    }
+    std::vector<Buf> piece_tables;
+    MkPieces pieces_of(size_t op_index, int mat) {
+        const MkMat& M = mg.ops[op_index].mat[mat];
+        // the count table was pushed in order: find it by position
+        size_t idx = 0;
+        for (size_t i = 0; i < op_index; ++i)
+            if (mg.ops[i].kind == MK_GEMV) idx += mg.ops[i].nmat;
+        MkPieces pc{};
+        pc.pieces = M.pieces;
+        pc.count = (const uint8_t*)piece_tables[idx + mat].ptr();
+        pc.P = M.P;
+        return pc;
+    }
+    void norm_input(size_t op_index, const Norm& n, bool add, uint64_t sc_in, uint64_t sc_out) {
+        MkOp& op = mg.ops[op_index];
+        need(n.present || true, "");
+        need(!n.cfg.subtract_mean && n.cfg.has_scale, "norm variant");
+        op.in_kind = MK_IN_NORM;
+        op.shortcut_in = (const __nv_bfloat16*)sc_in;
+        op.shortcut_out = (__nv_bfloat16*)sc_out;
+        op.norm_scales = (const float*)n.scales.ptr();
+        op.norm_eps = n.cfg.epsilon; op.norm_scale_offset = n.cfg.scale_offset;
+        op.norm_residual_add = add; op.norm_full_layer = n.cfg.full_layer;
+    }
+
+    void build() {
+        const char* env = getenv("UZU_MEGA");
+        need(!env || atoi(env) != 0, "disabled by UZU_MEGA=0");
+        need(!e->tp_sharded, "tensor-parallel shard");
+        need(!e->has_logit_scale && !e->has_logit_soft_cap, "logit transform");
+        need((e->vocab % 4) == 0, "vocabulary size");
+        need((e->model_dim % 64) == 0, "model dimension");
+        for (auto& L : e->layers) {
+            if (L.is_attention) {
+                check_linear(L.attn.qkv); check_linear(L.attn.out);
+                if (L.attn.has_gate) check_linear(L.attn.gate);
+                const uint32_t D = L.attn.head_dim, G = L.attn.num_heads / L.attn.num_groups;
+                need(D == 64 || D == 128 || D == 256, "head dimension");
+                need(G >= 1 && G <= 4 && L.attn.num_heads % L.attn.num_groups == 0, "query heads per kv head");
+                need(L.attn.is_causal, "non-causal attention");
+                need((uint32_t)e->ctx->sm_count >= L.attn.num_groups, "more kv heads than SMs");
+            } else {
+                check_linear(L.dn.in_proj); check_linear(L.dn.out_proj);
+                need(L.dn.head_dim == 128, "DeltaNet key head dimension");
+                need(L.dn.value_head_dim == 64 || L.dn.value_head_dim == 128 || L.dn.value_head_dim == 256, "DeltaNet value head dimension");
+                need((L.dn.value_dim % 256) == 0 && (L.dn.key_dim % 128) == 0 && (L.dn.value_dim % 128) == 0, "DeltaNet dimensions");
+                need(L.dn.kernel_size >= 2 && L.dn.kernel_size - 1 <= 7, "DeltaNet conv taps");
+                need(L.dn.num_heads % L.dn.num_groups == 0, "DeltaNet heads");
+            }
+            check_linear(L.up); check_linear(L.down);
+            need((L.hidden_dim % 16) == 0 && L.up.out_dim == 2 * L.hidden_dim, "MLP dimensions");
+        }
+        check_linear(e->out_emb);
+        need(bits != 0, "no quantised linear");
+        const uint32_t npg = group_size * bits / 4;
+        // partition parameters first (the piece tables depend on the number of consumer warps)
+        MegaConfig probe{};
+        need(mega_config(e->ctx, npg, bits, 0, &probe), "quantisation geometry not covered by the persistent kernel");
+        W = probe.grid * probe.ncw;
+
+        const uint32_t H = e->model_dim;
+        uint64_t S[2] = {e->shortcut.ptr(), e->shortcut2.ptr()};
+        int cur = 0;
+        uint32_t max_attn_scratch = 0, max_parts = 0, max_hk = 1, max_vd = 1, max_kvh = 1;
+        for (auto& L : e->layers) {
+            if (L.is_attention) {
+                const uint32_t G = L.attn.num_heads / L.attn.num_groups;
+                max_attn_scratch = std::max<uint32_t>(max_attn_scratch, probe.ncw * G * (L.attn.head_dim + 2) * 4);
+                max_parts = std::max<uint32_t>(max_parts, probe.grid * G * (L.attn.head_dim + 2));
+                max_kvh = std::max(max_kvh, L.attn.num_groups);
+            } else {
+                max_hk = std::max(max_hk, L.dn.num_groups);
+                max_vd = std::max(max_vd, L.dn.value_dim);
+            }
+        }
+        scratch = std::max<size_t>(scratch, max_attn_scratch + 64);
+        mg.attn_part = dev_zero((size_t)std::max(max_parts, 64u) * 4);
+        mg.attn_tickets = dev_zero(max_kvh * 4);
+        mg.dn_qk = dev_zero((size_t)max_hk * 2 * 128 * 4);
+        mg.dn_kq = dev_zero((size_t)max_hk * 4);
+        mg.dn_v = dev_zero((size_t)max_vd * 4);
+        mg.dn_raw = dev_zero((size_t)max_vd * 4);
+        mg.argmax_keys = dev_zero((size_t)probe.grid * 8);
+
+        size_t prev_down = (size_t)-1;
+        for (size_t i = 0; i < e->layers.size(); ++i) {
+            Layer& L = e->layers[i];
+            LayerState& St = e->state[i];
+            auto mixer_source = [&](size_t oi) {
+                MkOp& op = mg.ops[oi];
+                if (i == 0) {
+                    op.src_kind = MK_SRC_EMBED;
+                    MkEmbed& E = op.embed;
+                    const WeightMatrix& w = e->in_emb.w;
+                    E.weights = (const uint8_t*)w.values.ptr(); E.scales = (const __nv_bfloat16*)w.scales.ptr();
+                    E.zero_points = (const uint8_t*)w.zero_points.ptr(); E.biases = (const __nv_bfloat16*)w.biases.ptr();
+                    E.full_precision = w.prologue == UZU_B_FULL_PRECISION; E.mode = w.mode; E.group_size = w.group_size ? w.group_size : 64;
+                    E.method = w.prologue == UZU_B_SCALE_BIAS_DEQUANT ? UZU_QMETHOD_SCALE_BIAS
+                               : w.prologue == UZU_B_SCALE_ZERO_POINT_DEQUANT ? UZU_QMETHOD_SCALE_ZERO_POINT : UZU_QMETHOD_SCALE_SYMMETRIC;
+                    E.vocab = e->vocab; E.input_scale = e->input_scale;
+                    need(E.full_precision || (E.group_size % 8) == 0, "embedding group size");
+                } else {
+                    op.src_kind = MK_SRC_PIECES;
+                    op.src_pc = pieces_of(prev_down, 0);
+                }
+            };
+            size_t mix_out;
+            if (L.is_attention) {
+                const AttentionLayer& A = L.attn;
+                const uint32_t D = A.head_dim, Hq = A.num_heads, Hkv = A.num_groups;
+                const size_t o_in = A.has_gate ? gemv({&A.gate, &A.qkv}) : gemv({&A.qkv});
+                const int qkv_mat = A.has_gate ? 1 : 0;
+                norm_input(o_in, L.pre_mixer, i > 0, S[cur], S[cur ^ 1]);
+                mixer_source(o_in);
+                cur ^= 1;
+                MkOp prep{};
+                prep.kind = MK_PREP;
+                prep.qkv_pc = pieces_of(o_in, qkv_mat);
+                prep.queries = (__nv_bfloat16*)e->queries.ptr();
+                prep.keys = (__nv_bfloat16*)St.keys; prep.values = (__nv_bfloat16*)St.values;
+                prep.attn_out = (__nv_bfloat16*)e->attn_out.ptr();
+                prep.num_q_heads = Hq; prep.num_kv_heads = Hkv; prep.head_dim = D;
+                if (A.rope_index >= 0) {
+                    prep.rope_dim = e->ropes[A.rope_index].head_dim;
+                    need(prep.rope_dim <= D && (prep.rope_dim % 2) == 0, "rope dimension");
+                    prep.rope_cos = (const float*)e->rope_cos[A.rope_index].ptr();
+                    prep.rope_sin = (const float*)e->rope_sin[A.rope_index].ptr();
+                }
+                auto nq = [&](const Norm& n, const float*& sc, float& eps, float& off, uint32_t& full, uint32_t& has, uint32_t& present) {
+                    present = n.present;
+                    if (!n.present) return;
+                    need(!n.cfg.subtract_mean, "q/k norm variant");
+                    sc = (const float*)n.scales.ptr(); eps = n.cfg.epsilon; off = n.cfg.scale_offset; full = n.cfg.full_layer; has = n.cfg.has_scale;
+                };
+                nq(A.qnorm, prep.qnorm_scales, prep.qnorm_eps, prep.qnorm_offset, prep.qnorm_full_layer, prep.qnorm_has_scales, prep.qnorm_present);
+                nq(A.knorm, prep.knorm_scales, prep.knorm_eps, prep.knorm_offset, prep.knorm_full_layer, prep.knorm_has_scales, prep.knorm_present);
+                prep.attn_scale = A.has_scale ? A.scale : 1.0f / sqrtf((float)D);
+                prep.attn_part = (float*)mg.attn_part.ptr();
+                prep.attn_tickets = (unsigned int*)mg.attn_tickets.ptr();
+                mg.ops.push_back(prep);
+                MkOp at = prep;
+                at.kind = MK_ATTN;
+                mg.ops.push_back(at);
+                mix_out = gemv({&A.out});
+                MkOp& oo = mg.ops[mix_out];
+                oo.src_kind = MK_SRC_BF16;
+                oo.src_vec = (const __nv_bfloat16*)e->attn_out.ptr();
+                if (A.has_gate) { oo.in_kind = MK_IN_SIGMOID; oo.gate_pc = pieces_of(o_in, 0); }
+                else oo.in_kind = MK_IN_PLAIN;
+            } else {
+                const DeltaNetLayer& Dn = L.dn;
+                const size_t o_in = gemv({&Dn.in_proj});
+                norm_input(o_in, L.pre_mixer, i > 0, S[cur], S[cur ^ 1]);
+                mixer_source(o_in);
+                cur ^= 1;
+                MkOp dc{};
+                dc.kind = MK_DN_CONV;
+                dc.dn_in_pc = pieces_of(o_in, 0);
+                dc.dn_conv_weight = (const float*)Dn.conv_weight.ptr();
+                dc.dn_conv_bias = Dn.conv_has_bias ? (const float*)Dn.conv_bias.ptr() : nullptr;
+                dc.dn_conv_state = (float*)St.conv_state.ptr();
+                dc.dn_a_log = (const float*)Dn.a_log.ptr(); dc.dn_dt_bias = (const float*)Dn.dt_bias.ptr();
+                dc.dn_state = (float*)St.ssm_state.ptr();
+                dc.dn_qk = (float*)mg.dn_qk.ptr(); dc.dn_kq = (float*)mg.dn_kq.ptr(); dc.dn_v = (float*)mg.dn_v.ptr(); dc.dn_out_raw = (float*)mg.dn_raw.ptr();
+                dc.dn_kernel_size = Dn.kernel_size; dc.dn_key_dim = Dn.key_dim; dc.dn_value_dim = Dn.value_dim;
+                dc.dn_num_k_heads = Dn.num_groups; dc.dn_num_v_heads = Dn.num_heads; dc.dn_hv_dim = Dn.value_head_dim;
+                need(Dn.key_dim == Dn.num_groups * 128 && Dn.value_dim == Dn.num_heads * Dn.value_head_dim && Dn.conv_dim == 2 * Dn.key_dim + Dn.value_dim,
+                     "DeltaNet geometry");
+                need(Dn.total_proj_dim == Dn.conv_dim + Dn.value_dim + 2 * Dn.num_heads, "DeltaNet projection layout");
+                mg.ops.push_back(dc);
+                MkOp du = dc;
+                du.kind = MK_DN_UPDATE;
+                mg.ops.push_back(du);
+                mix_out = gemv({&Dn.out_proj});
+                MkOp& oo = mg.ops[mix_out];
+                oo.in_kind = MK_IN_DELTA;
+                oo.src_kind = MK_SRC_BF16;       // unused by MK_IN_DELTA (the row comes from dn_raw)
+                oo.src_vec = (const __nv_bfloat16*)e->delta_out.ptr();
+                oo.dn_raw = (const float*)mg.dn_raw.ptr();
+                oo.dn_norm_weight = (const float*)Dn.norm_weight.ptr();
+                oo.dn_z_pc = pieces_of(o_in, 0);
+                oo.dn_z_row0 = Dn.conv_dim;
+                oo.dn_heads = Dn.num_heads; oo.dn_head_v_dim = Dn.value_head_dim; oo.dn_eps = Dn.norm_epsilon;
+                need(Dn.out_proj.in_dim == Dn.value_dim, "DeltaNet out projection");
+            }
+            // pre_mlp_norm + DenseMlp (mlp/dense.rs:32-48)
+            const size_t o_up = gemv({&L.up});
+            norm_input(o_up, L.pre_mlp, true, S[cur], S[cur ^ 1]);
+            mg.ops[o_up].src_kind = MK_SRC_PIECES;
+            mg.ops[o_up].src_pc = pieces_of(mix_out, 0);
+            cur ^= 1;
+            MkOp act{};
+            act.kind = MK_ACT;
+            act.up_pc = pieces_of(o_up, 0);
+            act.hidden = (__nv_bfloat16*)e->gated.ptr();
+            act.act_dim = L.hidden_dim; act.act_type = L.act;
+            mg.ops.push_back(act);
+            const size_t o_down = gemv({&L.down});
+            mg.ops[o_down].in_kind = MK_IN_PLAIN;
+            mg.ops[o_down].src_kind = MK_SRC_BF16;
+            mg.ops[o_down].src_vec = (const __nv_bfloat16*)e->gated.ptr();
+            prev_down = o_down;
+            (void)H;
+        }
+        // output norm (residual add, transformer.rs:317-323) + readout + greedy argmax
+        const size_t o_out = gemv({&e->out_emb});
+        norm_input(o_out, e->out_norm, true, S[cur], S[cur ^ 1]);
+        mg.ops[o_out].src_kind = MK_SRC_PIECES;
+        mg.ops[o_out].src_pc = pieces_of(prev_down, 0);
+        MkOp lg{};
+        lg.kind = MK_LOGITS;
+        lg.logits_pc = pieces_of(o_out, 0);
+        lg.logits = (__nv_bfloat16*)e->logits.ptr();
+        lg.vocab = e->vocab;
+        lg.argmax_keys = (unsigned long long*)mg.argmax_keys.ptr();
+        mg.ops.push_back(lg);
+        MkOp fin = lg;
+        fin.kind = MK_FINISH;
+        mg.ops.push_back(fin);
+
+        need(mega_config(e->ctx, npg, bits, (uint32_t)scratch, &mg.cfg), "shared memory budget");
+        mg.ops_dev = make_buf(e, mg.ops.size() * sizeof(MkOp), UZU_BUFFER_DEVICE);
+        cudaMemcpyAsync((void*)mg.ops_dev.ptr(), mg.ops.data(), mg.ops.size() * sizeof(MkOp), cudaMemcpyHostToDevice, e->ctx->stream);
+        mg.barrier = dev_zero(256);
+        mg.error_flag = make_buf(e, 256, UZU_BUFFER_PINNED_HOST);
+        *(volatile unsigned int*)uzu_buffer_cpu_ptr(mg.error_flag.b) = 0u;
+        cudaError_t err = cudaStreamSynchronize(e->ctx->stream);
+        if (err != cudaSuccess) throw std::runtime_error(std::string("decode stream repack: ") + cudaGetErrorString(err));
+        mg.ok = true;
+    }
+};
+
+}  // namespace
+
+static void build_mega(uzu_engine* e) {
+    MegaBuilder b(e);
+    try {
+        b.build();
+    } catch (const std::exception& ex) {
+        e->mega.ok = false;
+        e->mega.why = ex.what();
+    }
+}
+
+static bool mega_usable(const uzu_engine* e) {
+    return e->mega.ok && e->sampling.kind == UZU_SAMPLING_GREEDY;
+}
+
+static void mega_check_error(uzu_engine* e) {
+    if (!e->mega.ok) return;
+    const unsigned int code = *(volatile unsigned int*)uzu_buffer_cpu_ptr(e->mega.error_flag.b);
+    if (code) {
+        e->mega.ok = false;
+        char buf[96];
+        snprintf(buf, sizeof buf, "persistent decode kernel timed out (code 0x%x); falling back to the per-kernel path", code);
+        throw std::runtime_error(buf);
+    }
+}
+
+static void launch_mega_step(uzu_engine* e, uint64_t dev_out, uint32_t dev_out_base_step) {
+    MkParams p{};
+    p.ops = (const MkOp*)e->mega.ops_dev.ptr();
+    p.nops = (uint32_t)e->mega.ops.size();
+    p.ncw = e->mega.cfg.ncw;
+    p.state = (MkStepState*)e->decode_state.ptr();
+    p.barrier = (unsigned int*)e->mega.barrier.ptr();
+    p.error_flag = (unsigned int*)e->mega.error_flag.ptr();
+    p.token_ids = (const uint32_t*)e->token_ids.ptr();
+    p.token_out = (uint32_t*)e->token_ids.ptr();
+    p.sampled = (uint32_t*)e->sampled.ptr();
+    p.host_ring = (volatile uint32_t*)e->host_ring.ptr();
+    p.dev_out = (uint32_t*)dev_out;
+    p.dev_out_base_step = dev_out_base_step;
+    p.token_ring = TOKEN_RING;
+    p.scratch_bytes = e->mega.cfg.scratch_bytes;
+    p.stages = e->mega.cfg.stages;
+    if (const char* err = mega_launch(e->ctx, e->mega.cfg, p)) throw std::runtime_error(std::string("decode_mega launch: ") + err);
+    e->launches += 1;
+}
+
 static void encode_sampling(uzu_engine* e, uzu_command_buffer* cmd, uint32_t rows) {
     const uzu_sampling_method& s = e->sampling;
     uzu_unified_sampling_args sa{};
@@ -1464,7 +1847,9 @@ static void issue_decode_step(uzu_engine* e, uint64_t dev_out, uint32_t dev_out_
         throw std::runtime_error("context overflow: raise max_context_length");
     state_prepare(e, e->context_length + 1);
     cudaStream_t s = e->ctx->stream;
-    if (e->opts.use_cuda_graph && !dev_out) {
+    if (mega_usable(e)) {
+        launch_mega_step(e, dev_out, dev_out_base_step);
+    } else if (e->opts.use_cuda_graph && !dev_out) {
         if (!e->graph_exec || e->graph_bucket != attention_bucket(e->context_length + 1) || !graph_sampling_matches(e))
             capture_decode_graph(e);
         cudaError_t err = cudaGraphLaunch(e->graph_exec, s);
@@ -1531,6 +1916,7 @@ uzu_status uzu_engine_create(uzu_context* ctx, const char* model_dir, const uzu_
         create_state_and_scratch(e);
         reset_state(e);
         e->fused_ok = e->opts.fused_decode && getenv("UZU_NO_FUSED") == nullptr && fused_decode_supported(e);
+        if (e->opts.fused_decode) build_mega(e);      // the persistent decode kernel is the fused path's next step: one launch per token
         check(uzu_context_synchronize(ctx));
     } catch (const std::exception& ex) {
         std::string msg = ex.what();
@@ -1638,6 +2024,7 @@ uzu_status uzu_engine_next(uzu_engine* e, uint32_t* out_token) {
             const uint32_t idx = e->steps_returned;
             cudaError_t err = cudaEventSynchronize(e->step_events[idx & 1]);
             if (err != cudaSuccess) throw std::runtime_error(std::string("decode step failed: ") + cudaGetErrorString(err));
+            mega_check_error(e);
             if (out_token) *out_token = ((volatile uint32_t*)uzu_buffer_cpu_ptr(e->host_ring.b))[idx % TOKEN_RING];
             e->steps_returned++;
         } else if (out_token) {
@@ -1652,6 +2039,7 @@ uzu_status uzu_engine_flush(uzu_engine* e, uint32_t* out_token) {
             const uint32_t idx = e->steps_returned;
             cudaError_t err = cudaEventSynchronize(e->step_events[idx & 1]);
             if (err != cudaSuccess) throw std::runtime_error(std::string("decode step failed: ") + cudaGetErrorString(err));
+            mega_check_error(e);
             if (out_token) *out_token = ((volatile uint32_t*)uzu_buffer_cpu_ptr(e->host_ring.b))[idx % TOKEN_RING];
             e->steps_returned++;
         } else if (out_token) {
@@ -1679,6 +2067,29 @@ uzu_status uzu_engine_forward(uzu_engine* e, const uint32_t* tokens, uint32_t co
 
 uint64_t uzu_engine_launch_count(const uzu_engine* e) { return e ? e->launches : 0; }
 
+// ---- persistent decode kernel controls (extension) ----
+int uzu_engine_decode_mode(const uzu_engine* e) { return e && e->mega.ok ? 1 : 0; }
+const char* uzu_engine_decode_mode_reason(const uzu_engine* e) { return e ? e->mega.why.c_str() : ""; }
+uzu_status uzu_engine_set_decode_mode(uzu_engine* e, int persistent) {
+    UZU_ENGINE_TRY({
+        cudaStreamSynchronize(e->ctx->stream);
+        if (!persistent) { e->mega.ok = false; if (e->mega.why.empty()) e->mega.why = "disabled by uzu_engine_set_decode_mode"; }
+        else if (!e->mega.ok) {
+            if (e->mega.ops.empty() || !e->mega.ops_dev.b) throw std::runtime_error("persistent decode kernel not available: " + e->mega.why);
+            *(volatile unsigned int*)uzu_buffer_cpu_ptr(e->mega.error_flag.b) = 0u;
+            e->mega.ok = true;
+        }
+    });
+}
+uzu_status uzu_engine_last_logits(uzu_engine* e, uint16_t* out_logits) {
+    UZU_ENGINE_TRY({
+        cudaError_t err = cudaStreamSynchronize(e->ctx->stream);
+        if (err != cudaSuccess) throw std::runtime_error(std::string("last_logits: ") + cudaGetErrorString(err));
+        mega_check_error(e);
+        cudaMemcpy(out_logits, (void*)e->logits.ptr(), (size_t)e->vocab * 2, cudaMemcpyDeviceToHost);
+    });
+}
+
 uzu_status uzu_engine_decode_timed(uzu_engine* e, uint32_t steps, double* out_seconds) {
     UZU_ENGINE_TRY({
         cudaStream_t s = e->ctx->stream;
@@ -1696,6 +2107,7 @@ uzu_status uzu_engine_decode_timed(uzu_engine* e, uint32_t steps, double* out_se
         cudaEventDestroy(b);
         e->steps_returned = e->steps_issued;
         if (err != cudaSuccess) throw std::runtime_error(std::string("decode_timed: ") + cudaGetErrorString(err));
+        mega_check_error(e);
         if (out_seconds) *out_seconds = (double)ms * 1e-3;
     });
 }
@@ -1711,6 +2123,7 @@ uzu_status uzu_engine_step_host(uzu_engine* e, uint32_t token_in, uint32_t* toke
         cudaMemcpyAsync(staging + 1, (void*)e->sampled.ptr(), 4, cudaMemcpyDeviceToHost, s); // D2H: this step's result
         cudaError_t err = cudaStreamSynchronize(s);
         if (err != cudaSuccess) throw std::runtime_error(std::string("step_host: ") + cudaGetErrorString(err));
+        mega_check_error(e);
         tok = staging[1];
         e->steps_returned = e->steps_issued;
         if (token_out) *token_out = tok;
