@@ -221,25 +221,31 @@ def bf16_to_f32(a):
     return (np.asarray(a, np.uint16).astype(np.uint32) << 16).view(np.float32)
 
 
-def parity_check(eng, model_dir: Path, threads: int, prompt_len: int = 6, steps: int = 3, budget_s: float = 90.0):
-    """The timed engine against the CPU oracle on the same checkpoint: a short prompt, then `steps` decode steps under teacher forcing
-    (oracle tokens fed to both). Reports greedy token ids (GPU vs oracle) and the last-row logit error. Bounded: gives up after budget_s."""
+def cpu_leg(eng, model_dir: Path, threads: int, budget_s: float, max_steps: int = 3):
+    """ONE bounded CPU leg for both reported objects: the oracle decodes a 1-token prompt and up to `max_steps` more tokens of the
+    full model (stops when `budget_s` of CPU time is spent; at least one decode step). Every oracle pass is timed (-> cpu_baseline,
+    cores = the threads used) and the same passes are the parity oracle for the timed engine: teacher-forced with the oracle's tokens,
+    greedy token ids and last-row logits compared step by step."""
     from oracle.model import OracleModel
-    t0 = time.perf_counter()
+    t_load = time.perf_counter()
     ref = OracleModel(model_dir, threads=threads, max_context=64)
+    log(f"[bench] oracle loaded in {time.perf_counter() - t_load:.1f}s ({threads} threads)")
     rng = np.random.default_rng(1)
-    prompt = rng.integers(0, ref.V, prompt_len).astype(np.uint32)
+    prompt = rng.integers(0, ref.V, 1).astype(np.uint32)
+    t0 = time.perf_counter()
     lr = ref.prefill(prompt)
+    pass_times = [time.perf_counter() - t0]
     eng.reset()
     first = eng.prefill(prompt)
     want = int(np.argmax(bf16_to_f32(lr[0])))
     ids_gpu, ids_ref, worst, gaps = [int(first)], [want], 0.0, []
     tok = want
-    done = 0
-    for _ in range(steps):
-        if time.perf_counter() - t0 > budget_s:
+    for i in range(max_steps):
+        if i > 0 and sum(pass_times) + pass_times[-1] > budget_s:
             break
+        t1 = time.perf_counter()
         lr = ref.forward([tok])
+        pass_times.append(time.perf_counter() - t1)
         got = eng.step_host(tok)
         lg = eng.last_logits()
         r, g = bf16_to_f32(lr[0]), bf16_to_f32(lg[0])
@@ -249,12 +255,17 @@ def parity_check(eng, model_dir: Path, threads: int, prompt_len: int = 6, steps:
         gaps.append(float((top[0] - top[1]) / max(abs(top[0]), 1e-30)))
         tok = int(np.argmax(r))
         ids_gpu.append(int(got)); ids_ref.append(tok)
-        done += 1
+        log(f"[bench] oracle pass {i + 1}: {pass_times[-1]:.1f}s")
     eng.reset()
-    return {"prompt_tokens": prompt_len, "decode_steps_checked": done, "token_ids_gpu": ids_gpu, "token_ids_oracle": ids_ref,
-            "token_ids_equal": ids_gpu == ids_ref, "max_logit_err_over_range": worst, "top2_gap_over_range": gaps,
-            "persistent_kernel": bool(eng.persistent_decode), "seconds": time.perf_counter() - t0,
-            "note": "teacher-forced with the oracle's tokens; logits are bf16, error is max|gpu - oracle| / max|oracle| over the vocabulary"}
+    decode_times = pass_times[1:]
+    cpu = {"value": len(decode_times) / sum(decode_times), "unit": "tokens/s", "cores": threads, "kind": "port",
+           "sample": f"{len(decode_times)} decode token(s) of the full model at context 1..{len(decode_times)} after a 1-token prompt "
+                     f"(bounded to ~{budget_s:.0f}s of CPU work; OpenMP over output columns with {threads} thread(s), the reference runs 1 worker thread)"}
+    parity = {"prompt_tokens": 1, "decode_steps_checked": len(decode_times), "token_ids_gpu": ids_gpu, "token_ids_oracle": ids_ref,
+              "token_ids_equal": ids_gpu == ids_ref, "max_logit_err_over_range": worst, "top2_gap_over_range": gaps,
+              "persistent_kernel": bool(eng.persistent_decode),
+              "note": "teacher-forced with the oracle's tokens; logits are bf16, error = max|gpu - oracle| / max|oracle| over the vocabulary"}
+    return cpu, parity
 
 
 def run_reference(args, rank: int):
@@ -461,7 +472,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     info = eng.info
     rng = np.random.default_rng(0)
     prompt = rng.integers(0, info.vocab_size, prefill).astype(np.uint32)
+    log(f"[bench] engine ready: {workload}, persistent decode = {eng.persistent_decode} {eng.persistent_decode_reason}")
     m = measure_decode(eng, dist, world, replicas, local_rank, prompt, K, W)
+    log(f"[bench] {workload}: {m['value']:.1f} tok/s device-resident, {m['e2e_value']:.1f} end to end, {m['launches']} launches")
     roof, extra = roofline_of(eng, workload, prefill, K, m["seconds"])
     ctx_mid = prefill + K / 2
     line = {
@@ -488,14 +501,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     threads = effective_cpus()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            v, sample = cpu_baseline(full_dir, threads=1, tokens=3 if workload.startswith("qwen") else 1)
-            line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": 1, "kind": "port", "sample": sample}
+            line["cpu_baseline"], line["parity"] = cpu_leg(eng, full_dir, threads, budget_s=45.0)
         except Exception as ex:  # the baseline must not take the measurement down
-            line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": 1, "kind": "port", "sample": f"failed: {ex}"}
-        try:
-            line["parity"] = parity_check(eng, full_dir, threads)
-        except Exception as ex:
-            line["parity"] = {"error": str(ex)[:300]}
+            line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": f"failed: {ex}"}
     eng.close()
     # ---- secondary line (N = 1): BASELINE.json configs[1], Qwen3.5-0.8B int4 prefill 512 / decode 128 ----
     if world == 1 and tp == 1 and not args.no_secondary and workload != SECONDARY:
@@ -533,13 +541,14 @@ def secondary_line(B, ctx, args, local_rank: int):
         rng = np.random.default_rng(0)
         prompt = rng.integers(0, eng.info.vocab_size, prefill).astype(np.uint32)
         m = measure_decode(eng, None, 1, 1, local_rank, prompt, K, max(args.warmup, 3))
+        log(f"[bench] {SECONDARY}: {m['value']:.1f} tok/s device-resident, {m['e2e_value']:.1f} end to end, {m['launches']} launches")
         roof, extra = roofline_of(eng, SECONDARY, prefill, K, m["seconds"])
         out = {"workload": workload_name(SECONDARY, prefill, K, 1), "value": m["value"], "unit": "tokens/s", "ms_per_step": 1000.0 * m["seconds"] / K,
                "e2e": m["e2e_value"], "gpu_launches": m["launches"], "roofline": roof, "prefill_tokens_per_s": prefill / m["prefill_s"],
                "decode_path": "persistent kernel (1 launch per token)" if eng.persistent_decode else "per-kernel path", **extra}
         if not args.no_cpu_baseline:
             try:
-                out["parity"] = parity_check(eng, mdir, effective_cpus())
+                out["cpu_baseline"], out["parity"] = cpu_leg(eng, mdir, effective_cpus(), budget_s=20.0)
             except Exception as ex:
                 out["parity"] = {"error": str(ex)[:300]}
         return out

@@ -150,7 +150,7 @@ uzu_engine_forward uzu_engine_batch_begin uzu_engine_batch_prefill uzu_engine_ba
 uzu_engine_batch_logits uzu_engine_batch_context_length uzu_engine_launch_count uzu_engine_decode_timed uzu_engine_step_host
 uzu_delta_net_fused_update_supported uzu_delta_net_fused_update_encode uzu_engine_time_linears uzu_engine_time_prefill_linears uzu_engine_time_linears_select uzu_debug_set_qmv_tuning uzu_debug_set_delta_prefill uzu_debug_set_prefill_attention uzu_debug_set_umma uzu_tp_get_unique_id uzu_context_tp_init uzu_context_tp_destroy uzu_context_tp_size
 uzu_context_tp_rank uzu_tp_p2p_export uzu_tp_p2p_import uzu_tp_all_reduce_encode uzu_tp_all_gather_encode uzu_fused_linear_supported uzu_fused_linear_encode
-uzu_engine_decode_mode uzu_engine_decode_mode_reason uzu_engine_set_decode_mode uzu_engine_last_logits""".split()
+uzu_engine_decode_mode uzu_engine_decode_mode_reason uzu_engine_set_decode_mode uzu_engine_last_logits uzu_engine_debug_decode_trace""".split()
 
 _lib = None
 
@@ -258,6 +258,7 @@ def load() -> C.CDLL:
         "uzu_engine_decode_mode_reason": (C.c_char_p, [vp]),
         "uzu_engine_set_decode_mode": (C.c_int, [vp, C.c_int]),
         "uzu_engine_last_logits": (C.c_int, [vp, C.POINTER(C.c_uint16)]),
+        "uzu_engine_debug_decode_trace": (C.c_int, [vp, u32, u32, C.POINTER(u32), C.POINTER(u64), C.POINTER(u32)]),
         "uzu_engine_time_linears": (C.c_int, [vp, u32, C.POINTER(C.c_double), C.POINTER(u64)]),
         "uzu_engine_time_prefill_linears": (C.c_int, [vp, u32, u32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "uzu_engine_time_linears_select": (C.c_int, [vp, u32, u32, C.POINTER(C.c_double), C.POINTER(u64)]),
@@ -540,6 +541,15 @@ class Engine:
 
     def set_persistent_decode(self, on: bool):
         _check(self.lib.uzu_engine_set_decode_mode(self.h, int(on)))
+
+    def decode_trace(self, cta: int = 0):
+        """One persistent decode step with per-phase SM-clock stamps of CTA `cta`: (kinds [n], cycles [n, 4])."""
+        cap = 4096
+        kinds = np.zeros(cap, dtype=np.uint32)
+        cyc = np.zeros((cap, 4), dtype=np.uint64)
+        n = u32()
+        _check(self.lib.uzu_engine_debug_decode_trace(self.h, cta, cap, kinds.ctypes.data_as(C.POINTER(u32)), cyc.ctypes.data_as(C.POINTER(u64)), C.byref(n)))
+        return kinds[:n.value], cyc[:n.value]
 
     def last_logits(self) -> np.ndarray:
         out = np.zeros((1, self.info.vocab_size), dtype=np.uint16)

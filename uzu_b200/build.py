@@ -1,7 +1,7 @@
 """Builds uzu_b200/lib/libuzu_b200.so with nvcc for sm_100a (in-tree; the .so travels to the GPU box).
 
 No torch, no cmake: plain `nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo` per source, then one
-link step. Objects are cached by (source mtime, flags). `python -m uzu_b200.build [--force] [--verbose]`.
+link step. Objects are cached by the content hash of (source, headers, flags). `python -m uzu_b200.build [--force] [--verbose]`.
 """
 from __future__ import annotations
 
@@ -40,17 +40,24 @@ SOURCES = {
 }
 
 
-def _deps_mtime() -> float:
-    hdrs = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [HERE.parent / "include" / "uzu_b200.h"]
-    return max(h.stat().st_mtime for h in hdrs)
+def _deps_digest() -> bytes:
+    hdrs = sorted(list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [HERE.parent / "include" / "uzu_b200.h"])
+    h = hashlib.sha1()
+    for f in hdrs:
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.digest()
 
 
 def _compile(src: Path, extra, verbose: bool, force: bool):
-    key = hashlib.sha1((" ".join(COMMON + extra)).encode()).hexdigest()[:8]
+    # the cache key is the CONTENT of the source, of every header and the flags (not mtimes: the gpurun snapshot does not keep them, and a
+    # stale-looking object would trigger a multi-minute rebuild on the GPU box)
+    key = hashlib.sha1(" ".join(COMMON + extra).encode() + src.read_bytes() + _deps_digest()).hexdigest()[:12]
     obj = OBJ / f"{src.stem}.{key}.o"
-    newest = max(src.stat().st_mtime, _deps_mtime())
-    if not force and obj.exists() and obj.stat().st_mtime >= newest:
+    if not force and obj.exists():
         return obj, None
+    for old in OBJ.glob(f"{src.stem}.*.o"):
+        old.unlink()
     cmd = [NVCC, *COMMON, *extra, "-c", str(src), "-o", str(obj)]
     if verbose:
         cmd.insert(1, "-Xptxas")
@@ -75,13 +82,16 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if verbose:
         for l in logs:
             print(l)
-    relink = force or bool(logs) or bool(extra) or not lib.exists() or any(o.stat().st_mtime > lib.stat().st_mtime for o in objs)
+    manifest = lib.with_suffix(".objects")
+    want = "\n".join(o.name for o in objs)
+    relink = force or bool(extra) or not lib.exists() or not manifest.exists() or manifest.read_text() != want
     if relink:
         cmd = [NVCC, "-shared", "-o", str(lib), *map(str, objs), "-ccbin", HOST_CXX, "-gencode", "arch=compute_100a,code=sm_100a",
                "-cudart", "static", "-Xlinker", "-z,defs", "-lpthread", "-ldl", "-lrt"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        manifest.write_text(want)
     return lib
 
 

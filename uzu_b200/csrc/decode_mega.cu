@@ -45,10 +45,24 @@ __device__ __forceinline__ bool mk_mbar_try_wait(uint32_t addr, uint32_t parity)
                  : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mk_bulk_copy(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src), "r"(bytes),
-                 "r"(mbar)
+__device__ __forceinline__ bool mk_mbar_test_wait(uint32_t addr, uint32_t parity) {     // non-blocking
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(addr), "r"(parity)
                  : "memory");
+    return ok != 0;
+}
+// the weight stream is read exactly once per token: evict-first keeps the small hot data (pieces, residual rows, norm scales) in L2
+__device__ __forceinline__ void mk_bulk_copy(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem), "l"(src),
+                 "r"(bytes), "r"(mbar), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t mk_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
 }
 __device__ __forceinline__ void mk_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ unsigned int mk_ld_acquire(const unsigned int* p) {
@@ -61,10 +75,12 @@ __device__ __forceinline__ void mk_st_release(unsigned int* p, unsigned int v) {
 constexpr long long MK_TIMEOUT_CLOCKS = 3000000000ll;   // ~1.5 s at 1.9 GHz
 
 struct MkWatch {
-    unsigned int* flag;
+    unsigned int* flag;        // device word polled by the spin loops (never host memory: a poll over PCIe from every thread costs milliseconds)
+    unsigned int* host_flag;   // pinned host mirror, written only on failure
     bool dead;
     __device__ __forceinline__ void fail(unsigned int code) {
-        *reinterpret_cast<volatile unsigned int*>(flag) = code;     // pinned host word: plain store (a racing second code is harmless)
+        *reinterpret_cast<volatile unsigned int*>(flag) = code;     // plain stores (a racing second code is harmless)
+        *reinterpret_cast<volatile unsigned int*>(host_flag) = code;
         dead = true;
     }
     __device__ __forceinline__ bool poll_dead() {
@@ -86,32 +102,28 @@ __device__ __forceinline__ void mk_wait(uint32_t mbar, uint32_t parity, MkWatch&
     }
 }
 
-// Grid barrier over the consumer warps of all CTAs (the producer warp never waits here). Arrivals counter + generation word; the
-// last arriver resets the counter and bumps the generation. Called by all consumer threads.
-__device__ __forceinline__ void mk_grid_sync(const MkParams& p, int ctid, int nct, MkWatch& w) {
+// Grid barrier over the consumer warps of all CTAs (the producer warp never waits here). One monotonic 64-bit arrival counter that is
+// never reset: barrier number `index` of a launch completes when the counter reaches barrier_base + (index + 1) * gridDim (the host
+// advances barrier_base by barriers_per_launch * gridDim per launch). Arrive = red.release (fire and forget: no round trip before the
+// wait starts), wait = ld.acquire polling by one thread. Called by all consumer threads.
+__device__ __forceinline__ void mk_grid_sync(const MkParams& p, uint32_t index, int ctid, int nct, MkWatch& w) {
     mk_bar_sync(1, nct);
     if (ctid == 0 && !w.dead) {
-        const unsigned int gen = mk_ld_acquire(p.barrier + 1);
-        __threadfence();
-        const unsigned int old = atomicAdd(p.barrier, 1u);
-        if (old == gridDim.x - 1) {
-            p.barrier[0] = 0u;
-            __threadfence();
-            mk_st_release(p.barrier + 1, gen + 1u);
-        } else {
-            const long long t0 = clock64();
-            uint32_t spins = 0;
-            while (mk_ld_acquire(p.barrier + 1) == gen) {
-                if ((++spins & 63u) == 0u) {
-                    if (w.poll_dead()) break;
-                    if (clock64() - t0 > MK_TIMEOUT_CLOCKS) { w.fail(0x100u); break; }
-                }
+        const unsigned long long target = p.barrier_base + (unsigned long long)(index + 1) * gridDim.x;
+        asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(p.barrier) : "memory");
+        const long long t0 = clock64();
+        uint32_t spins = 0;
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p.barrier) : "memory");
+            if (v >= target) break;
+            if ((++spins & 63u) == 0u) {
+                if (w.poll_dead()) break;
+                if (clock64() - t0 > MK_TIMEOUT_CLOCKS) { w.fail(0x100u); break; }
             }
         }
-        __threadfence();
     }
     mk_bar_sync(1, nct);
-    w.poll_dead();
 }
 
 __device__ __forceinline__ void mk_mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -130,25 +142,30 @@ __device__ __forceinline__ uint32_t mk_nib_pair(uint32_t w, int shift, uint32_t 
 // ---------------------------------------------------------------------------------------------------------------------------------
 // pieces
 // ---------------------------------------------------------------------------------------------------------------------------------
-// bf16-rounded matmul output rows [row, row + 4) (row % 4 == 0): sum of the tile's pieces in piece order, one RNE rounding
-__device__ __forceinline__ float4 mk_rows4(const MkPieces& pc, uint32_t row) {
+// bf16-rounded matmul output rows [row, row + 4) (row % 4 == 0): sum of the tile's P piece slots in slot order (unused slots hold zeros),
+// one RNE rounding. All P loads are independent: one L2 round trip.
+__device__ __forceinline__ float4 mk_rows4_raw(const MkPieces& pc, uint32_t row) {
     const uint32_t tile = row >> 4, r = row & 15u;
-    const uint32_t cnt = pc.count[tile];
     const float4* base = reinterpret_cast<const float4*>(pc.pieces + ((size_t)tile * pc.P) * 16 + r);
     float4 s = __ldcg(base);
-    for (uint32_t q = 1; q < cnt; ++q) {
+#pragma unroll 4
+    for (uint32_t q = 1; q < pc.P; ++q) {
         const float4 v = __ldcg(base + (size_t)q * 4);
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
+    return s;
+}
+__device__ __forceinline__ float4 mk_rows4(const MkPieces& pc, uint32_t row) {
+    float4 s = mk_rows4_raw(pc, row);
     s.x = round_bf16(s.x); s.y = round_bf16(s.y); s.z = round_bf16(s.z); s.w = round_bf16(s.w);
     return s;
 }
 __device__ __forceinline__ float mk_row1(const MkPieces& pc, uint32_t row) {
     const uint32_t tile = row >> 4, r = row & 15u;
-    const uint32_t cnt = pc.count[tile];
     const float* base = pc.pieces + ((size_t)tile * pc.P) * 16 + r;
     float s = __ldcg(base);
-    for (uint32_t q = 1; q < cnt; ++q) s += __ldcg(base + (size_t)q * 16);
+#pragma unroll 4
+    for (uint32_t q = 1; q < pc.P; ++q) s += __ldcg(base + (size_t)q * 16);
     return round_bf16(s);
 }
 // eight consecutive bf16-rounded rows packed as 4 x bf16x2 (row % 8 == 0)
@@ -199,10 +216,13 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) decode_mega_kernel(const Mk
     __shared__ float red[NCW + 4];
     __shared__ unsigned long long redk[NCW];
     __shared__ unsigned int sm_ticket;
+    // phase descriptors are staged in shared memory one phase ahead: every field read of a phase is a shared-memory access instead of a
+    // chain of first-touch global loads (measured: ~3 us per phase before this)
+    __shared__ MkOp sops[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t W = gridDim.x * NCW;
-    MkWatch watch{p.error_flag, false};
+    MkWatch watch{reinterpret_cast<unsigned int*>(p.barrier + 1), p.error_flag, false};
 
     if (tid == 0) {
         for (int i = 0; i < NCW * S; ++i) {
@@ -215,28 +235,54 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) decode_mega_kernel(const Mk
 
     if (warp == NCW) {
         // ================================================= producer warp ====================================================
-        // lane l feeds consumer warp l: the same walk over (GEMV phase, range) the consumer does, S stages ahead at most
-        if (lane < NCW) {
-            uint32_t q = 0;                                   // unit sequence number of this consumer warp (across phases)
-            const uint32_t full0 = mk_smem_u32(bars + lane * S), empty0 = mk_smem_u32(bars + NCW * S + lane * S);
-            const uint32_t ring0 = mk_smem_u32(ring + (size_t)lane * S * MK_STAGE_BYTES);
-            for (uint32_t oi = 0; oi < p.nops && !watch.dead; ++oi) {
-                const MkOp* op = p.ops + oi;
-                if (op->kind != MK_GEMV) continue;
-                uint32_t ri, weff, u, ue;
-                mk_my_range(blockIdx.x, lane, op->units, W, ri, weff, u, ue);
-                while (u < ue && !watch.dead) {
-                    const int mi = (op->nmat > 1 && u >= op->mat[1].unit0) ? 1 : 0;
-                    const uint32_t mend = min(ue, op->mat[mi].unit0 + op->mat[mi].tiles * op->mat[mi].C);
-                    const uint8_t* src = op->mat[mi].stream + (size_t)(u - op->mat[mi].unit0) * MK_STAGE_BYTES;
-                    for (; u < mend && !watch.dead; ++u, ++q, src += MK_STAGE_BYTES) {
-                        const uint32_t s = q % S, ph = (q / S) & 1u;
-                        mk_wait(empty0 + s * 8u, ph ^ 1u, watch, 0x200u);
-                        if (watch.dead) break;
-                        mk_mbar_expect_tx(full0 + s * 8u, MK_STAGE_BYTES);
-                        mk_bulk_copy(ring0 + s * MK_STAGE_BYTES, src, MK_STAGE_BYTES, full0 + s * 8u);
+        // lane l feeds consumer warp l: the same walk over (GEMV phase, range) the consumer does, S stages ahead at most. The lanes
+        // stay converged in ONE polling loop with a non-blocking mbarrier test: a lane whose ring is full (its consumer is parked at a
+        // grid barrier) must not stall the lanes whose rings have room -- that is exactly when the next phase's weights are prefetched.
+        const bool active = lane < NCW;
+        uint32_t q = 0;                                       // unit sequence number of this consumer warp (across phases)
+        const uint32_t full0 = mk_smem_u32(bars + (active ? lane : 0) * S), empty0 = mk_smem_u32(bars + NCW * S + (active ? lane : 0) * S);
+        const uint32_t ring0 = mk_smem_u32(ring + (size_t)(active ? lane : 0) * S * MK_STAGE_BYTES);
+        uint32_t oi = 0, u = 0, ue = 0, mend = 0;
+        const uint8_t* src = nullptr;
+        bool done = !active;
+        auto load_op = [&](uint32_t from) {       // first GEMV phase at index >= from in which this consumer warp owns units
+            for (oi = from; oi < p.nops; ++oi) {
+                if (p.ops[oi].kind != MK_GEMV) continue;
+                uint32_t ri, weff;
+                mk_my_range(blockIdx.x, lane, p.ops[oi].units, W, ri, weff, u, ue);
+                if (u < ue) return true;
+            }
+            return false;
+        };
+        auto load_segment = [&]() {               // the part of [u, ue) that lies in one matrix: one contiguous byte range of its stream
+            const MkOp* op = p.ops + oi;
+            const int mi = (op->nmat > 1 && u >= op->mat[1].unit0) ? 1 : 0;
+            mend = min(ue, op->mat[mi].unit0 + op->mat[mi].tiles * op->mat[mi].C);
+            src = op->mat[mi].stream + (size_t)(u - op->mat[mi].unit0) * MK_STAGE_BYTES;
+        };
+        if (active) {
+            if (load_op(0)) load_segment();
+            else done = true;
+        }
+        const uint64_t policy = mk_evict_first_policy();
+        const long long t0 = clock64();
+        uint32_t spins = 0;
+        while (__any_sync(0xffffffffu, !done)) {
+            if (!done) {
+                const uint32_t s = q % S, ph = (q / S) & 1u;
+                if (mk_mbar_test_wait(empty0 + s * 8u, ph ^ 1u)) {
+                    mk_mbar_expect_tx(full0 + s * 8u, MK_STAGE_BYTES);
+                    mk_bulk_copy(ring0 + s * MK_STAGE_BYTES, src, MK_STAGE_BYTES, full0 + s * 8u, policy);
+                    ++q; ++u; src += MK_STAGE_BYTES;
+                    if (u >= mend) {
+                        if (u >= ue && !load_op(oi + 1)) done = true;
+                        if (!done) load_segment();
                     }
                 }
+            }
+            if ((++spins & 1023u) == 0u) {
+                if (watch.poll_dead()) done = true;
+                else if (clock64() - t0 > 8 * MK_TIMEOUT_CLOCKS) { watch.fail(0x200u); done = true; }   // a whole step never takes this long
             }
         }
         return;
@@ -257,8 +303,16 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) decode_mega_kernel(const Mk
     const int b_chunk = CPM == 2 ? (g >> 1) : g;
     const bool b_lane = CPM == 2 ? ((g & 1) == (t >> 1)) : true;
 
+#define MK_TRACE(k) do { if (p.trace && blockIdx.x == p.trace_cta && tid == 0) p.trace[(size_t)oi * 4 + (k)] = (unsigned long long)clock64(); } while (0)
+    constexpr int OPV = (int)(sizeof(MkOp) / 16);
+    if (tid < OPV) reinterpret_cast<uint4*>(&sops[0])[tid] = __ldg(reinterpret_cast<const uint4*>(p.ops) + tid);
+    mk_bar_sync(2, NCT);
     for (uint32_t oi = 0; oi < p.nops; ++oi) {
-        const MkOp& op = p.ops[oi];
+        const MkOp& op = sops[oi & 1];
+        // next phase's descriptor: its buffer was last read in phase oi - 1, which every thread left before the previous grid barrier;
+        // the CTA-wide sync inside this phase's grid barrier publishes it
+        if (oi + 1 < p.nops && tid >= NCT - OPV) reinterpret_cast<uint4*>(&sops[(oi + 1) & 1])[tid - (NCT - OPV)] = __ldg(reinterpret_cast<const uint4*>(p.ops + oi + 1) + (tid - (NCT - OPV)));
+        MK_TRACE(0);
         switch (op.kind) {
         case MK_GEMV: {
             // ---------------- stage the activation row (every CTA: the row is <= 32 KB) ----------------------------------------
@@ -275,6 +329,22 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) decode_mega_kernel(const Mk
             uint4 vals[MAXO];
             const uint32_t in_kind = op.in_kind, src_kind = op.src_kind;
             if (tid < 4) xs[items_all + tid] = make_uint4(0, 0, 0, 0);
+            if (op.dn_commit) {
+                // side job: advance the rolling conv state of the DeltaNet layer whose update phase just finished (every reader of the
+                // old state is behind the grid barrier): state[t - 1] = state[t], state[last] = x (conv_update.rs:40-55)
+                const uint32_t conv_dim = 2 * op.dn_key_dim + op.dn_value_dim, taps = op.dn_kernel_size - 1;
+                for (uint32_t ch = blockIdx.x + gridDim.x * tid; ch < conv_dim; ch += gridDim.x * NCT) {
+                    const float x = mk_row1(op.dn_in_pc, ch);
+                    float* st = op.dn_conv_state + (size_t)ch * taps;
+                    float prev[7];
+#pragma unroll
+                    for (uint32_t tp = 1; tp < 7; ++tp) prev[tp] = tp < taps ? st[tp] : 0.0f;
+#pragma unroll
+                    for (uint32_t tp = 1; tp < 7; ++tp)
+                        if (tp < taps) st[tp - 1] = prev[tp];
+                    st[taps - 1] = x;
+                }
+            }
             // -- pass 1: the row before the (optional) normalisation, 8 elements per thread step
             float ssq = 0.0f;
 #pragma unroll
@@ -283,7 +353,20 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) decode_mega_kernel(const Mk
                 vals[r] = make_uint4(0, 0, 0, 0);
                 if (o >= octets_all || e0 >= K) continue;
                 uint4 v;
-                if (src_kind == MK_SRC_BF16) v = __ldcg(reinterpret_cast<const uint4*>(op.src_vec + e0));
+                if (in_kind == MK_IN_GATED) {
+                    // GatedActMul folded into the consumer: rows [0, F) of the fused up projection are `up`, rows [F, 2F) `gate`
+                    const float4 u0 = mk_rows4(op.gated_pc, e0), u1 = mk_rows4(op.gated_pc, e0 + 4);
+                    const float4 g0 = mk_rows4(op.gated_pc, K + e0), g1 = mk_rows4(op.gated_pc, K + e0 + 4);
+                    const float uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w}, gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                    float hh[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) hh[i] = __fmul_rn(uu[i], round_bf16(act_f32_nofma(op.gated_act, gg[i])));
+                    __nv_bfloat162 tt;
+                    tt = __floats2bfloat162_rn(hh[0], hh[1]); v.x = *reinterpret_cast<uint32_t*>(&tt);
+                    tt = __floats2bfloat162_rn(hh[2], hh[3]); v.y = *reinterpret_cast<uint32_t*>(&tt);
+                    tt = __floats2bfloat162_rn(hh[4], hh[5]); v.z = *reinterpret_cast<uint32_t*>(&tt);
+                    tt = __floats2bfloat162_rn(hh[6], hh[7]); v.w = *reinterpret_cast<uint32_t*>(&tt);
+                } else if (src_kind == MK_SRC_BF16) v = __ldcg(reinterpret_cast<const uint4*>(op.src_vec + e0));
                 else if (src_kind == MK_SRC_PIECES) v = mk_rows8_bf16(op.src_pc, op.src_row0 + e0);
                 else {
                     // embedding row of the input token (quant_embedding_lookup_kernel / fp_embedding_lookup_kernel arithmetic)
@@ -439,6 +522,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) decode_mega_kernel(const Mk
                 if ((o & (OPG - 1)) == 0 && gl < ngroups) sx[gl] = part;
             }
             mk_bar_sync(2, NCT);
+            MK_TRACE(1);
 
             // ---------------- this warp's contiguous range of units -------------------------------------------------------------
             const uint64_t U = op.units;
@@ -516,67 +600,84 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) decode_mega_kernel(const Mk
             }
             break;
         }
-        case MK_PREP: {
-            // QKVNorm(q) + QKVNorm(k) + AttentionPrepare (qkv_norm.rs:36-76, attention_prepare.rs:34-126): one warp per head
-            const uint32_t Hq = op.num_q_heads, Hkv = op.num_kv_heads, D = op.head_dim;
-            const float* cosr = op.rope_cos ? op.rope_cos + (size_t)position * op.rope_dim : nullptr;
-            const float* sinr = op.rope_sin ? op.rope_sin + (size_t)position * op.rope_dim : nullptr;
-            for (uint32_t h = gw; h < Hq + 2 * Hkv; h += W) {
-                const bool is_q = h < Hq, is_k = !is_q && h < Hq + Hkv;
-                const float* nscales = is_q ? op.qnorm_scales : op.knorm_scales;
-                const bool normed = (is_q && op.qnorm_present) || (is_k && op.knorm_present);
-                const float eps = is_q ? op.qnorm_eps : op.knorm_eps, offs = is_q ? op.qnorm_offset : op.knorm_offset;
-                const uint32_t full = is_q ? op.qnorm_full_layer : op.knorm_full_layer, has_sc = is_q ? op.qnorm_has_scales : op.knorm_has_scales;
-                float rms = 0.0f;
-                if (normed) {
-                    float total = 0.0f;
-                    for (uint32_t i = lane; i < D; i += 32) {
-                        const float v = mk_row1(op.qkv_pc, h * D + i);
-                        total = __fadd_rn(total, __fmul_rn(v, v));
-                    }
-                    total = warp_sum(total);
-                    rms = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn(total, (float)D), eps)));
-                }
-                auto element = [&](uint32_t dd) {   // the bf16 row value RoPE reads
-                    float r = mk_row1(op.qkv_pc, h * D + dd);
-                    if (normed) {
-                        const float normalized = __fmul_rn(r, rms);
-                        if (!has_sc) r = round_bf16(normalized);
-                        else if (full) r = round_bf16(__fmul_rn(normalized, __fadd_rn(nscales[dd], offs)));
-                        else r = round_bf16(__fmul_rn(round_bf16(normalized), round_bf16(__fadd_rn(nscales[dd], offs))));
-                    }
-                    return r;
-                };
-                for (uint32_t dd = lane; dd < D; dd += 32) {
-                    float e = element(dd);
-                    if (cosr && dd < op.rope_dim && (is_q || is_k)) {
-                        const uint32_t half = op.rope_dim / 2;
-                        const uint32_t paired = dd < half ? dd + half : dd - half;
-                        const float pv = element(paired);
-                        const float signed_p = dd < half ? -pv : pv;
-                        e = round_bf16(__fadd_rn(__fmul_rn(e, cosr[dd]), __fmul_rn(signed_p, sinr[dd])));
-                    }
-                    const __nv_bfloat16 eb = f2bf(e);
-                    if (is_q) op.queries[(size_t)h * D + dd] = eb;
-                    else if (is_k) op.keys[((size_t)position * Hkv + (h - Hq)) * D + dd] = eb;
-                    else op.values[((size_t)position * Hkv + (h - Hq - Hkv)) * D + dd] = eb;
-                }
-            }
-            break;
-        }
         case MK_ATTN: {
-            // Decode attention over keys [0, position] (attention_single_pass.rs:49-126 arithmetic: q pre-scaled in f32, expf, f32
-            // accumulators; plain causal decode: every cached key is visible). CTAs per kv head = gridDim / Hkv; a CTA owns one
-            // contiguous key range of one kv head for all G query heads; lane groups of D / 8 lanes own one key row each.
+            // QKVNorm + RoPE + KV append (qkv_norm.rs:36-76, attention_prepare.rs:34-126) folded into decode attention over keys
+            // [0, position] (attention_single_pass.rs:49-126 arithmetic: bf16 q pre-scaled in f32, expf, f32 accumulators; plain causal
+            // decode: every cached key is visible). CTAs per kv head = gridDim / Hkv; a CTA owns one contiguous key range of one kv head
+            // for all G query heads; lane groups of D / 8 lanes own one key row each. The CTA that owns the LAST range appends the new
+            // K / V rows to the cache before its key loop (it is the only reader of that row).
             const uint32_t Hq = op.num_q_heads, Hkv = op.num_kv_heads, D = op.head_dim, G = Hq / Hkv;
             const uint32_t seq = position + 1;
             const uint32_t cph = gridDim.x / Hkv;
             const uint32_t LPK = D / 8, KPW = 32 / LPK;
             const uint32_t step_keys = NCW * KPW;
-            const uint32_t kp = ((seq + cph - 1) / cph + step_keys - 1) / step_keys * step_keys;    // keys per CTA part: whole CTA steps
+            // keys per CTA part: whole CTA steps, at least four per warp (one full batch of loads in flight): short contexts use few CTAs
+            // per kv head instead of many tiny parts whose merge would dominate
+            const uint32_t kp = max(((seq + cph - 1) / cph + step_keys - 1) / step_keys, 4u) * step_keys;
             const uint32_t nparts = (seq + kp - 1) / kp;
             const uint32_t kvh = blockIdx.x / cph, part = blockIdx.x % cph;
             if (blockIdx.x >= cph * Hkv || part >= nparts) break;
+            float* sq = reinterpret_cast<float*>(scratch);               // [G][D] scaled queries, later reused by the warp merge
+            {
+                // warp w < G: query head kvh * G + w; the last part's warps G and G + 1: the new key / value rows
+                const bool last_part = part == nparts - 1;
+                const uint32_t role = (uint32_t)warp;
+                if (role < G || (last_part && role < G + 2)) {
+                    const bool is_q = role < G, is_k = role == G;
+                    const uint32_t h = is_q ? kvh * G + role : (is_k ? Hq + kvh : Hq + Hkv + kvh);
+                    const bool normed = (is_q && op.qnorm_present) || (is_k && op.knorm_present);
+                    const float* nscales = is_q ? op.qnorm_scales : op.knorm_scales;
+                    const float eps = is_q ? op.qnorm_eps : op.knorm_eps, offs = is_q ? op.qnorm_offset : op.knorm_offset;
+                    const uint32_t full = is_q ? op.qnorm_full_layer : op.knorm_full_layer, has_sc = is_q ? op.qnorm_has_scales : op.knorm_has_scales;
+                    const bool roped = op.rope_cos != nullptr && (is_q || is_k);
+                    const uint32_t rd = op.rope_dim, half = rd / 2;
+                    constexpr int EPT = 8;                               // D <= 256: elements dd = lane + 32 i
+                    float ev[EPT], pv[EPT];
+                    // every load of this head first (one L2 round trip), then the arithmetic
+#pragma unroll
+                    for (int i = 0; i < EPT; ++i) {
+                        const uint32_t dd = lane + 32 * i;
+                        ev[i] = 0.0f; pv[i] = 0.0f;
+                        if (dd < D) {
+                            ev[i] = mk_row1(op.qkv_pc, h * D + dd);
+                            if (roped && dd < rd) pv[i] = mk_row1(op.qkv_pc, h * D + (dd < half ? dd + half : dd - half));
+                        }
+                    }
+                    float rms = 0.0f;
+                    if (normed) {
+                        float total = 0.0f;
+#pragma unroll
+                        for (int i = 0; i < EPT; ++i) total = __fadd_rn(total, __fmul_rn(ev[i], ev[i]));   // lane-strided, then the xor tree: the standalone kernel's order
+                        total = warp_sum(total);
+                        rms = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn(total, (float)D), eps)));
+                    }
+                    auto normalise = [&](float r, uint32_t dd) {
+                        const float normalized = __fmul_rn(r, rms);
+                        if (!has_sc) return round_bf16(normalized);
+                        if (full) return round_bf16(__fmul_rn(normalized, __fadd_rn(nscales[dd], offs)));
+                        return round_bf16(__fmul_rn(round_bf16(normalized), round_bf16(__fadd_rn(nscales[dd], offs))));
+                    };
+                    const float* cosr = roped ? op.rope_cos + (size_t)position * rd : nullptr;
+                    const float* sinr = roped ? op.rope_sin + (size_t)position * rd : nullptr;
+#pragma unroll
+                    for (int i = 0; i < EPT; ++i) {
+                        const uint32_t dd = lane + 32 * i;
+                        if (dd >= D) continue;
+                        float e = ev[i];
+                        if (normed) e = normalise(e, dd);
+                        if (roped && dd < rd) {
+                            float pr = pv[i];
+                            if (normed) pr = normalise(pr, dd < half ? dd + half : dd - half);
+                            const float signed_p = dd < half ? -pr : pr;
+                            e = round_bf16(__fadd_rn(__fmul_rn(e, cosr[dd]), __fmul_rn(signed_p, sinr[dd])));
+                        }
+                        if (is_q) sq[role * D + dd] = __fmul_rn(op.attn_scale, e);
+                        else if (is_k) op.keys[((size_t)position * Hkv + kvh) * D + dd] = f2bf(e);
+                        else op.values[((size_t)position * Hkv + kvh) * D + dd] = f2bf(e);
+                    }
+                }
+            }
+            mk_bar_sync(2, NCT);
             const uint32_t sub = lane / LPK, li = lane % LPK, d0 = li * 8;
             const uint32_t kbeg = part * kp, kend = min(seq, kbeg + kp);
             constexpr int MAXG = 4;       // query heads per kv head held in registers (the host rejects larger groups)
@@ -587,16 +688,15 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) decode_mega_kernel(const Mk
 #pragma unroll
                 for (int e = 0; e < 8; ++e) { o[h][e] = 0.0f; qf[h][e] = 0.0f; }
                 if ((uint32_t)h < G) {
-                    const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(op.queries + ((size_t)(kvh * G + h)) * D + d0));
-                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { qf[h][2 * e] = __fmul_rn(op.attn_scale, __low2float(h2[e])); qf[h][2 * e + 1] = __fmul_rn(op.attn_scale, __high2float(h2[e])); }
+                    const float4 qa = *reinterpret_cast<const float4*>(sq + h * D + d0), qb = *reinterpret_cast<const float4*>(sq + h * D + d0 + 4);
+                    qf[h][0] = qa.x; qf[h][1] = qa.y; qf[h][2] = qa.z; qf[h][3] = qa.w; qf[h][4] = qb.x; qf[h][5] = qb.y; qf[h][6] = qb.z; qf[h][7] = qb.w;
                 }
             }
+            mk_bar_sync(2, NCT);                                       // sq is reused below
             const __nv_bfloat16* kbase = op.keys + (size_t)kvh * D + d0;
             const __nv_bfloat16* vbase = op.values + (size_t)kvh * D + d0;
             const size_t rstride = (size_t)Hkv * D;
-            constexpr int UU = 2;     // key rows in flight per lane group
+            constexpr int UU = 4;     // key rows in flight per lane group (all loads of a batch are issued before any is consumed)
             // the loop bound is warp-uniform (the lane groups of a warp run in lockstep: the shuffles below need every lane);
             // rows past the end of the range are masked with ok[]
             for (uint32_t kb = kbeg + warp * KPW; kb < kend; kb += step_keys * UU) {
@@ -629,11 +729,11 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) decode_mega_kernel(const Mk
                         if (ok[u_]) {
                             const float mnew = fmaxf(mrun[h], sdot);
                             const float factor = (mrun[h] == -INFINITY) ? 0.0f : expf(mrun[h] - mnew);
-                            const float pv = expf(sdot - mnew);
-                            lrun[h] = lrun[h] * factor + pv;
+                            const float pv_ = expf(sdot - mnew);
+                            lrun[h] = lrun[h] * factor + pv_;
                             mrun[h] = mnew;
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) o[h][e] = fmaf(pv, vf[e], o[h][e] * factor);
+                            for (int e = 0; e < 8; ++e) o[h][e] = fmaf(pv_, vf[e], o[h][e] * factor);
                         }
                     }
                 }
@@ -672,17 +772,24 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) decode_mega_kernel(const Mk
             for (uint32_t idx = tid; idx < G * D; idx += NCT) {
                 const uint32_t h = idx / D, dd = idx % D;
                 float M = -INFINITY;
+#pragma unroll
                 for (int w_ = 0; w_ < NCW; ++w_) M = fmaxf(M, sml[((size_t)w_ * G + h) * 2]);
                 float L = 0.0f, O = 0.0f;
+#pragma unroll
                 for (int w_ = 0; w_ < NCW; ++w_) {
                     const float mw = sml[((size_t)w_ * G + h) * 2];
                     const float f = (mw == -INFINITY) ? 0.0f : expf(mw - M);
                     L += sml[((size_t)w_ * G + h) * 2 + 1] * f;
                     O += so[((size_t)w_ * G + h) * D + dd] * f;
                 }
-                pbase[(size_t)h * (D + 2) + dd] = O;
-                if (dd == 0) { pbase[(size_t)h * (D + 2) + D] = M; pbase[(size_t)h * (D + 2) + D + 1] = L; }
+                if (nparts == 1) {
+                    op.attn_out[((size_t)(kvh * G + h)) * D + dd] = f2bf(O / L);       // a single part: no cross-CTA merge
+                } else {
+                    pbase[(size_t)h * (D + 2) + dd] = O;
+                    if (dd == 0) { pbase[(size_t)h * (D + 2) + D] = M; pbase[(size_t)h * (D + 2) + D + 1] = L; }
+                }
             }
+            if (nparts == 1) break;
             // the last CTA of this kv head merges the parts (fixed order) and writes the bf16 attention output
             __threadfence();
             mk_bar_sync(2, NCT);
@@ -694,8 +801,10 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) decode_mega_kernel(const Mk
                 for (uint32_t idx = tid; idx < G * D; idx += NCT) {
                     const uint32_t h = idx / D, dd = idx % D;
                     float M = -INFINITY;
+#pragma unroll 8
                     for (uint32_t pi = 0; pi < nparts; ++pi) M = fmaxf(M, __ldcg(hb + ((size_t)pi * G + h) * (D + 2) + D));
                     float L = 0.0f, O = 0.0f;
+#pragma unroll 8
                     for (uint32_t pi = 0; pi < nparts; ++pi) {
                         const float* pp = hb + ((size_t)pi * G + h) * (D + 2);
                         const float f = expf(__ldcg(pp + D) - M);
@@ -711,7 +820,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) decode_mega_kernel(const Mk
         case MK_ACT: {
             // GatedActMul (gated_act_mul/mod.rs:5-12): hidden[j] = bf16(bf16(up_j) * bf16(act(bf16(gate_j)))), rows [0, F) up, [F, 2F) gate
             const uint32_t F = op.act_dim;
-            for (uint32_t j = (blockIdx.x * NCT + tid) * 4u; j < F; j += gridDim.x * NCT * 4u) {
+            for (uint32_t j = (blockIdx.x + gridDim.x * tid) * 4u; j < F; j += gridDim.x * NCT * 4u) {
                 const float4 up = mk_rows4(op.up_pc, j), gt = mk_rows4(op.up_pc, F + j);
                 const float m0 = round_bf16(act_f32_nofma(op.act_type, gt.x)), m1 = round_bf16(act_f32_nofma(op.act_type, gt.y));
                 const float m2 = round_bf16(act_f32_nofma(op.act_type, gt.z)), m3 = round_bf16(act_f32_nofma(op.act_type, gt.w));
@@ -722,89 +831,78 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) decode_mega_kernel(const Mk
             }
             break;
         }
-        case MK_DN_CONV: {
-            // DeltaNetConvUpdate (gdn/conv_update.rs:8-55) for all channels + L2-normalised q / k and k.q per k head (update.rs:60-80).
-            // Work items: k heads (a warp owns the head's 128 q and 128 k channels), then blocks of 128 v channels.
-            constexpr uint32_t DK = 128;
-            const uint32_t Hk = op.dn_num_k_heads, taps = op.dn_kernel_size - 1;
-            const uint32_t vblocks = op.dn_value_dim / DK;
-            auto conv = [&](uint32_t ch) {      // returns the bf16-rounded SiLU output, advances the rolling state
-                const float x = mk_row1(op.dn_in_pc, ch);
-                const float* wv = op.dn_conv_weight + (size_t)ch * op.dn_kernel_size;
-                float* st = op.dn_conv_state + (size_t)ch * taps;
-                float acc = op.dn_conv_bias ? op.dn_conv_bias[ch] : 0.0f;
-                float prev[7];
-#pragma unroll
-                for (uint32_t tp = 0; tp < 7; ++tp) {
-                    prev[tp] = 0.0f;
-                    if (tp < taps) { prev[tp] = st[tp]; acc = __fadd_rn(acc, __fmul_rn(prev[tp], wv[tp])); }
-                }
-                acc = __fadd_rn(acc, __fmul_rn(x, wv[taps]));
-#pragma unroll
-                for (uint32_t tp = 1; tp < 7; ++tp)
-                    if (tp < taps) st[tp - 1] = prev[tp];
-                st[taps - 1] = x;
-                return round_bf16(act_f32_nofma(UZU_ACT_SILU, acc));
-            };
-            for (uint32_t item = gw; item < Hk + vblocks; item += W) {
-                if (item < Hk) {
-                    float qv[4], kv[4], qn = 0.0f, kn = 0.0f;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        qv[i] = conv(item * DK + lane * 4 + i);
-                        kv[i] = conv(op.dn_key_dim + item * DK + lane * 4 + i);
-                        qn = __fadd_rn(qn, __fmul_rn(qv[i], qv[i]));
-                        kn = __fadd_rn(kn, __fmul_rn(kv[i], kv[i]));
-                    }
-                    qn = warp_sum(qn); kn = warp_sum(kn);
-                    const float qi = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(qn, 1e-6f))), ki = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(kn, 1e-6f)));
-                    const float qscale = __fdiv_rn(1.0f, __fsqrt_rn((float)DK));
-                    float kq = 0.0f;
-                    float4 qo, ko;
-                    float* qp = &qo.x;
-                    float* kp_ = &ko.x;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        qp[i] = __fmul_rn(__fmul_rn(qv[i], qi), qscale);
-                        kp_[i] = __fmul_rn(kv[i], ki);
-                        kq = __fadd_rn(kq, __fmul_rn(kp_[i], qp[i]));
-                    }
-                    kq = warp_sum(kq);
-                    *reinterpret_cast<float4*>(op.dn_qk + ((size_t)item * 2) * DK + lane * 4) = qo;
-                    *reinterpret_cast<float4*>(op.dn_qk + ((size_t)item * 2 + 1) * DK + lane * 4) = ko;
-                    if (lane == 0) op.dn_kq[item] = kq;
-                } else {
-                    const uint32_t vb = item - Hk;
-                    float4 vo;
-                    float* vp = &vo.x;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) vp[i] = conv(2 * op.dn_key_dim + vb * DK + lane * 4 + i);
-                    *reinterpret_cast<float4*>(op.dn_v + (size_t)vb * DK + lane * 4) = vo;
-                }
-            }
-            break;
-        }
         case MK_DN_UPDATE: {
-            // Gated delta rule (gdn/update.rs:82-118), one warp per state row [128] of S[Hv][Dv][128]; the raw output goes to dn_out_raw,
-            // the head RMS norm * silu(z) is applied by the consumer (MK_IN_DELTA staging of the out projection)
+            // DeltaNetConvUpdate (read-only: the rolling state is committed by the next phase's staging) + L2-normalised q / k + gated delta
+            // rule (gdn/conv_update.rs:8-55, gdn/update.rs:13-118). CTAs per v head = gridDim / Hv; a CTA owns a block of the head's Dv
+            // state rows (one warp per row); the raw output goes to dn_out_raw, the head RMS norm * silu(z) is applied by the consumer
+            // (MK_IN_DELTA staging of the out projection).
             constexpr uint32_t DK = 128;
             const uint32_t Hv = op.dn_num_v_heads, Dv = op.dn_hv_dim, Hk = op.dn_num_k_heads;
-            const uint32_t conv_dim = 2 * op.dn_key_dim + op.dn_value_dim;
-            for (uint32_t row = gw; row < Hv * Dv; row += W) {
-                const uint32_t hv = row / Dv, hk = hv / (Hv / Hk);
+            const uint32_t conv_dim = 2 * op.dn_key_dim + op.dn_value_dim, taps = op.dn_kernel_size - 1;
+            const uint32_t cph = gridDim.x / Hv;
+            const uint32_t hv = blockIdx.x / cph, part = blockIdx.x % cph;
+            if (blockIdx.x >= cph * Hv) break;
+            const uint32_t rows_per = (Dv + cph - 1) / cph;
+            const uint32_t r0 = part * rows_per, r1 = min(Dv, r0 + rows_per);
+            if (r0 >= r1) break;
+            const uint32_t hk = hv / (Hv / Hk);
+            float* sqk = reinterpret_cast<float*>(scratch);          // [2][128] conv outputs, then normalised q / k
+            float* sv = sqk + 2 * DK;                                // [rows of this CTA]
+            float* sred = sv + 256;                                  // [16] partial sums
+            auto conv = [&](uint32_t ch) {                           // bf16-rounded SiLU output of channel ch; the state is only read
+                const float x = mk_row1(op.dn_in_pc, ch);
+                const float* wv = op.dn_conv_weight + (size_t)ch * op.dn_kernel_size;
+                const float* st = op.dn_conv_state + (size_t)ch * taps;
+                float acc = op.dn_conv_bias ? op.dn_conv_bias[ch] : 0.0f;
+                const float wlast = wv[taps];
+                float sv_[7], wt[7];
+#pragma unroll
+                for (uint32_t tp = 0; tp < 7; ++tp) { sv_[tp] = tp < taps ? st[tp] : 0.0f; wt[tp] = tp < taps ? wv[tp] : 0.0f; }
+#pragma unroll
+                for (uint32_t tp = 0; tp < 7; ++tp)
+                    if (tp < taps) acc = __fadd_rn(acc, __fmul_rn(sv_[tp], wt[tp]));
+                acc = __fadd_rn(acc, __fmul_rn(x, wlast));
+                return round_bf16(act_f32_nofma(UZU_ACT_SILU, acc));
+            };
+            float mine = 0.0f;
+            if (tid < 2 * (int)DK) {
+                mine = conv(tid < (int)DK ? hk * DK + tid : op.dn_key_dim + hk * DK + (tid - DK));
+                sqk[tid] = mine;
+            } else if (tid - 2 * DK < r1 - r0) {
+                sv[tid - 2 * DK] = conv(2 * op.dn_key_dim + hv * Dv + r0 + (tid - 2 * DK));
+            }
+            // L2 norms over the 128 q values (warps 0..3) and the 128 k values (warps 4..7)
+            float sqv = warp_sum(__fmul_rn(mine, mine));
+            if (lane == 0 && warp < 8) sred[warp] = sqv;
+            mk_bar_sync(2, NCT);
+            const float qn = __fadd_rn(__fadd_rn(sred[0], sred[1]), __fadd_rn(sred[2], sred[3]));
+            const float kn = __fadd_rn(__fadd_rn(sred[4], sred[5]), __fadd_rn(sred[6], sred[7]));
+            const float qi = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(qn, 1e-6f))), ki = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(kn, 1e-6f)));
+            const float qscale = __fdiv_rn(1.0f, __fsqrt_rn((float)DK));
+            mk_bar_sync(2, NCT);                                     // everyone has read sred before it is reused
+            float kqp = 0.0f;
+            if (tid < (int)DK) {
+                const float qq = __fmul_rn(__fmul_rn(sqk[tid], qi), qscale), kk = __fmul_rn(sqk[DK + tid], ki);
+                kqp = __fmul_rn(kk, qq);
+                sqk[tid] = qq; sqk[DK + tid] = kk;
+            }
+            kqp = warp_sum(kqp);
+            if (lane == 0 && warp < 4) sred[8 + warp] = kqp;
+            mk_bar_sync(2, NCT);
+            const float kq = __fadd_rn(__fadd_rn(sred[8], sred[9]), __fadd_rn(sred[10], sred[11]));
+            const float beta_raw = mk_row1(op.dn_in_pc, conv_dim + op.dn_value_dim + hv);
+            const float a_raw = mk_row1(op.dn_in_pc, conv_dim + op.dn_value_dim + Hv + hv);
+            const float beta = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-beta_raw)));
+            const float sp_in = __fadd_rn(a_raw, op.dn_dt_bias[hv]);
+            const float sp = sp_in > 20.0f ? sp_in : logf(__fadd_rn(1.0f, expf(sp_in)));
+            const float gdec = __fmul_rn(-expf(op.dn_a_log[hv]), sp);
+            const float decay = expf(gdec);
+            const float4 q4 = *(reinterpret_cast<const float4*>(sqk) + lane), k4 = *(reinterpret_cast<const float4*>(sqk + DK) + lane);
+            for (uint32_t r = r0 + warp; r < r1; r += NCW) {
+                const uint32_t row = hv * Dv + r;
                 float* srow = op.dn_state + (size_t)row * DK;
                 const float4 s = *(reinterpret_cast<const float4*>(srow) + lane);
-                const float4 q4 = __ldcg(reinterpret_cast<const float4*>(op.dn_qk + ((size_t)hk * 2) * DK) + lane);
-                const float4 k4 = __ldcg(reinterpret_cast<const float4*>(op.dn_qk + ((size_t)hk * 2 + 1) * DK) + lane);
-                const float kq = __ldcg(op.dn_kq + hk);
-                const float v_i = __ldcg(op.dn_v + row);
-                const float beta_raw = mk_row1(op.dn_in_pc, conv_dim + op.dn_value_dim + hv);
-                const float beta = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-beta_raw)));
-                const float a_raw = mk_row1(op.dn_in_pc, conv_dim + op.dn_value_dim + Hv + hv);
-                const float sp_in = __fadd_rn(a_raw, op.dn_dt_bias[hv]);
-                const float sp = sp_in > 20.0f ? sp_in : logf(__fadd_rn(1.0f, expf(sp_in)));
-                const float gdec = __fmul_rn(-expf(op.dn_a_log[hv]), sp);
-                const float decay = expf(gdec);
+                const float v_i = sv[r - r0];
                 float sqa = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s.x, q4.x), __fmul_rn(s.y, q4.y)), __fmul_rn(s.z, q4.z)), __fmul_rn(s.w, q4.w));
                 float ska = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s.x, k4.x), __fmul_rn(s.y, k4.y)), __fmul_rn(s.z, k4.z)), __fmul_rn(s.w, k4.w));
                 sqa = warp_sum(sqa);
@@ -877,8 +975,11 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) decode_mega_kernel(const Mk
         }
         default: break;
         }
-        if (op.kind != MK_FINISH) mk_grid_sync(p, tid, NCT, watch);
+        MK_TRACE(2);
+        if (op.kind != MK_FINISH) mk_grid_sync(p, oi, tid, NCT, watch);
+        MK_TRACE(3);
     }
+#undef MK_TRACE
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------
@@ -972,7 +1073,7 @@ static const char* launch_variant(uzu_context* ctx, const MegaConfig& cfg, const
     const uint64_t bit = 1ull << (ctx->device & 63);
     make_current(ctx);
     if (!(done.load(std::memory_order_acquire) & bit)) {
-        cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<NPG, BITS, NCW, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+        cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<NPG, BITS, NCW, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);
         if (e != cudaSuccess) return cudaGetErrorString(e);
         done.fetch_or(bit, std::memory_order_release);
     }
@@ -1006,7 +1107,7 @@ bool mega_config(uzu_context* ctx, uint32_t npg, uint32_t bits, uint32_t scratch
     c.grid = (uint32_t)ctx->sm_count;
     c.scratch_bytes = (scratch_bytes + 127u) & ~127u;
     c.smem_bytes = c.scratch_bytes + ((2u * c.ncw * c.stages * 8u + 127u) & ~127u) + (size_t)c.ncw * c.stages * MK_STAGE_BYTES;
-    if (c.smem_bytes > 227u * 1024u - 2048u) return false;
+    if (c.smem_bytes > 227u * 1024u - 4096u) return false;
     *out = c;
     return true;
 }

@@ -11,15 +11,16 @@ namespace uzu {
 constexpr uint32_t MK_STAGE_BYTES = 4608;     // one unit: 16 rows x 256 packed bytes (4096 B) + 512 B of per-group coefficients
 constexpr uint32_t MK_MAX_MATS = 2;
 
-enum MkKind : uint32_t { MK_GEMV = 1, MK_PREP = 2, MK_ATTN = 3, MK_ACT = 4, MK_DN_CONV = 5, MK_DN_UPDATE = 6, MK_LOGITS = 7, MK_FINISH = 8 };
-enum MkInput : uint32_t { MK_IN_PLAIN = 0, MK_IN_NORM = 1, MK_IN_SIGMOID = 2, MK_IN_DELTA = 3 };
+enum MkKind : uint32_t { MK_GEMV = 1, MK_ATTN = 3, MK_ACT = 4, MK_DN_UPDATE = 6, MK_LOGITS = 7, MK_FINISH = 8 };
+enum MkInput : uint32_t { MK_IN_PLAIN = 0, MK_IN_NORM = 1, MK_IN_SIGMOID = 2, MK_IN_DELTA = 3, MK_IN_GATED = 4 };
 enum MkSource : uint32_t { MK_SRC_BF16 = 0, MK_SRC_PIECES = 1, MK_SRC_EMBED = 2 };
 
 // Output of a streamed GEMV: every (tile, warp range) intersection leaves one partial sum of the tile's 16 rows ("piece").
-// Row r of the matmul output = bf16( sum_{p < count[r / 16]} pieces[((r / 16) * P + p) * 16 + r % 16] ), summed in piece order.
+// Row r of the matmul output = bf16( sum_{p < P} pieces[((r / 16) * P + p) * 16 + r % 16] ), summed in slot order. The partition is static,
+// so the slots a tile does not use are never written: they keep the zeros of the initial memset and the consumers need no per-tile count
+// (one dependent load less on the critical path of every phase).
 struct MkPieces {
     const float* pieces;
-    const uint8_t* count;     // pieces per tile (static: depends on the partition only)
     uint32_t P;               // piece slots per tile
     uint32_t pad;
 };
@@ -41,7 +42,7 @@ struct MkEmbed {              // quantised / full-precision input embedding row 
     float input_scale;
 };
 
-struct MkOp {
+struct alignas(16) MkOp {
     uint32_t kind, pad0;
     // ---- MK_GEMV -----------------------------------------------------------------------------------------------------------
     uint32_t nmat, units;
@@ -60,6 +61,11 @@ struct MkOp {
     uint32_t norm_residual_add, norm_full_layer;
     // MK_IN_SIGMOID (sigmoid_gate.rs:7-22): x = src_vec * sigmoid(gate row), gate row from pieces
     MkPieces gate_pc;
+    // MK_IN_GATED (gated_act_mul/mod.rs:5-12): x[j] = bf16(bf16(up_j) * bf16(act(bf16(gate_j)))), rows [0, F) up / [F, 2F) gate of gated_pc
+    MkPieces gated_pc;
+    uint32_t gated_act, pad5;
+    // optional side job of the staging: commit the rolling conv state of the previous MK_DN_UPDATE phase (dn_* fields below)
+    uint32_t dn_commit, pad6;
     // MK_IN_DELTA (gdn/update.rs:120-144): x = raw * inv_rms(head) * norm_weight * silu(z)
     const float* dn_raw;           // [Hv * Dv] f32 written by MK_DN_UPDATE
     const float* dn_norm_weight;   // [Dv]
@@ -96,9 +102,6 @@ struct MkOp {
     const float* dn_a_log;
     const float* dn_dt_bias;
     float* dn_state;               // [Hv][Dv][128]
-    float* dn_qk;                  // scratch [Hk][2][128] normalised q, k
-    float* dn_kq;                  // scratch [Hk]
-    float* dn_v;                   // scratch [value_dim]
     float* dn_out_raw;             // [Hv * Dv]
     uint32_t dn_kernel_size, dn_key_dim, dn_value_dim, dn_num_k_heads, dn_num_v_heads, dn_hv_dim;
     // ---- MK_LOGITS / MK_FINISH ------------------------------------------------------------------------------------------------
@@ -107,6 +110,8 @@ struct MkOp {
     uint32_t vocab, pad4;
     unsigned long long* argmax_keys;   // [grid]
 };
+
+static_assert(sizeof(MkOp) % 16 == 0 && sizeof(MkOp) <= 1024, "MkOp is copied to shared memory in 16-byte pieces");
 
 struct MkStepState {               // == engine.cu's DecodeState
     uint32_t position, step;
@@ -117,8 +122,9 @@ struct MkParams {
     const MkOp* ops;
     uint32_t nops, ncw;            // consumer warps per CTA the program was partitioned for
     MkStepState* state;
-    unsigned int* barrier;         // [0] arrivals, [1] generation
-    unsigned int* error_flag;      // set when a spin loop times out (the kernel bails out instead of hanging the GPU)
+    unsigned long long* barrier;   // [0] monotonic arrival counter (never reset: launch k's barrier b completes at barrier_base + (b + 1) * grid), [1] low word = device-side error flag polled by the spin loops
+    unsigned long long barrier_base;
+    unsigned int* error_flag;      // pinned host mirror of the error flag, written only when a spin loop times out (the kernel drains instead of hanging)
     const uint32_t* token_ids;     // [1] input token (device-chained)
     uint32_t* token_out;           // == token_ids (next input)
     uint32_t* sampled;
@@ -127,6 +133,8 @@ struct MkParams {
     uint32_t dev_out_base_step, token_ring;
     uint32_t scratch_bytes;        // shared-memory scratch (activation row / attention merge) carved in front of the rings
     uint32_t stages;
+    unsigned long long* trace;     // debug: [nops][4] SM clock stamps of CTA trace_cta (op start, after staging, after body, after barrier) or null
+    uint32_t trace_cta, pad;
 };
 
 // decode_mega.cu

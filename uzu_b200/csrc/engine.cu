@@ -425,8 +425,9 @@ struct uzu_engine {
         std::string why;                 // why the model is not covered (diagnostics)
         uzu::MegaConfig cfg{};
         std::vector<uzu::MkOp> ops;
-        Buf ops_dev, barrier, error_flag, argmax_keys, attn_part, attn_tickets, dn_qk, dn_kq, dn_v, dn_raw;
+        Buf ops_dev, barrier, error_flag, argmax_keys, attn_part, attn_tickets, dn_raw;
         uint64_t stream_bytes = 0;
+        uint64_t barrier_base = 0;       // arrivals the monotonic grid-barrier counter has seen before the next launch
     } mega;
 };
 
@@ -1411,37 +1412,26 @@ struct MegaBuilder {
         for (uint32_t i = 0; i < nm; ++i) {
             MkMat& M = op.mat[i];
             need(M.k == op.k, "matrices of a phase must share the input row");
-            std::vector<uint8_t> cnt(M.tiles);
             uint32_t P = 1;
             for (uint32_t t = 0; t < M.tiles; ++t) {
                 const uint32_t a = range_of((uint64_t)M.unit0 + (uint64_t)t * M.C, U, Weff), b = range_of((uint64_t)M.unit0 + (uint64_t)(t + 1) * M.C - 1, U, Weff);
-                cnt[t] = (uint8_t)(b - a + 1);
                 P = std::max(P, b - a + 1);
             }
-            need(P <= 255, "too many pieces per tile");
+            need(P <= 64, "too many pieces per tile");
             M.P = P;
+            // unused slots of a tile are never written: they keep these zeros, so consumers sum all P slots without a per-tile count
             Buf pieces = dev_zero((size_t)M.tiles * P * 16 * 4);
-            Buf counts = make_buf(e, std::max<size_t>(M.tiles, 256), UZU_BUFFER_DEVICE);
-            cudaMemcpyAsync((void*)counts.ptr(), cnt.data(), M.tiles, cudaMemcpyHostToDevice, e->ctx->stream);
-            cudaStreamSynchronize(e->ctx->stream);     // cnt is a local
             M.pieces = (float*)pieces.ptr();
-            piece_tables.push_back(counts);
         }
         const uint32_t C = op.mat[0].C, gps = 512 / (group_size * bits / 4);
         scratch = std::max(scratch, (size_t)(C * 64 + 4) * 16 + (size_t)C * gps * 4 + 64);
         mg.ops.push_back(op);
         return mg.ops.size() - 1;
     }
-    std::vector<Buf> piece_tables;
     MkPieces pieces_of(size_t op_index, int mat) {
         const MkMat& M = mg.ops[op_index].mat[mat];
-        // the count table was pushed in order: find it by position
-        size_t idx = 0;
-        for (size_t i = 0; i < op_index; ++i)
-            if (mg.ops[i].kind == MK_GEMV) idx += mg.ops[i].nmat;
         MkPieces pc{};
         pc.pieces = M.pieces;
-        pc.count = (const uint8_t*)piece_tables[idx + mat].ptr();
         pc.P = M.P;
         return pc;
     }
@@ -1507,13 +1497,11 @@ struct MegaBuilder {
                 max_vd = std::max(max_vd, L.dn.value_dim);
             }
         }
-        scratch = std::max<size_t>(scratch, max_attn_scratch + 64);
+        scratch = std::max<size_t>(scratch, std::max<size_t>(max_attn_scratch + 64, (256 + 256 + 32) * 4));
         mg.attn_part = dev_zero((size_t)std::max(max_parts, 64u) * 4);
         mg.attn_tickets = dev_zero(max_kvh * 4);
-        mg.dn_qk = dev_zero((size_t)max_hk * 2 * 128 * 4);
-        mg.dn_kq = dev_zero((size_t)max_hk * 4);
-        mg.dn_v = dev_zero((size_t)max_vd * 4);
         mg.dn_raw = dev_zero((size_t)max_vd * 4);
+        (void)max_hk;
         mg.argmax_keys = dev_zero((size_t)probe.grid * 8);
 
         size_t prev_down = (size_t)-1;
@@ -1548,7 +1536,7 @@ struct MegaBuilder {
                 mixer_source(o_in);
                 cur ^= 1;
                 MkOp prep{};
-                prep.kind = MK_PREP;
+                prep.kind = MK_ATTN;
                 prep.qkv_pc = pieces_of(o_in, qkv_mat);
                 prep.queries = (__nv_bfloat16*)e->queries.ptr();
                 prep.keys = (__nv_bfloat16*)St.keys; prep.values = (__nv_bfloat16*)St.values;
@@ -1571,10 +1559,8 @@ struct MegaBuilder {
                 prep.attn_scale = A.has_scale ? A.scale : 1.0f / sqrtf((float)D);
                 prep.attn_part = (float*)mg.attn_part.ptr();
                 prep.attn_tickets = (unsigned int*)mg.attn_tickets.ptr();
+                prep.kind = MK_ATTN;              // q/k norm + RoPE + KV append are folded into the attention phase
                 mg.ops.push_back(prep);
-                MkOp at = prep;
-                at.kind = MK_ATTN;
-                mg.ops.push_back(at);
                 mix_out = gemv({&A.out});
                 MkOp& oo = mg.ops[mix_out];
                 oo.src_kind = MK_SRC_BF16;
@@ -1588,25 +1574,32 @@ struct MegaBuilder {
                 mixer_source(o_in);
                 cur ^= 1;
                 MkOp dc{};
-                dc.kind = MK_DN_CONV;
+                dc.kind = MK_DN_UPDATE;
                 dc.dn_in_pc = pieces_of(o_in, 0);
                 dc.dn_conv_weight = (const float*)Dn.conv_weight.ptr();
                 dc.dn_conv_bias = Dn.conv_has_bias ? (const float*)Dn.conv_bias.ptr() : nullptr;
                 dc.dn_conv_state = (float*)St.conv_state.ptr();
                 dc.dn_a_log = (const float*)Dn.a_log.ptr(); dc.dn_dt_bias = (const float*)Dn.dt_bias.ptr();
                 dc.dn_state = (float*)St.ssm_state.ptr();
-                dc.dn_qk = (float*)mg.dn_qk.ptr(); dc.dn_kq = (float*)mg.dn_kq.ptr(); dc.dn_v = (float*)mg.dn_v.ptr(); dc.dn_out_raw = (float*)mg.dn_raw.ptr();
+                dc.dn_out_raw = (float*)mg.dn_raw.ptr();
                 dc.dn_kernel_size = Dn.kernel_size; dc.dn_key_dim = Dn.key_dim; dc.dn_value_dim = Dn.value_dim;
                 dc.dn_num_k_heads = Dn.num_groups; dc.dn_num_v_heads = Dn.num_heads; dc.dn_hv_dim = Dn.value_head_dim;
                 need(Dn.key_dim == Dn.num_groups * 128 && Dn.value_dim == Dn.num_heads * Dn.value_head_dim && Dn.conv_dim == 2 * Dn.key_dim + Dn.value_dim,
                      "DeltaNet geometry");
                 need(Dn.total_proj_dim == Dn.conv_dim + Dn.value_dim + 2 * Dn.num_heads, "DeltaNet projection layout");
+                {
+                    const uint32_t cph = probe.grid / Dn.num_heads;
+                    need(cph >= 1, "more DeltaNet heads than SMs");
+                    const uint32_t rows_per = (Dn.value_head_dim + cph - 1) / cph;
+                    need(probe.ncw >= 8 && probe.ncw * 32 >= 256 + rows_per && rows_per <= 256, "DeltaNet rows per CTA");
+                }
                 mg.ops.push_back(dc);
-                MkOp du = dc;
-                du.kind = MK_DN_UPDATE;
-                mg.ops.push_back(du);
                 mix_out = gemv({&Dn.out_proj});
                 MkOp& oo = mg.ops[mix_out];
+                // the staging of this phase also commits the rolling conv state (all readers of the old state are behind the barrier)
+                oo.dn_commit = 1;
+                oo.dn_in_pc = dc.dn_in_pc; oo.dn_conv_state = dc.dn_conv_state;
+                oo.dn_kernel_size = dc.dn_kernel_size; oo.dn_key_dim = dc.dn_key_dim; oo.dn_value_dim = dc.dn_value_dim;
                 oo.in_kind = MK_IN_DELTA;
                 oo.src_kind = MK_SRC_BF16;       // unused by MK_IN_DELTA (the row comes from dn_raw)
                 oo.src_vec = (const __nv_bfloat16*)e->delta_out.ptr();
@@ -1623,14 +1616,27 @@ struct MegaBuilder {
             mg.ops[o_up].src_kind = MK_SRC_PIECES;
             mg.ops[o_up].src_pc = pieces_of(mix_out, 0);
             cur ^= 1;
-            MkOp act{};
-            act.kind = MK_ACT;
-            act.up_pc = pieces_of(o_up, 0);
-            act.hidden = (__nv_bfloat16*)e->gated.ptr();
-            act.act_dim = L.hidden_dim; act.act_type = L.act;
-            mg.ops.push_back(act);
+            // GatedActMul: small hidden dims fold it into the down projection's staging (every CTA recomputes the F activations, one
+            // barrier less); large ones keep a separate elementwise phase spread over all SMs
+            static const uint32_t fold_max = [] { const char* v = getenv("UZU_MEGA_ACT_FOLD_MAX"); return v ? (uint32_t)atoi(v) : 6144u; }();
+            const bool fold_act = L.hidden_dim <= fold_max;
+            if (!fold_act) {
+                MkOp act{};
+                act.kind = MK_ACT;
+                act.up_pc = pieces_of(o_up, 0);
+                act.hidden = (__nv_bfloat16*)e->gated.ptr();
+                act.act_dim = L.hidden_dim; act.act_type = L.act;
+                mg.ops.push_back(act);
+            }
             const size_t o_down = gemv({&L.down});
-            mg.ops[o_down].in_kind = MK_IN_PLAIN;
+            if (fold_act) {
+                mg.ops[o_down].in_kind = MK_IN_GATED;
+                mg.ops[o_down].gated_pc = pieces_of(o_up, 0);
+                mg.ops[o_down].gated_act = L.act;
+                need(L.down.in_dim == L.hidden_dim, "down projection input");
+            } else {
+                mg.ops[o_down].in_kind = MK_IN_PLAIN;
+            }
             mg.ops[o_down].src_kind = MK_SRC_BF16;
             mg.ops[o_down].src_vec = (const __nv_bfloat16*)e->gated.ptr();
             prev_down = o_down;
@@ -1691,13 +1697,17 @@ static void mega_check_error(uzu_engine* e) {
     }
 }
 
-static void launch_mega_step(uzu_engine* e, uint64_t dev_out, uint32_t dev_out_base_step) {
+static void launch_mega_step(uzu_engine* e, uint64_t dev_out, uint32_t dev_out_base_step, unsigned long long* trace = nullptr, uint32_t trace_cta = 0) {
     MkParams p{};
+    p.trace = trace;
+    p.trace_cta = trace_cta;
     p.ops = (const MkOp*)e->mega.ops_dev.ptr();
     p.nops = (uint32_t)e->mega.ops.size();
     p.ncw = e->mega.cfg.ncw;
     p.state = (MkStepState*)e->decode_state.ptr();
-    p.barrier = (unsigned int*)e->mega.barrier.ptr();
+    p.barrier = (unsigned long long*)e->mega.barrier.ptr();
+    p.barrier_base = e->mega.barrier_base;
+    e->mega.barrier_base += (uint64_t)(e->mega.ops.size() - 1) * e->mega.cfg.grid;     // every phase but the last ends with a grid barrier
     p.error_flag = (unsigned int*)e->mega.error_flag.ptr();
     p.token_ids = (const uint32_t*)e->token_ids.ptr();
     p.token_out = (uint32_t*)e->token_ids.ptr();
@@ -2077,8 +2087,32 @@ uzu_status uzu_engine_set_decode_mode(uzu_engine* e, int persistent) {
         else if (!e->mega.ok) {
             if (e->mega.ops.empty() || !e->mega.ops_dev.b) throw std::runtime_error("persistent decode kernel not available: " + e->mega.why);
             *(volatile unsigned int*)uzu_buffer_cpu_ptr(e->mega.error_flag.b) = 0u;
+            cudaMemset((void*)e->mega.barrier.ptr(), 0, 256);
+            e->mega.barrier_base = 0;
             e->mega.ok = true;
         }
+    });
+}
+uzu_status uzu_engine_debug_decode_trace(uzu_engine* e, uint32_t cta, uint32_t capacity, uint32_t* out_kinds, uint64_t* out_cycles, uint32_t* out_nops) {
+    UZU_ENGINE_TRY({
+        if (!mega_usable(e)) throw std::runtime_error("decode trace: the persistent decode kernel is not active");
+        const uint32_t n = (uint32_t)e->mega.ops.size();
+        if (out_nops) *out_nops = n;
+        if (capacity < n || !out_kinds || !out_cycles) throw std::runtime_error("decode trace: capacity too small");
+        if (e->context_length + 1 > e->max_context + MAX_ROWS) throw std::runtime_error("context overflow");
+        state_prepare(e, e->context_length + 1);
+        Buf tr = make_buf(e, (size_t)n * 4 * 8, UZU_BUFFER_DEVICE);
+        cudaMemsetAsync((void*)tr.ptr(), 0, (size_t)n * 4 * 8, e->ctx->stream);
+        launch_mega_step(e, 0, 0, (unsigned long long*)tr.ptr(), cta);
+        cudaEventRecord(e->step_events[e->steps_issued & 1], e->ctx->stream);
+        e->steps_issued++;
+        accept(e, 1);
+        e->steps_returned = e->steps_issued;
+        cudaError_t err = cudaStreamSynchronize(e->ctx->stream);
+        if (err != cudaSuccess) throw std::runtime_error(std::string("decode trace: ") + cudaGetErrorString(err));
+        mega_check_error(e);
+        cudaMemcpy(out_cycles, (void*)tr.ptr(), (size_t)n * 4 * 8, cudaMemcpyDeviceToHost);
+        for (uint32_t i = 0; i < n; ++i) out_kinds[i] = e->mega.ops[i].kind;
     });
 }
 uzu_status uzu_engine_last_logits(uzu_engine* e, uint16_t* out_logits) {
