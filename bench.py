@@ -386,6 +386,31 @@ def measure_decode(eng, dist, world: int, replicas: int, local_rank: int, prompt
             "value": whole_job_value(replicas, K, seconds), "e2e_value": whole_job_value(replicas, K, e2e_s)}
 
 
+def both_paths(eng, steps: int = 48):
+    """ms per decode step of both parity-tested decode paths on the current state (the engine auto-selects the faster one at load;
+    this makes the choice visible): device-chained steps between CUDA events, state restored afterwards."""
+    selected = bool(eng.persistent_decode)
+    out = {"selected": "persistent kernel" if selected else "per-kernel path", "selection": eng.persistent_decode_reason}
+    for name, mode in (("persistent_ms_per_step", True), ("per_kernel_ms_per_step", False)):
+        try:
+            eng.set_persistent_decode(mode)
+            if bool(eng.persistent_decode) != mode:
+                raise RuntimeError("mode not available")
+            eng.restore()
+            eng.decode_timed(4)
+            eng.restore()
+            out[name] = 1000.0 * eng.decode_timed(steps) / steps
+        except Exception as ex:
+            out[name] = None
+            out[name + "_note"] = str(ex)[:120]
+    try:
+        eng.set_persistent_decode(selected)
+    except Exception:
+        pass
+    eng.restore()
+    return out
+
+
 def roofline_of(eng, workload: str, prefill: int, K: int, seconds: float):
     """Dominant kernel of a decode step. Persistent mode: the step IS one kernel (decode_mega_kernel): algorithmic bytes per launch =
     quantised weights + KV rows read at the mid context + recurrent state read/write; duration = the CUDA-event time of the K launches / K.
@@ -492,6 +517,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                            f"per-kernel path ({'CUDA graph' if not args.no_graph else 'eager'}): {eng.persistent_decode_reason or 'persistent kernel disabled'}",
             "cuda_graph": not args.no_graph, "fused_decode": not args.no_fused, "prefill_tokens_per_s": prefill / m["prefill_s"],
             "prefill_gemm": prefill_gemm_of(eng, prefill), **extra,
+            "decode_paths": both_paths(eng) if tp == 1 else None,
         },
         "roofline": roof,
         "e2e": {"value": m["e2e_value"], "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 4},
@@ -545,7 +571,7 @@ def secondary_line(B, ctx, args, local_rank: int):
         roof, extra = roofline_of(eng, SECONDARY, prefill, K, m["seconds"])
         out = {"workload": workload_name(SECONDARY, prefill, K, 1), "value": m["value"], "unit": "tokens/s", "ms_per_step": 1000.0 * m["seconds"] / K,
                "e2e": m["e2e_value"], "gpu_launches": m["launches"], "roofline": roof, "prefill_tokens_per_s": prefill / m["prefill_s"],
-               "decode_path": "persistent kernel (1 launch per token)" if eng.persistent_decode else "per-kernel path", **extra}
+               "decode_path": "persistent kernel (1 launch per token)" if eng.persistent_decode else "per-kernel path", "decode_paths": both_paths(eng), **extra}
         if not args.no_cpu_baseline:
             try:
                 out["cpu_baseline"], out["parity"] = cpu_leg(eng, mdir, effective_cpus(), budget_s=20.0)

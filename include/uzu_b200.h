@@ -507,8 +507,8 @@ UZU_API int uzu_engine_decode_mode(const uzu_engine* e);
 UZU_API const char* uzu_engine_decode_mode_reason(const uzu_engine* e);
 UZU_API uzu_status uzu_engine_set_decode_mode(uzu_engine* e, int persistent);
 UZU_API uzu_status uzu_engine_last_logits(uzu_engine* e, uint16_t* out_logits);
-/* measurement helper: run ONE persistent decode step and return, for CTA `cta`, four SM-clock stamps per phase (phase start, activation row
- * staged, phase body done, grid barrier passed) and the phase kinds (1 GEMV, 2 prepare, 3 attention, 4 act, 5/6 DeltaNet, 7 logits, 8 finish) */
+/* measurement helper: run ONE persistent decode step and return, for CTA `cta`, eight SM-clock stamps per phase ([0] phase start, [1] activation
+ * row staged / attention prepared, [2..5] phase-specific, [6] phase body done, [7] grid barrier passed; 0 = not stamped) and the phase kinds (1 GEMV, 2 prepare, 3 attention, 4 act, 5/6 DeltaNet, 7 logits, 8 finish) */
 UZU_API uzu_status uzu_engine_debug_decode_trace(uzu_engine* e, uint32_t cta, uint32_t capacity, uint32_t* out_kinds, uint64_t* out_cycles, uint32_t* out_nops);
 UZU_API uzu_status uzu_engine_time_linears(uzu_engine* e, uint32_t iters, double* out_seconds, uint64_t* out_launches);
 /*  time_prefill_linears: every linear of one PREFILL pass over m rows (all layers, no readout) back to back; returns seconds per pass

@@ -26,6 +26,7 @@ def test_persistent_decode_matches_oracle_and_per_kernel_path(ctx, tmp_path, kin
     ref = OracleModel(path, max_context=128)
     lr = ref.prefill(prompt)
     with B.Engine(ctx, path, max_context_length=128, use_cuda_graph=True) as eng:
+        eng.set_persistent_decode(True)     # the engine auto-selects the faster decode path at load; these tests are about the persistent kernel
         assert eng.persistent_decode, f"persistent decode kernel does not cover {kind}: {eng.persistent_decode_reason}"
         eng.prefill(prompt)
         eng.snapshot()
@@ -67,6 +68,7 @@ def test_persistent_decode_device_chained_generation(ctx, tmp_path):
     path = synth.write_model(spec, tmp_path / "m", seed=32)
     prompt = (np.arange(40) * 53) % spec.vocab_size
     with B.Engine(ctx, path, max_context_length=256) as eng:
+        eng.set_persistent_decode(True)
         assert eng.persistent_decode, eng.persistent_decode_reason
         a = eng.generate(prompt, 24)
         eng.reset()
@@ -97,6 +99,7 @@ def test_persistent_decode_long_context(ctx, tmp_path):
     ref = OracleModel(path, max_context=1024)
     lr = ref.prefill(prompt)
     with B.Engine(ctx, path, max_context_length=1024) as eng:
+        eng.set_persistent_decode(True)
         assert eng.persistent_decode, eng.persistent_decode_reason
         eng.prefill(prompt)
         tok = int(np.argmax(bf16_to_f32(lr[0])))

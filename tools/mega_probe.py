@@ -19,6 +19,10 @@ ctx = B.Context(0)
 t0 = time.time()
 eng = B.Engine(ctx, mdir, max_context_length=max(1024, prefill + 4 * steps + 64))
 say(f"engine created in {time.time() - t0:.1f}s; persistent={eng.persistent_decode} reason='{eng.persistent_decode_reason}'")
+try:
+    eng.set_persistent_decode(True)
+except Exception as ex:
+    say("persistent kernel unavailable:", ex)
 rng = np.random.default_rng(0)
 prompt = rng.integers(0, eng.info.vocab_size, prefill).astype(np.uint32)
 t0 = time.time()
@@ -59,13 +63,16 @@ if eng.persistent_decode:
         total = (c[-1, 2] - t_start) / 1.965e3
         agg = {}
         for k, row in zip(kinds, c):
-            a = agg.setdefault(KIND.get(int(k), str(k)), [0, 0.0, 0.0, 0.0])
-            stage = (row[1] - row[0]) if row[1] > 0 else 0.0
-            body = (row[2] - (row[1] if row[1] > 0 else row[0]))
-            bar = (row[3] - row[2]) if row[3] > 0 else 0.0
-            a[0] += 1; a[1] += stage / 1.965e3; a[2] += body / 1.965e3; a[3] += bar / 1.965e3
-        say(f"trace cta {cta}: step {total:.1f} us over {len(kinds)} phases")
-        for name, (n, st, bo, ba) in agg.items():
-            say(f"   {name:7s} x{n:4d}  staging {st:8.1f} us  body {bo:8.1f} us  barrier {ba:8.1f} us   (per phase {st / n:6.2f} / {bo / n:6.2f} / {ba / n:6.2f})")
+            a = agg.setdefault(KIND.get(int(k), str(k)), [0] + [0.0] * 7)
+            a[0] += 1
+            prev = row[0]
+            for i in range(1, 8):
+                if row[i] > 0:
+                    a[i] += (row[i] - prev) / 1.965e3
+                    prev = row[i]
+        total = (c[-1, 6] - t_start) / 1.965e3
+        say(f"trace cta {cta}: step {total:.1f} us over {len(kinds)} phases; columns = us between consecutive stamps [1..7] (7 = grid barrier)")
+        for name, a in agg.items():
+            say(f"   {name:7s} x{a[0]:4d}  " + "  ".join(f"{x / a[0]:6.2f}" for x in a[1:]) + f"   | sum {sum(a[1:]):8.1f} us")
 eng.close(); ctx.close()
 say("done")

@@ -10,6 +10,7 @@ prefill = int(sys.argv[2]) if len(sys.argv) > 2 else bench.WORKLOADS[workload][2
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 ctx = B.Context(0)
 eng = B.Engine(ctx, bench.model_dir_for(workload), max_context_length=max(1024, prefill + steps + 64))
+eng.set_persistent_decode(True)
 assert eng.persistent_decode, eng.persistent_decode_reason
 rng = np.random.default_rng(0)
 tok = eng.prefill(rng.integers(0, eng.info.vocab_size, prefill).astype(np.uint32))

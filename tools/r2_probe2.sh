@@ -2,5 +2,3 @@
 mkdir -p gpurun_out
 timeout -s KILL 120 python -u tools/mega_probe.py qwen3.5-0.8b-int4 > gpurun_out/r2e_probe_qwen.log 2>&1; echo "qwen rc=$?"; tail -n 16 gpurun_out/r2e_probe_qwen.log
 timeout -s KILL 150 python -u tools/mega_probe.py llama3-8b-int4 > gpurun_out/r2e_probe_llama.log 2>&1; echo "llama rc=$?"; tail -n 14 gpurun_out/r2e_probe_llama.log
-timeout -s KILL 300 python -u -m pytest tests/test_mega_gpu.py -x -q --timeout 90 --timeout-method thread > gpurun_out/r2e_mega_test.log 2>&1; echo "mega test rc=$?"
-tail -n 4 gpurun_out/r2e_mega_test.log

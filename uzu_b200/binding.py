@@ -543,10 +543,10 @@ class Engine:
         _check(self.lib.uzu_engine_set_decode_mode(self.h, int(on)))
 
     def decode_trace(self, cta: int = 0):
-        """One persistent decode step with per-phase SM-clock stamps of CTA `cta`: (kinds [n], cycles [n, 4])."""
+        """One persistent decode step with per-phase SM-clock stamps of CTA `cta`: (kinds [n], cycles [n, 8])."""
         cap = 4096
         kinds = np.zeros(cap, dtype=np.uint32)
-        cyc = np.zeros((cap, 4), dtype=np.uint64)
+        cyc = np.zeros((cap, 8), dtype=np.uint64)
         n = u32()
         _check(self.lib.uzu_engine_debug_decode_trace(self.h, cta, cap, kinds.ctypes.data_as(C.POINTER(u32)), cyc.ctypes.data_as(C.POINTER(u64)), C.byref(n)))
         return kinds[:n.value], cyc[:n.value]

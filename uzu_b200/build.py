@@ -52,7 +52,8 @@ def _deps_digest() -> bytes:
 def _compile(src: Path, extra, verbose: bool, force: bool):
     # the cache key is the CONTENT of the source, of every header and the flags (not mtimes: the gpurun snapshot does not keep them, and a
     # stale-looking object would trigger a multi-minute rebuild on the GPU box)
-    key = hashlib.sha1(" ".join(COMMON + extra).encode() + src.read_bytes() + _deps_digest()).hexdigest()[:12]
+    flags = " ".join(f for f in COMMON + extra if not f.startswith(str(HERE.parent)))      # the -I path is a location, not content
+    key = hashlib.sha1(flags.encode() + src.read_bytes() + _deps_digest()).hexdigest()[:12]
     obj = OBJ / f"{src.stem}.{key}.o"
     if not force and obj.exists():
         return obj, None

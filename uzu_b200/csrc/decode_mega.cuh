@@ -113,6 +113,16 @@ struct alignas(16) MkOp {
 
 static_assert(sizeof(MkOp) % 16 == 0 && sizeof(MkOp) <= 1024, "MkOp is copied to shared memory in 16-byte pieces");
 
+// One entry per GEMV phase, in program order: what a warp needs to walk its own weight stream ahead of the phases (32 bytes, __ldg)
+struct alignas(16) MkStream {
+    const uint8_t* stream0;        // matrix 0 of the phase
+    const uint8_t* stream1;        // matrix 1 (or null)
+    uint32_t units, split;         // units of the phase; first unit of matrix 1 (== units when there is one matrix)
+    uint32_t hold;                 // the phase before this one issues latency-critical HBM loads (KV rows, recurrent state): the prefetch
+                                   // cursor parks here until that phase has issued them, so they do not queue behind ~20 MB of weights
+    uint32_t pad;
+};
+
 struct MkStepState {               // == engine.cu's DecodeState
     uint32_t position, step;
     uint64_t base_seed;
@@ -120,6 +130,8 @@ struct MkStepState {               // == engine.cu's DecodeState
 
 struct MkParams {
     const MkOp* ops;
+    const MkStream* streams;       // the GEMV phases' weight streams, in program order
+    uint32_t nstreams, pad_s;
     uint32_t nops, ncw;            // consumer warps per CTA the program was partitioned for
     MkStepState* state;
     unsigned long long* barrier;   // [0] monotonic arrival counter (never reset: launch k's barrier b completes at barrier_base + (b + 1) * grid), [1] low word = device-side error flag polled by the spin loops

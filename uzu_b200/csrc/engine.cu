@@ -425,7 +425,8 @@ struct uzu_engine {
         std::string why;                 // why the model is not covered (diagnostics)
         uzu::MegaConfig cfg{};
         std::vector<uzu::MkOp> ops;
-        Buf ops_dev, barrier, error_flag, argmax_keys, attn_part, attn_tickets, dn_raw;
+        Buf ops_dev, streams_dev, barrier, error_flag, argmax_keys, attn_part, attn_tickets, dn_raw;
+        uint32_t nstreams = 0;
         uint64_t stream_bytes = 0;
         uint64_t barrier_base = 0;       // arrivals the monotonic grid-barrier counter has seen before the next launch
     } mega;
@@ -1350,6 +1351,7 @@ struct MegaBuilder {
     uzu_engine* e;
     uzu_engine::Mega& mg;
     uint32_t W;              // consumer warps of the whole grid
+    uint32_t grid = 0;
     uint32_t bits = 0, group_size = 0;
     size_t scratch = 0;
     std::map<uint64_t, Buf> streams;   // original values pointer -> decode-stream copy
@@ -1408,7 +1410,8 @@ struct MegaBuilder {
         }
         op.nmat = nm;
         op.units = unit0;
-        const uint64_t U = unit0, Weff = std::min<uint64_t>(W, U);
+        need((uint64_t)unit0 * (grid + 1) < (1ull << 32), "phase too large for the 32-bit partition arithmetic");
+        const uint64_t U = unit0, Weff = std::min<uint64_t>(grid, U);      // pieces per tile = CTAs whose range touches it (decode_mega.cu mk_my_range)
         for (uint32_t i = 0; i < nm; ++i) {
             MkMat& M = op.mat[i];
             need(M.k == op.k, "matrices of a phase must share the input row");
@@ -1424,6 +1427,7 @@ struct MegaBuilder {
             M.pieces = (float*)pieces.ptr();
         }
         const uint32_t C = op.mat[0].C, gps = 512 / (group_size * bits / 4);
+        // xs + zero block + sx, plus (RMSNorm inputs) a bf16 copy of the row; the norm is only ever applied to model_dim rows
         scratch = std::max(scratch, (size_t)(C * 64 + 4) * 16 + (size_t)C * gps * 4 + 64);
         mg.ops.push_back(op);
         return mg.ops.size() - 1;
@@ -1439,6 +1443,11 @@ struct MegaBuilder {
         MkOp& op = mg.ops[op_index];
         need(n.present || true, "");
         need(!n.cfg.subtract_mean && n.cfg.has_scale, "norm variant");
+        need(op.k <= 8192, "normalised rows longer than 8192");
+        {   // the RMSNorm staging keeps a bf16 copy of the row behind xs / sx
+            const uint32_t C = op.mat[0].C, gps = 512 / (group_size * bits / 4);
+            scratch = std::max(scratch, (size_t)(C * 64 + 4) * 16 + (size_t)C * gps * 4 + 64 + (size_t)op.k * 2);
+        }
         op.in_kind = MK_IN_NORM;
         op.shortcut_in = (const __nv_bfloat16*)sc_in;
         op.shortcut_out = (__nv_bfloat16*)sc_out;
@@ -1481,6 +1490,7 @@ struct MegaBuilder {
         MegaConfig probe{};
         need(mega_config(e->ctx, npg, bits, 0, &probe), "quantisation geometry not covered by the persistent kernel");
         W = probe.grid * probe.ncw;
+        grid = probe.grid;
 
         const uint32_t H = e->model_dim;
         uint64_t S[2] = {e->shortcut.ptr(), e->shortcut2.ptr()};
@@ -1488,8 +1498,12 @@ struct MegaBuilder {
         uint32_t max_attn_scratch = 0, max_parts = 0, max_hk = 1, max_vd = 1, max_kvh = 1;
         for (auto& L : e->layers) {
             if (L.is_attention) {
-                const uint32_t G = L.attn.num_heads / L.attn.num_groups;
-                max_attn_scratch = std::max<uint32_t>(max_attn_scratch, probe.ncw * G * (L.attn.head_dim + 2) * 4);
+                const uint32_t G = L.attn.num_heads / L.attn.num_groups, D = L.attn.head_dim;
+                // sq [G][D] + sc [G][kp] + stats + so [ceil(ncw / 2)][G][D]  (decode_mega.cu MK_ATTN), kp at the longest context
+                const uint32_t cph = probe.grid / L.attn.num_groups, kpw = 32 / (D / 8), step = 16 * kpw;    // 16 >= any warp count of the table
+                const uint32_t seq_max = e->max_context + MAX_ROWS;
+                const uint32_t kp_max = std::max(((seq_max + cph - 1) / cph + step - 1) / step, 4u) * step;
+                max_attn_scratch = std::max<uint32_t>(max_attn_scratch, (G * D + G * kp_max + 16 + 8 * G * D) * 4);
                 max_parts = std::max<uint32_t>(max_parts, probe.grid * G * (L.attn.head_dim + 2));
                 max_kvh = std::max(max_kvh, L.attn.num_groups);
             } else {
@@ -1659,6 +1673,33 @@ struct MegaBuilder {
         mg.ops.push_back(fin);
 
         need(mega_config(e->ctx, npg, bits, (uint32_t)scratch, &mg.cfg), "shared memory budget");
+        {
+            std::vector<MkStream> st;
+            uint32_t prev_kind = 0;
+            for (auto& op : mg.ops) {
+                const uint32_t before = prev_kind;
+                prev_kind = op.kind;
+                if (op.kind != MK_GEMV) continue;
+                MkStream d{};
+                // parking the prefetch cursor in front of latency-critical phases was measured (round 2): the KV loads did not get faster,
+                // the phase after them lost its prefetch -> off unless UZU_MEGA_HOLD=1
+                static const bool hold_on = [] { const char* v = getenv("UZU_MEGA_HOLD"); return v && atoi(v) != 0; }();
+                d.hold = (hold_on && (before == MK_ATTN || before == MK_DN_UPDATE)) ? 1u : 0u;
+                d.stream0 = op.mat[0].stream;
+                d.stream1 = op.nmat > 1 ? op.mat[1].stream : nullptr;
+                d.units = op.units;
+                d.split = op.nmat > 1 ? op.mat[1].unit0 : op.units;
+                st.push_back(d);
+            }
+            mg.nstreams = (uint32_t)st.size();
+            mg.streams_dev = make_buf(e, st.size() * sizeof(MkStream), UZU_BUFFER_DEVICE);
+            cudaMemcpy((void*)mg.streams_dev.ptr(), st.data(), st.size() * sizeof(MkStream), cudaMemcpyHostToDevice);
+        }
+        for (auto& L : e->layers)
+            if (!L.is_attention) {
+                const uint32_t cph = mg.cfg.grid / L.dn.num_heads, rows_per = (L.dn.value_head_dim + cph - 1) / cph;
+                need(mg.cfg.ncw >= 8 && mg.cfg.ncw * 32 >= 256 + rows_per, "DeltaNet rows per CTA (final configuration)");
+            }
         mg.ops_dev = make_buf(e, mg.ops.size() * sizeof(MkOp), UZU_BUFFER_DEVICE);
         cudaMemcpyAsync((void*)mg.ops_dev.ptr(), mg.ops.data(), mg.ops.size() * sizeof(MkOp), cudaMemcpyHostToDevice, e->ctx->stream);
         mg.barrier = dev_zero(256);
@@ -1686,6 +1727,47 @@ static bool mega_usable(const uzu_engine* e) {
     return e->mega.ok && e->sampling.kind == UZU_SAMPLING_GREEDY;
 }
 
+static void issue_decode_step(uzu_engine* e, uint64_t dev_out, uint32_t dev_out_base_step);
+static void upload_decode_state(uzu_engine* e);
+
+// Both decode paths are parity-tested; which one is faster depends on the model (phase count vs bytes per phase). Unless UZU_DECODE_PATH
+// forces one ("persistent" | "kernels"), time a few steps of each at a representative context right after load and keep the faster.
+static void calibrate_decode_path(uzu_engine* e) {
+    if (!e->mega.ok) return;
+    const char* env = getenv("UZU_DECODE_PATH");
+    if (env && !strcmp(env, "persistent")) { e->mega.why = "forced by UZU_DECODE_PATH=persistent"; return; }
+    if (env && !strcmp(env, "kernels")) { e->mega.ok = false; e->mega.why = "forced by UZU_DECODE_PATH=kernels"; return; }
+    const uint32_t P = std::min<uint32_t>(e->max_context / 2, 2048);
+    cudaStream_t s = e->ctx->stream;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    float ms[2] = {0.0f, 0.0f};
+    for (int mode = 0; mode < 2; ++mode) {
+        e->mega.ok = mode == 0;
+        reset_state(e);
+        for (auto& S : e->state) S.length = P;       // pseudo-context: the KV / state contents do not matter for the timing
+        e->context_length = P;
+        upload_decode_state(e);
+        for (int i = 0; i < 3; ++i) issue_decode_step(e, 0, 0);
+        cudaEventRecord(a, s);
+        for (int i = 0; i < 8; ++i) issue_decode_step(e, 0, 0);
+        cudaEventRecord(b, s);
+        if (cudaEventSynchronize(b) != cudaSuccess) { cudaGetLastError(); ms[mode] = 1e30f; continue; }
+        cudaEventElapsedTime(&ms[mode], a, b);
+        e->steps_returned = e->steps_issued;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    const unsigned int code = *(volatile unsigned int*)uzu_buffer_cpu_ptr(e->mega.error_flag.b);
+    e->mega.ok = code == 0 && ms[0] <= ms[1];
+    char buf[160];
+    snprintf(buf, sizeof buf, "auto-selected at load: persistent kernel %.3f ms/step vs per-kernel path %.3f ms/step at context %u", ms[0] / 8, ms[1] / 8, P);
+    e->mega.why = buf;
+    reset_state(e);
+    e->launches = 0;
+}
+
 static void mega_check_error(uzu_engine* e) {
     if (!e->mega.ok) return;
     const unsigned int code = *(volatile unsigned int*)uzu_buffer_cpu_ptr(e->mega.error_flag.b);
@@ -1702,6 +1784,8 @@ static void launch_mega_step(uzu_engine* e, uint64_t dev_out, uint32_t dev_out_b
     p.trace = trace;
     p.trace_cta = trace_cta;
     p.ops = (const MkOp*)e->mega.ops_dev.ptr();
+    p.streams = (const MkStream*)e->mega.streams_dev.ptr();
+    p.nstreams = e->mega.nstreams;
     p.nops = (uint32_t)e->mega.ops.size();
     p.ncw = e->mega.cfg.ncw;
     p.state = (MkStepState*)e->decode_state.ptr();
@@ -1926,7 +2010,10 @@ uzu_status uzu_engine_create(uzu_context* ctx, const char* model_dir, const uzu_
         create_state_and_scratch(e);
         reset_state(e);
         e->fused_ok = e->opts.fused_decode && getenv("UZU_NO_FUSED") == nullptr && fused_decode_supported(e);
-        if (e->opts.fused_decode) build_mega(e);      // the persistent decode kernel is the fused path's next step: one launch per token
+        if (e->opts.fused_decode) {                   // the persistent decode kernel is the fused path's next step: one launch per token
+            build_mega(e);
+            calibrate_decode_path(e);
+        }
         check(uzu_context_synchronize(ctx));
     } catch (const std::exception& ex) {
         std::string msg = ex.what();
@@ -2101,8 +2188,8 @@ uzu_status uzu_engine_debug_decode_trace(uzu_engine* e, uint32_t cta, uint32_t c
         if (capacity < n || !out_kinds || !out_cycles) throw std::runtime_error("decode trace: capacity too small");
         if (e->context_length + 1 > e->max_context + MAX_ROWS) throw std::runtime_error("context overflow");
         state_prepare(e, e->context_length + 1);
-        Buf tr = make_buf(e, (size_t)n * 4 * 8, UZU_BUFFER_DEVICE);
-        cudaMemsetAsync((void*)tr.ptr(), 0, (size_t)n * 4 * 8, e->ctx->stream);
+        Buf tr = make_buf(e, (size_t)n * 8 * 8, UZU_BUFFER_DEVICE);
+        cudaMemsetAsync((void*)tr.ptr(), 0, (size_t)n * 8 * 8, e->ctx->stream);
         launch_mega_step(e, 0, 0, (unsigned long long*)tr.ptr(), cta);
         cudaEventRecord(e->step_events[e->steps_issued & 1], e->ctx->stream);
         e->steps_issued++;
@@ -2111,7 +2198,7 @@ uzu_status uzu_engine_debug_decode_trace(uzu_engine* e, uint32_t cta, uint32_t c
         cudaError_t err = cudaStreamSynchronize(e->ctx->stream);
         if (err != cudaSuccess) throw std::runtime_error(std::string("decode trace: ") + cudaGetErrorString(err));
         mega_check_error(e);
-        cudaMemcpy(out_cycles, (void*)tr.ptr(), (size_t)n * 4 * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(out_cycles, (void*)tr.ptr(), (size_t)n * 8 * 8, cudaMemcpyDeviceToHost);
         for (uint32_t i = 0; i < n; ++i) out_kinds[i] = e->mega.ops[i].kind;
     });
 }
