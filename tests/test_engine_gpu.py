@@ -366,3 +366,42 @@ def test_delta_net_fused_conv_update_matches_two_kernels(ctx):
     for o_u, o_f in zip(res[0][0], res[1][0]):
         assert (o_u == o_f).all()
     assert (res[0][1] == res[1][1]).all() and (res[0][2] == res[1][2]).all()
+
+
+def test_real_qwen35_0p8b_dims_both_decode_paths(ctx, tmp_path):
+    """BASELINE configs[1] at its REAL dimensions (Qwen3.5-0.8B hybrid: 18 DeltaNet + 6 attention layers, model_dim 1024, vocabulary
+    248320, int4 gs64), not a toy: a short prompt, then decode steps under teacher forcing through BOTH decode paths (per-kernel CUDA-graph
+    path and the persistent whole-token kernel) against the CPU oracle. Greedy token ids must match wherever the oracle's top-2 gap is
+    not a near-tie; logits within the bf16 output budget."""
+    import os
+    spec = synth.PRESETS["qwen3.5-0.8b"](bits=4, group_size=64, hybrid=True)
+    path = synth.write_model(spec, tmp_path / "m", seed=0)
+    rng = np.random.default_rng(12)
+    prompt = rng.integers(0, spec.vocab_size, 3)
+    threads = max(1, min(16, len(os.sched_getaffinity(0))))
+    ref = OracleModel(path, threads=threads, max_context=64)
+    lr0 = ref.prefill(prompt)
+    steps, refs = [], []
+    tok = int(np.argmax(bf16_to_f32(lr0[0])))
+    for _ in range(3):
+        steps.append(tok)
+        lr = ref.forward([tok])
+        refs.append(lr)
+        tok = int(np.argmax(bf16_to_f32(lr[0])))
+    with B.Engine(ctx, path, max_context_length=1024) as eng:
+        for persistent in (False, True):
+            eng.set_persistent_decode(persistent)
+            assert eng.persistent_decode == persistent, eng.persistent_decode_reason
+            eng.reset()
+            first = eng.prefill(prompt)
+            top = np.sort(bf16_to_f32(lr0[0]))[::-1]
+            if top[0] - top[1] > 0.05 * abs(top[0]):
+                assert first == steps[0]
+            for i, t in enumerate(steps):
+                got = eng.step_host(t)
+                lg = eng.last_logits()
+                _logit_check(lg, refs[i], f"real Qwen3.5-0.8B dims, persistent={persistent}, step {i}")
+                r = bf16_to_f32(refs[i][0])
+                top = np.sort(r)[::-1]
+                if top[0] - top[1] > 0.05 * abs(top[0]):
+                    assert got == int(np.argmax(r)), (persistent, i, got)

@@ -43,6 +43,33 @@ def test_quantized_matmul_f32_out(ctx, m, n, k, bits, gs, method):
     assert_f32_close(got, ref, rtol=1e-3, atol=1e-4, what=f"matmul {m}x{n}x{k} int{bits} gs{gs} {method}")
 
 
+# shapes the round-1 review found untested against the oracle: the readout matrices of the BASELINE models and int8 gs64 at Llama-3-8B K
+BASELINE_SHAPES = [
+    (1, 128256, 4096, 4, 64, "zp"),    # Llama-3-8B readout
+    (1, 248320, 1024, 4, 64, "zp"),    # Qwen3.5-0.8B readout
+    (1, 6144, 4096, 8, 64, "zp"),      # Llama-3-8B int8 qkv
+    (1, 4096, 14336, 8, 64, "zp"),     # Llama-3-8B int8 down (split-K)
+    (8, 4096, 4096, 8, 64, "zp"),      # config 4: eight sequences share the weight pass
+]
+
+
+@pytest.mark.parametrize("m,n,k,bits,gs,method", BASELINE_SHAPES)
+def test_quantized_matmul_baseline_shapes(ctx, m, n, k, bits, gs, method):
+    """Full matrices on the GPU; the oracle (scalar C) checks a seeded sample of 2048 output rows -- restating the loop on a row subset is the
+    same function on those rows."""
+    x, w, kw = _quant_case(300 + n % 1000 + k, m, n, k, bits, gs, METHODS[method])
+    got = G.matmul(ctx, x, w, m=m, n=n, k=k, d_f32=True, **kw)
+    rows = np.sort(np.random.default_rng(n).choice(n, size=min(n, 2048), replace=False))
+    sub = dict(kw)
+    sub["scales"] = np.ascontiguousarray(kw["scales"][rows])
+    if kw.get("zero_points") is not None:
+        sub["zero_points"] = np.ascontiguousarray(kw["zero_points"][rows])
+    if kw.get("biases") is not None:
+        sub["biases"] = np.ascontiguousarray(kw["biases"][rows])
+    ref = O.matmul(x, np.ascontiguousarray(w[rows]), m=m, n=len(rows), k=k, d_f32=True, **sub)
+    assert_f32_close(got[:, rows], ref, rtol=1e-3, atol=1e-4, what=f"matmul {m}x{n}x{k} int{bits} gs{gs} {method} (sampled rows)")
+
+
 @pytest.mark.parametrize("m,n,k,bits,gs,method", QUANT_CASES[:9])
 def test_quantized_matmul_bf16_out(ctx, m, n, k, bits, gs, method):
     x, w, kw = _quant_case(200 + n + k, m, n, k, bits, gs, METHODS[method])

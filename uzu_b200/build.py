@@ -57,8 +57,9 @@ def _compile(src: Path, extra, verbose: bool, force: bool):
     obj = OBJ / f"{src.stem}.{key}.o"
     if not force and obj.exists():
         return obj, None
-    for old in OBJ.glob(f"{src.stem}.*.o"):
-        old.unlink()
+    if not os.environ.get("UZU_B200_LIB_OUT"):          # experiment builds keep the default objects
+        for old in OBJ.glob(f"{src.stem}.*.o"):
+            old.unlink()
     cmd = [NVCC, *COMMON, *extra, "-c", str(src), "-o", str(obj)]
     if verbose:
         cmd.insert(1, "-Xptxas")
@@ -75,7 +76,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     # kernel experiments: UZU_B200_EXTRA_NVCC="-DFOO=1" adds flags to matmul.cu, UZU_B200_LIB_OUT names the output library
     extra = os.environ.get("UZU_B200_EXTRA_NVCC", "").split()
     lib = Path(os.environ["UZU_B200_LIB_OUT"]) if os.environ.get("UZU_B200_LIB_OUT") else LIB
-    srcs = [(CSRC / name, flags + (extra if name == "matmul.cu" else [])) for name, flags in SOURCES.items() if (CSRC / name).exists()]
+    srcs = [(CSRC / name, flags + (extra if name in ("matmul.cu", "decode_mega.cu") else [])) for name, flags in SOURCES.items() if (CSRC / name).exists()]
     with ThreadPoolExecutor(max_workers=8) as ex:
         results = list(ex.map(lambda sf: _compile(sf[0], sf[1], verbose, force), srcs))
     objs = [o for o, _ in results]

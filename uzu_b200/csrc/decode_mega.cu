@@ -132,10 +132,17 @@ __device__ __forceinline__ void mk_mma_16816(float (&d)[4], uint32_t a0, uint32_
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-// (128 + q_lo, 128 + q_hi) as two exact bf16 from nibbles `shift` and `shift + 16` of w: one shift + one LOP3 (magic kept in a register)
+// (128 + q_lo, 128 + q_hi) as two exact bf16 from nibbles `shift` and `shift + 16` of w: one shift + one LOP3 (magic kept in a register).
+// The GEMV body is bound by the integer ALU pipe (ncu r2: ~75 % active inside the bodies, FMA pipe ~6 %): UZU_MK_SHIFT_MODE moves shifts to
+// the FMA pipe as multiply-high (IMAD.HI). 1: plain shifts; 2: shifts by 4 and 12 on the FMA pipe, by 8 on the ALU pipe; 0: all on FMA.
+#ifndef UZU_MK_SHIFT_MODE
+#define UZU_MK_SHIFT_MODE 1
+#endif
 __device__ __forceinline__ uint32_t mk_nib_pair(uint32_t w, int shift, uint32_t magic) {
-    uint32_t r;
-    const uint32_t s = shift ? (w >> shift) : w;
+    uint32_t r, s;
+    if (shift == 0) s = w;
+    else if (UZU_MK_SHIFT_MODE == 1 || (UZU_MK_SHIFT_MODE == 2 && shift == 8)) s = w >> shift;
+    else s = __umulhi(w, 1u << (32 - shift));
     asm("lop3.b32 %0, %1, 0x000f000f, %2, 0xea;" : "=r"(r) : "r"(s), "r"(magic));   // (s & mask) | magic
     return r;
 }
