@@ -192,6 +192,7 @@ def test_attention_prepare_bit_exact(ctx):
 ATTN_CASES = [  # H, Hkv, seq, suffix, D, causal
     (4, 4, 16, 1, 64, False), (8, 2, 40, 4, 128, True), (4, 1, 64, 8, 64, True), (32, 8, 700, 1, 128, True),
     (8, 2, 1500, 1, 256, True), (64, 8, 300, 2, 128, True), (6, 2, 90, 3, 128, True), (3, 1, 50, 1, 64, True),
+    (32, 8, 2304, 1, 128, True),      # Llama-3-8B decode at the end of BASELINE config 3 (prefill 2048 + decode 256)
 ]
 
 

@@ -127,3 +127,28 @@ def test_two_rank_nccl_engine_matches_unsharded_oracle(tmp_path, exchange):
     assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-4000:])
     d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert d["err"] <= 0.02 * d["scale"] + 1e-3 and len(d["tokens"]) == 12, d
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_two_contexts_on_two_devices_in_one_process():
+    """cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): a second context on another GPU of the same process must be able to
+    launch the > 48 KB shared-memory GEMV too (round 1 kept a per-process flag: the second device's launches failed)."""
+    from oracle import oracle as O
+    from tests import gpu_ops as G
+    rng = np.random.default_rng(3)
+    n, k = 2048, 4096
+    w = rng.integers(0, 256, (n, k // 2), dtype=np.uint8)
+    sc = O.f32_to_bf16(rng.uniform(0.01, 0.3, (n, k // 64)).astype(np.float32))
+    zp = rng.integers(0, 256, (n, k // 128), dtype=np.uint8)
+    x = O.f32_to_bf16(rng.uniform(-0.3, 0.3, (1, k)).astype(np.float32))
+    ref = O.matmul(x, w, m=1, n=n, k=k, scales=sc, zero_points=zp, method=O.QM_ZERO_POINT, d_f32=True)
+    outs = []
+    ctxs = [B.Context(0), B.Context(1)]
+    try:
+        for c in ctxs + ctxs[::-1]:              # interleave the devices on one host thread
+            outs.append(G.matmul(c, x, w, m=1, n=n, k=k, scales=sc, zero_points=zp, method=O.QM_ZERO_POINT, d_f32=True))
+    finally:
+        for c in ctxs:
+            c.close()
+    for got in outs:
+        assert np.allclose(got, ref, rtol=1e-3, atol=1e-3)
