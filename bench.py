@@ -421,7 +421,7 @@ def roofline_of(eng, workload: str, prefill: int, K: int, seconds: float):
     tfile = ROOT / "profiles" / "roofline_traffic.json"
     if tfile.exists():
         try:
-            traffic = json.loads(tfile.read_text()).get(workload)
+            traffic = json.loads(tfile.read_text()).get(f"{workload}:{'persistent' if eng.persistent_decode else 'per-kernel'}")
         except Exception:
             traffic = None
     ctx_mid = prefill + K / 2
@@ -648,7 +648,7 @@ def run_batched(args, eng, ctx, dist, rank, world, local_rank, workload, prefill
         "config": {"workload": f"{workload}: prefill {prefill}, decode {K}, batch {nseq} (independent sequences, one weight pass per step), greedy",
                    "parallelism": "replicas" if world > 1 else "single", "batch": nseq, "per_gpu_value": value / world, "weight_bytes_per_token": info.weight_bytes_per_token,
                    "cache_policy": f"inputs larger than L2: {info.weight_bytes_per_token / 1e6:.0f} MB of weights streamed every step vs 126 MB L2",
-                   "cuda_graph": False},
+                   "cuda_graph": not args.no_graph, "launches_per_step": int(launches) // max(1, K)},
         "roofline": {"bound": "hbm", "achieved": info.weight_bytes_per_token * (K / seconds) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": info.weight_bytes_per_token * (K / seconds) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                      "kernel": "whole batched step (weights streamed once per step for all sequences)"},

@@ -17,15 +17,17 @@ from uzu_b200 import synth
 pytestmark = [pytest.mark.gpu]
 
 
+@pytest.mark.parametrize("graph", [False, True])
 @pytest.mark.parametrize("kind,nseq", [("llama", 3), ("qwen-hybrid", 2), ("llama-512", 8)])
-def test_batched_decode_matches_independent_oracles(ctx, tmp_path, kind, nseq):
+def test_batched_decode_matches_independent_oracles(ctx, tmp_path, kind, nseq, graph):
+    """graph=True: the batched step is captured once into a CUDA graph and replayed with per-sequence positions read from the device."""
     spec = synth.tiny(kind)
     path = synth.write_model(spec, tmp_path / "m", seed=41)
     rng = np.random.default_rng(9)
     prompts = [rng.integers(0, spec.vocab_size, 5 + 7 * b) for b in range(nseq)]        # different lengths -> different positions per row
     refs = [OracleModel(path, max_context=128) for _ in range(nseq)]
     ref_logits = [r.prefill(p) for r, p in zip(refs, prompts)]
-    with B.Engine(ctx, path, max_context_length=128, use_cuda_graph=False) as eng:
+    with B.Engine(ctx, path, max_context_length=128, use_cuda_graph=graph) as eng:
         eng.batch_begin(nseq)
         firsts = [eng.batch_prefill(b, prompts[b]) for b in range(nseq)]
         toks = []
