@@ -768,338 +768,8 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_stream_kernel(const QmvPara
 // lane unpacks only the two (scale, zero-point) pairs of its own chunk: the affine work drops 4x, the
 // accumulator is zeroed once per 4 KB, and the two register buffers ping-pong without copies.
 // -------------------------------------------------------------------------------------------------
-template <int NPG>
-__global__ void __launch_bounds__(QS_WARPS * 32, 4) qmv_decode_kernel(const QmvParams p) {
-    static_assert(NPG == 64 || NPG == 128, "decode kernel covers int4 gs64 / gs128 and int8 gs64");
-    constexpr int CPM = NPG >= 128 ? 1 : 2;
-    constexpr int GPS = 512 / NPG;    // groups per super-chunk: 8 or 4
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    const uint32_t nc_all = p.chunks_total;
-    const uint32_t row_items = (nc_all * 16u + 31u) & ~31u;
-    const uint32_t ngroups = p.groups_per_row;
-    uint4* xs = reinterpret_cast<uint4*>(smem_raw);                            // [row_items] + one zero block of 4 x uint4
-    float* sx = reinterpret_cast<float*>(smem_raw + (size_t)(row_items + 4) * 16);   // [ngroups]
-    uint32_t magic;
-    asm volatile("mov.b32 %0, 0x43004300;" : "=r"(magic));
-
-    struct Buf {
-        uint4 wa[4], wb[4];
-        uint32_t sa, sb, ca, cb;
-    };
-    struct Item {
-        uint32_t tile, slice, cb, ce;
-        const uint8_t *wa_base, *wb_base;
-        const __nv_bfloat16 *sa_base, *sb_base;
-        const uint8_t *za_base, *zb_base;      // zero points (bytes) or MLX biases
-    };
-    const float mult128 = p.bits == 4 ? 128.0f : 128.0f * 17.0f;
-    const float sym_mid = p.bits == 4 ? 8.0f : 128.0f;
-    const bool lane_has_groups = 2 * t < GPS;       // NPG = 128: only lanes t = 0, 1 own columns
-    // which chunk of a super-chunk this lane feeds into the MMA B operand (column n = g)
-    const int b_chunk = CPM == 2 ? (g >> 1) : g;
-    const bool b_lane = CPM == 2 ? ((g & 1) == (t >> 1)) : true;
-
-    auto setup = [&](Item& it, uint32_t item) {
-        it.tile = item / p.kslices;
-        it.slice = item % p.kslices;
-        it.cb = it.slice * p.chunks_per_slice;
-        it.ce = min(p.chunks_total, it.cb + p.chunks_per_slice);
-        const uint32_t row_a = min(it.tile * 16u + (uint32_t)g, p.n - 1), row_b = min(it.tile * 16u + (uint32_t)g + 8u, p.n - 1);
-        it.wa_base = p.w + (size_t)row_a * p.row_bytes + (size_t)t * 16;
-        it.wb_base = p.w + (size_t)row_b * p.row_bytes + (size_t)t * 16;
-        it.sa_base = p.scales + (size_t)row_a * ngroups + 2 * t;
-        it.sb_base = p.scales + (size_t)row_b * ngroups + 2 * t;
-        if (p.method == UZU_QMETHOD_SCALE_BIAS) {
-            it.za_base = reinterpret_cast<const uint8_t*>(p.biases + (size_t)row_a * ngroups + 2 * t);
-            it.zb_base = reinterpret_cast<const uint8_t*>(p.biases + (size_t)row_b * ngroups + 2 * t);
-        } else if (p.bits == 4) {
-            it.za_base = p.zero_points + (size_t)row_a * p.zp_stride + t;
-            it.zb_base = p.zero_points + (size_t)row_b * p.zp_stride + t;
-        } else {
-            it.za_base = p.zero_points + (size_t)row_a * p.zp_stride + 2 * t;
-            it.zb_base = p.zero_points + (size_t)row_b * p.zp_stride + 2 * t;
-        }
-    };
-    auto load = [&](Buf& b, const Item& it, uint32_t c0) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            b.wa[j] = ldg_stream_u4(it.wa_base + (size_t)(c0 + j) * 64);
-            b.wb[j] = ldg_stream_u4(it.wb_base + (size_t)(c0 + j) * 64);
-        }
-        b.sa = b.sb = b.ca = b.cb = 0;
-        if (lane_has_groups) {
-            const uint32_t gi = (c0 * 128u) / NPG;   // groups gi + 2t, gi + 2t + 1 belong to this lane
-            b.sa = __ldg(reinterpret_cast<const uint32_t*>(it.sa_base + gi));
-            b.sb = __ldg(reinterpret_cast<const uint32_t*>(it.sb_base + gi));
-            if (p.method == UZU_QMETHOD_SCALE_ZERO_POINT) {
-                if (p.bits == 4) {
-                    b.ca = __ldg(it.za_base + gi / 2);
-                    b.cb = __ldg(it.zb_base + gi / 2);
-                } else {
-                    b.ca = __ldg(reinterpret_cast<const uint16_t*>(it.za_base + gi));
-                    b.cb = __ldg(reinterpret_cast<const uint16_t*>(it.zb_base + gi));
-                }
-            } else if (p.method == UZU_QMETHOD_SCALE_BIAS) {
-                b.ca = __ldg(reinterpret_cast<const uint32_t*>(it.za_base + (size_t)gi * 2));
-                b.cb = __ldg(reinterpret_cast<const uint32_t*>(it.zb_base + (size_t)gi * 2));
-            }
-        }
-        if (p.xor_mask) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                b.wa[j].x ^= p.xor_mask; b.wa[j].y ^= p.xor_mask; b.wa[j].z ^= p.xor_mask; b.wa[j].w ^= p.xor_mask;
-                b.wb[j].x ^= p.xor_mask; b.wb[j].y ^= p.xor_mask; b.wb[j].z ^= p.xor_mask; b.wb[j].w ^= p.xor_mask;
-            }
-        }
-    };
-
-    // ---- work distribution ------------------------------------------------------------------------------------
-    // A CTA owns an item = (group of TPC row tiles, global k-slice). Inside the item the k range of a tile is interleaved
-    // over WPT warps by super-chunk (so the CTA reads WPT x 256 contiguous bytes of every row per step) and the WPT
-    // partial sums meet in shared memory: no global atomics unless the host asked for a global k split (few-row shapes).
-    const uint32_t WPT = p.warps_per_tile, TPC = QS_WARPS / WPT;
-    const uint32_t tile_local = warp / WPT, kpart = warp % WPT;
-    const uint32_t tiles = (p.n + 15u) / 16u;
-    const uint32_t tile_groups = (tiles + TPC - 1) / TPC;
-    const uint32_t items_cta = tile_groups * p.kslices;
-    float* red = sx + ((ngroups + 3u) & ~3u);      // [2][QS_WARPS][16]
-
-    auto setup_cta = [&](Item& it, uint32_t item) {
-        const uint32_t tg = item / p.kslices;
-        setup(it, (tg * TPC + tile_local) * p.kslices + item % p.kslices);
-    };
-    auto first_sc = [&](const Item& it) { return it.cb + kpart * 4u; };
-
-    // The weights do not depend on the previous kernel: request this warp's first two super-chunks before waiting on
-    // the producer of the activations (programmatic dependent launch) and before the staging work.
-    Buf A, B;
-    Item cur;
-    uint32_t item = blockIdx.x;
-    bool preloaded = false;
-    if (item < items_cta) {
-        setup_cta(cur, item);
-        if (cur.tile < tiles) {
-            const uint32_t c0 = first_sc(cur);
-            if (c0 < cur.ce) load(A, cur, c0);
-            if (c0 + 4u * WPT < cur.ce) load(B, cur, c0 + 4u * WPT);
-        }
-        preloaded = true;
-    }
-    pdl_launch_dependents();
-    pdl_wait();
-    if (tid < 4) xs[row_items + tid] = make_uint4(0, 0, 0, 0);
-
-    {   // one-time staging of the activation row: all global loads of a batch are issued before any is consumed
-        constexpr uint32_t IPG = NPG / 8;
-        constexpr int BATCH = 4;
-        for (uint32_t base = tid; base < row_items; base += blockDim.x * BATCH) {
-            uint4 v[BATCH];
-#pragma unroll
-            for (int u = 0; u < BATCH; ++u) {
-                const uint32_t it = base + u * blockDim.x;
-                const uint32_t pos = it * 8u;
-                v[u] = make_uint4(0, 0, 0, 0);
-                if (it < nc_all * 16u && pos < p.np) {
-                    if (p.bits == 4) v[u] = *reinterpret_cast<const uint4*>(p.x + pos);
-                    else {
-                        const uint2 h = *reinterpret_cast<const uint2*>(p.x + pos / 2);
-                        v[u].x = h.x; v[u].y = h.y;
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < BATCH; ++u) {
-                const uint32_t it = base + u * blockDim.x;
-                if (it >= row_items) break;      // warp-uniform: row_items is a multiple of 32
-                const uint32_t pos = it * 8u;
-                uint4 out;
-                float part = 0.0f;
-                if (p.bits == 4) {
-                    out.x = __byte_perm(v[u].x, v[u].z, 0x5410);
-                    out.y = __byte_perm(v[u].x, v[u].z, 0x7632);
-                    out.z = __byte_perm(v[u].y, v[u].w, 0x5410);
-                    out.w = __byte_perm(v[u].y, v[u].w, 0x7632);
-                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { part += __low2float(h2[e]); part += __high2float(h2[e]); }
-                } else {
-                    __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v[u].x);
-                    __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&v[u].y);
-                    const float x0 = __low2float(a), x1 = __high2float(a), x2 = __low2float(b), x3 = __high2float(b);
-                    __nv_bfloat162 o0 = __floats2bfloat162_rn(x0, x2);
-                    __nv_bfloat162 o1 = __floats2bfloat162_rn(16.0f * x0, 16.0f * x2);
-                    __nv_bfloat162 o2 = __floats2bfloat162_rn(x1, x3);
-                    __nv_bfloat162 o3 = __floats2bfloat162_rn(16.0f * x1, 16.0f * x3);
-                    out.x = *reinterpret_cast<uint32_t*>(&o0);
-                    out.y = *reinterpret_cast<uint32_t*>(&o1);
-                    out.z = *reinterpret_cast<uint32_t*>(&o2);
-                    out.w = *reinterpret_cast<uint32_t*>(&o3);
-                    part = ((x0 + x1) + x2) + x3;
-                }
-                if (it < nc_all * 16u) xs[it] = out;
-#pragma unroll
-                for (uint32_t o = 1; o < IPG; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                const uint32_t gl = pos / NPG;
-                if ((it & (IPG - 1)) == 0 && gl < ngroups) sx[gl] = part;
-            }
-        }
-    }
-    __syncthreads();
-
-    uint32_t parity = 0;
-    for (; item < items_cta; item += gridDim.x, parity ^= 1u) {
-        if (!preloaded) {
-            setup_cta(cur, item);
-            if (cur.tile < tiles) {
-                const uint32_t c0 = first_sc(cur);
-                if (c0 < cur.ce) load(A, cur, c0);
-                if (c0 + 4u * WPT < cur.ce) load(B, cur, c0 + 4u * WPT);
-            }
-        }
-        preloaded = false;
-        const uint32_t tile = cur.tile, slice = cur.slice, ce = cur.ce;
-        const uint32_t step = 4u * WPT;
-
-        float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
-
-        auto compute = [&](const Buf& b, uint32_t c0) {
-            // two independent accumulator fragments halve the dependent HMMA chain (32 MMAs per super-chunk)
-            float d[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d2[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t wav[4] = {b.wa[j].x, b.wa[j].y, b.wa[j].z, b.wa[j].w};
-                const uint32_t wbv[4] = {b.wb[j].x, b.wb[j].y, b.wb[j].z, b.wb[j].w};
-                const bool feeds = b_lane && b_chunk == j;
-                // lanes that do not feed this chunk's column read a shared zero block (no predication, no register zeroing)
-                const uint4* xrow = feeds ? xs + ((size_t)(c0 + j) * 4 + t) * 4 : xs + row_items;
-#pragma unroll
-                for (int w_ = 0; w_ < 4; ++w_) {
-                    const uint4 xb = xrow[w_];
-                    const uint32_t a0 = nib_pair_fast(wav[w_], 0, magic), a1 = nib_pair_fast(wav[w_], 4, magic), a2 = nib_pair_fast(wav[w_], 8, magic), a3 = nib_pair_fast(wav[w_], 12, magic);
-                    const uint32_t b0 = nib_pair_fast(wbv[w_], 0, magic), b1 = nib_pair_fast(wbv[w_], 4, magic), b2 = nib_pair_fast(wbv[w_], 8, magic), b3 = nib_pair_fast(wbv[w_], 12, magic);
-                    mma_16816(d, a0, b0, a1, b1, xb.x, xb.y);
-                    mma_16816(d2, a2, b2, a3, b3, xb.z, xb.w);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) d[i] += d2[i];
-            // this lane's two D columns (2t, 2t+1) hold groups gi + 2t and gi + 2t + 1 of rows g (d0, d1) and g+8 (d2, d3)
-            if (lane_has_groups) {
-                const uint32_t gi = (c0 * 128u) / NPG + 2 * t;
-                const float2 sxv = *reinterpret_cast<const float2*>(sx + gi);
-                const float sa0 = __uint_as_float(b.sa << 16), sa1 = __uint_as_float(b.sa & 0xffff0000u);
-                const float sb0 = __uint_as_float(b.sb << 16), sb1 = __uint_as_float(b.sb & 0xffff0000u);
-                if (p.method == UZU_QMETHOD_SCALE_ZERO_POINT) {
-                    float ka0, ka1, kb0, kb1;   // value = s * (d + k * Sx)
-                    if (p.bits == 4) {
-                        ka0 = -((float)(b.ca & 15u) + mult128); ka1 = -((float)((b.ca >> 4) & 15u) + mult128);
-                        kb0 = -((float)(b.cb & 15u) + mult128); kb1 = -((float)((b.cb >> 4) & 15u) + mult128);
-                    } else {
-                        ka0 = -((float)(b.ca & 255u) + mult128); ka1 = -((float)((b.ca >> 8) & 255u) + mult128);
-                        kb0 = -((float)(b.cb & 255u) + mult128); kb1 = -((float)((b.cb >> 8) & 255u) + mult128);
-                    }
-                    acc0 += sa0 * (d[0] + ka0 * sxv.x);
-                    acc1 += sa1 * (d[1] + ka1 * sxv.y);
-                    acc2 += sb0 * (d[2] + kb0 * sxv.x);
-                    acc3 += sb1 * (d[3] + kb1 * sxv.y);
-                } else if (p.method == UZU_QMETHOD_SCALE_BIAS) {
-                    const float ba0 = __uint_as_float(b.ca << 16), ba1 = __uint_as_float(b.ca & 0xffff0000u);
-                    const float bb0 = __uint_as_float(b.cb << 16), bb1 = __uint_as_float(b.cb & 0xffff0000u);
-                    acc0 += sa0 * (d[0] - mult128 * sxv.x) + ba0 * sxv.x;
-                    acc1 += sa1 * (d[1] - mult128 * sxv.y) + ba1 * sxv.y;
-                    acc2 += sb0 * (d[2] - mult128 * sxv.x) + bb0 * sxv.x;
-                    acc3 += sb1 * (d[3] - mult128 * sxv.y) + bb1 * sxv.y;
-                } else {
-                    const float k = -(sym_mid + mult128);
-                    acc0 += sa0 * (d[0] + k * sxv.x);
-                    acc1 += sa1 * (d[1] + k * sxv.y);
-                    acc2 += sb0 * (d[2] + k * sxv.x);
-                    acc3 += sb1 * (d[3] + k * sxv.y);
-                }
-            }
-        };
-
-        if (tile < tiles) {
-            for (uint32_t c0 = first_sc(cur); c0 < ce; c0 += 2 * step) {
-                const bool has_b = c0 + step < ce;
-                compute(A, c0);
-                if (c0 + 2 * step < ce) load(A, cur, c0 + 2 * step);
-                if (!has_b) break;
-                compute(B, c0 + step);
-                if (c0 + 3 * step < ce) load(B, cur, c0 + 3 * step);
-            }
-        }
-        // prefetch the next item of this CTA before the reduction (its weights are independent of everything above)
-        const uint32_t next_item = item + gridDim.x;
-        Item nxt;
-        if (next_item < items_cta) {
-            setup_cta(nxt, next_item);
-            if (nxt.tile < tiles) {
-                const uint32_t c0 = first_sc(nxt);
-                if (c0 < nxt.ce) load(A, nxt, c0);
-                if (c0 + step < nxt.ce) load(B, nxt, c0 + step);
-            }
-            preloaded = true;
-        }
-
-        // ---- quad reduction (fixed order), CTA reduction through shared memory, epilogue --------------------------------
-        float ra = acc0 + acc1, rb = acc2 + acc3;
-        ra += __shfl_xor_sync(0xffffffffu, ra, 1);
-        rb += __shfl_xor_sync(0xffffffffu, rb, 1);
-        ra += __shfl_xor_sync(0xffffffffu, ra, 2);
-        rb += __shfl_xor_sync(0xffffffffu, rb, 2);
-        float* redp = red + parity * (QS_WARPS * 16);
-        if (t == 0) {
-            redp[warp * 16 + g] = ra;
-            redp[warp * 16 + g + 8] = rb;
-        }
-        __syncthreads();
-        auto epilogue_store = [&](uint32_t row, float v) {
-            if (row >= p.n) return;
-            float value = p.ab_scale * v;
-            if (p.accumulate) value += p.d_is_f32 ? reinterpret_cast<float*>(p.d)[row] : __bfloat162float(reinterpret_cast<__nv_bfloat16*>(p.d)[row]);
-            if (p.bias) value += __bfloat162float(p.bias[row]);
-            if (p.has_soft_cap) value = p.soft_cap * tanhf(value / p.soft_cap);
-            if (p.d_is_f32) reinterpret_cast<float*>(p.d)[row] = value;
-            else reinterpret_cast<__nv_bfloat16*>(p.d)[row] = __float2bfloat16_rn(value);
-        };
-        // warp w < TPC finishes tile_local = w: lanes 0..15 own one output row each
-        if (warp < TPC) {
-            const uint32_t my_tile = (item / p.kslices) * TPC + warp;
-            if (my_tile < tiles) {
-                float sum = 0.0f;
-                if (lane < 16)
-                    for (uint32_t kp = 0; kp < WPT; ++kp) sum += redp[(warp * WPT + kp) * 16 + lane];
-                if (p.kslices == 1) {
-                    if (lane < 16) epilogue_store(my_tile * 16u + lane, sum);
-                } else {
-                    float* wst = p.ws + ((size_t)my_tile * p.kslices + slice) * 16;
-                    if (lane < 16) wst[lane] = sum;
-                    __threadfence();
-                    __syncwarp();
-                    unsigned int ticket = 0;
-                    if (lane == 0) ticket = atomicAdd(&p.counters[my_tile], 1u);
-                    ticket = __shfl_sync(0xffffffffu, ticket, 0);
-                    if (ticket == p.kslices - 1) {
-                        __threadfence();
-                        if (lane < 16) {
-                            const float* wt = p.ws + (size_t)my_tile * p.kslices * 16;
-                            float total = 0.0f;
-                            for (uint32_t sl = 0; sl < p.kslices; ++sl) total += __ldcg(wt + (size_t)sl * 16 + lane);
-                            epilogue_store(my_tile * 16u + lane, total);
-                        }
-                        __syncwarp();
-                        if (lane == 0) p.counters[my_tile] = 0;
-                    }
-                }
-            }
-        }
-        cur = nxt;
-        (void)slice;
-    }
-}
+// (The register-pipelined instance of this specialisation, qmv_decode_kernel, was removed in round 2: it was reachable only through
+// UZU_QMV_REGS after the cp.async variant below replaced it; rows too long for the rings take the streaming kernel above.)
 
 // -------------------------------------------------------------------------------------------------
 // cp.async variant of the decode kernel: the same arithmetic, but the weight stream lands in a per-warp
@@ -1778,13 +1448,6 @@ static void launch_qmv(uzu_command_buffer* cmd, const QmvParams& p, uint32_t til
     after_launch(cmd, "qmv_kernel");
 }
 
-template <int NPG>
-static void launch_qmv_decode(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
-    static std::atomic<uint64_t> smem_opt_in{0};
-    opt_in_dynamic_smem(cmd, qmv_decode_kernel<NPG>, (int)(200 * 1024), smem_opt_in);
-    launch(cmd, "qmv_decode_kernel", qmv_decode_kernel<NPG>, dim3(grid), dim3(QS_WARPS * 32), smem, p);
-}
-
 template <int NPG, int STAGES, int METHOD, int BITS, int PRO, bool EPI>
 static void launch_qmv_decode_async_s(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
     static std::atomic<uint64_t> smem_opt_in{0};
@@ -1948,7 +1611,9 @@ static bool encode_matmul(uzu_command_buffer* cmd, uzu_context* ctx_for_query, c
             const uint32_t items = tiles * ks;
             const uint32_t use_grid = std::min(grid, std::max(1u, (items + QS_WARPS - 1) / QS_WARPS));
             static const bool no_decode_kernel = getenv("UZU_QMV_NO_DECODE") != nullptr;
-            if (mb == 1 && (npg == 64 || npg == 128) && !no_decode_kernel) {
+            // the m == 1 decode kernel needs the activation row + its rings in shared memory; longer rows take the streaming kernel below
+            const size_t decode_smem = stream_smem + 2 * QS_WARPS * 16 * 4 + 64 + (size_t)QS_WARPS * QA_STAGES * QA_STAGE_BYTES;
+            if (mb == 1 && (npg == 64 || npg == 128) && !no_decode_kernel && decode_smem <= 200u * 1024u) {
                 // CTA items: TPC tiles x one global k-slice; k split over the CTA's warps first, over CTAs only for few-row shapes
                 uint32_t dks = 1;
                 {
@@ -2001,7 +1666,6 @@ static bool encode_matmul(uzu_command_buffer* cmd, uzu_context* ctx_for_query, c
                 p.kslices = dks;
                 p.warps_per_tile = wpt;
                 const size_t dsmem = stream_smem + 2 * QS_WARPS * 16 * 4 + 64;
-                static const bool use_regs = getenv("UZU_QMV_REGS") != nullptr;
                 const size_t asmem = dsmem + (size_t)QS_WARPS * QA_STAGES * QA_STAGE_BYTES;
                 const size_t fsmem = asmem + (fused && fused->prologue ? (size_t)a.k * 2 + 64 : 0);
                 if (fused) {
@@ -2043,7 +1707,7 @@ static bool encode_matmul(uzu_command_buffer* cmd, uzu_context* ctx_for_query, c
                     else launch_qmv_decode_async<128>(cmd, p, agrid, lsmem);
                     return true;
                 }
-                if (!use_regs && asmem <= 200u * 1024u) {
+                {
                     const uint32_t per_sm = std::max(1u, std::min(per_sm_cap, (uint32_t)((220u * 1024u) / (asmem + 1024u))));
                     const uint32_t aitems = std::max(1u, tgroups * dks), amax = per_sm * (uint32_t)ctx->sm_count;
                     const uint32_t rounds = (aitems + amax - 1) / amax;
@@ -2054,10 +1718,6 @@ static bool encode_matmul(uzu_command_buffer* cmd, uzu_context* ctx_for_query, c
                     else launch_qmv_decode_async<128>(cmd, p, agrid, lsmem);
                     continue;
                 }
-                const uint32_t dgrid = std::min(std::min(grid, 4u * (uint32_t)ctx->sm_count), std::max(1u, tgroups * dks));   // 128 regs -> 4 CTAs / SM
-                if (npg == 64) launch_qmv_decode<64>(cmd, p, dgrid, dsmem);
-                else launch_qmv_decode<128>(cmd, p, dgrid, dsmem);
-                continue;
             }
             if (fused) return false;
             switch (npg) {
