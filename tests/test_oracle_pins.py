@@ -383,3 +383,67 @@ def test_delta_net_update_vs_float64():
         z = xf[2 * kd + vd + hv * Dv: 2 * kd + vd + (hv + 1) * Dv]
         ref[hv * Dv:(hv + 1) * Dv] = o / np.sqrt((o * o).mean() + 1e-6) * nw * (z / (1 + np.exp(-z)))
     np.testing.assert_allclose(bf16_to_f32(out), ref, rtol=1.5e-2, atol=2e-3)
+
+
+# ---- round 2: float64 twins for the remaining thin spots (conv update, two-pass block merge, sigmoid gate, KV-cache update) ----
+
+def test_delta_net_conv_update_vs_float64():
+    """gdn/conv_update.rs:8-55: out = silu(bias + sum_t state[t] * w[t] + x * w[last]) rounded to bf16; state shifts left and takes x."""
+    rng = np.random.default_rng(21)
+    for K, C_, has_bias in [(4, 96, True), (2, 40, False), (7, 17, True)]:
+        w = rng.standard_normal((C_, K)).astype(np.float32) * 0.5
+        bias = rng.standard_normal(C_).astype(np.float32) * 0.1 if has_bias else None
+        x = f32_to_bf16(rng.standard_normal(C_).astype(np.float32))
+        st = rng.standard_normal((C_, K - 1)).astype(np.float32)
+        st0, xf = st.astype(np.float64), bf16_to_f32(x).astype(np.float64)
+        io = x.copy()
+        O.delta_net_conv_update(w, bias if has_bias else np.zeros(C_, np.float32), io, st, K, C_) if has_bias else \
+            O.delta_net_conv_update(w, None, io, st, K, C_)
+        acc = (bias.astype(np.float64) if has_bias else 0.0) + (st0 * w[:, :K - 1]).sum(1) + xf * w[:, K - 1]
+        ref = acc / (1 + np.exp(-acc))
+        np.testing.assert_allclose(bf16_to_f32(io), ref, rtol=1e-2, atol=2e-3)          # bf16 output
+        np.testing.assert_array_equal(st[:, :K - 2], st0[:, 1:].astype(np.float32))       # shifted left, exactly
+        np.testing.assert_array_equal(st[:, K - 2], bf16_to_f32(x))                       # newest input, exactly
+
+
+def test_two_pass_partials_merge_like_a_float64_softmax():
+    """attention_two_pass.rs:55-189: pass 1 leaves per-block (max, sum, unnormalised output); pass 2 merges 32 blocks. The merged
+    result must be the float64 softmax over all keys, and each block's statistics must be the float64 statistics of ITS keys
+    (block of key i = i % 32)."""
+    H, Hkv, seq, suffix, D = 4, 2, 200, 1, 64
+    q, k, v = attention_inputs(H, Hkv, seq, suffix, D)
+    kw = dict(head_dim=D, gqa_factor=H // Hkv, sequence_length=seq, k_head_stride=seq * D, k_seq_stride=D, v_head_stride=seq * D,
+              v_seq_stride=D, scale=float(np.float32(1.0) / np.sqrt(np.float32(D))), num_heads=H, suffix_length=suffix, is_causal=True)
+    out, partials, sums, maxs = O.attention_two_pass(q, k, v, return_partials=True, **kw)
+    qf = bf16_to_f32(q).astype(np.float64).reshape(H, suffix, D)
+    kf = bf16_to_f32(k).astype(np.float64).reshape(Hkv, seq, D)
+    vf = bf16_to_f32(v).astype(np.float64).reshape(Hkv, seq, D)
+    for h in range(H):
+        s = (kf[h // (H // Hkv)] @ (qf[h, 0] * kw["scale"]))
+        for blk in range(32):
+            idx = np.arange(blk, seq, 32)
+            m = s[idx].max()
+            np.testing.assert_allclose(maxs[0, h, blk], m, rtol=1e-5, atol=1e-5)
+            p = np.exp(s[idx] - m)
+            np.testing.assert_allclose(sums[0, h, blk], p.sum(), rtol=1e-4)
+            np.testing.assert_allclose(partials[0, h, blk], p @ vf[h // (H // Hkv)][idx], rtol=1e-3, atol=1e-4)
+        p = np.exp(s - s.max()); p /= p.sum()
+        np.testing.assert_allclose(bf16_to_f32(out[0, h]), p @ vf[h // (H // Hkv)], rtol=1e-2, atol=2e-3)
+
+
+def test_sigmoid_gate_and_kv_cache_update_closed_forms():
+    rng = np.random.default_rng(22)
+    gate = f32_to_bf16(rng.standard_normal(300).astype(np.float32) * 3)
+    val = f32_to_bf16(rng.standard_normal(300).astype(np.float32))
+    got = O.sigmoid_gate(gate, val.copy())
+    ref = bf16_to_f32(val).astype(np.float64) / (1 + np.exp(-bf16_to_f32(gate).astype(np.float64)))
+    np.testing.assert_allclose(bf16_to_f32(got), ref, rtol=1e-2, atol=1e-3)
+    # kv_cache_update.rs:7-28: copies are applied in order, a later copy sees the rows written by an earlier one
+    E = 16
+    keys = f32_to_bf16(rng.standard_normal((10, E)).astype(np.float32)); values = f32_to_bf16(rng.standard_normal((10, E)).astype(np.float32))
+    copies = [(7, 2), (2, 5), (9, 7)]
+    ek, ev = keys.copy(), values.copy()
+    for s_, d_ in copies:
+        ek[d_] = ek[s_]; ev[d_] = ev[s_]
+    O.kv_cache_update(keys, values, copies, E)
+    assert (keys == ek).all() and (values == ev).all()
