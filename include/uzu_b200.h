@@ -195,6 +195,10 @@ typedef struct uzu_fused_linear_args {
     /* epilogue 1: the matmul's n = 2F rows are [up | gate] (DenseMlp's fused up projection, mlp/dense.rs:32-48); instead of the
      * 2F row the kernel stores hidden[j] = GatedActMul(up_j, gate_j) (act_type) as bf16 [F] into matmul.d. prologue may be 0. */
     uint32_t epilogue, reserved0;
+    /* optional decode-stream copy of matmul.b (unit-major 4608-byte units, built by the engine at load; 0 = none): the decode GEMV then feeds
+     * its shared-memory rings with one TMA bulk copy per stage (UBLKCP) instead of per-lane cp.async. With a stream, prologue 0 + epilogue 0
+     * (a plain GEMV over matmul.a) is accepted too. */
+    uint64_t decode_stream;
 } uzu_fused_linear_args;
 /* Tuning sweeps only (tools/): override the decode GEMV's work split; 0 = heuristic. Process-wide, not thread-safe. */
 UZU_API void uzu_debug_set_qmv_tuning(int warps_per_tile, int k_slices, int ctas_per_sm, int stages);

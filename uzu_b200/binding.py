@@ -123,7 +123,7 @@ TpAllGatherArgs = _struct("uzu_tp_all_gather_args", [("src", u64), ("dst", u64),
 FusedLinearArgs = _struct("uzu_fused_linear_args", [
     ("matmul", MatmulArgs), ("prologue", u32), ("norm_input", u64), ("norm_shortcut_in", u64), ("norm_scales", u64), ("shortcut_out", u64),
     ("norm_epsilon", f32), ("norm_scale_offset", f32), ("norm_residual_add", u32), ("norm_full_layer", u32), ("act_operand", u64),
-    ("act_type", u32), ("sg_attn", u64), ("sg_gate", u64), ("epilogue", u32), ("reserved0", u32)])
+    ("act_type", u32), ("sg_attn", u64), ("sg_gate", u64), ("epilogue", u32), ("reserved0", u32), ("decode_stream", u64)])
 
 ABI_STRUCTS = [DeltaNetFusedUpdateArgs, QkNormConfig, AttentionPrepareNormArgs, FusedLinearArgs, RingParams, TrieNode, KvCopy, MatmulArgs, NormalizationArgs, QkvNormArgs, AttentionPrepareArgs, AttentionArgs,
                AttentionTwoPass2Args, KvCacheUpdateArgs, GatedActMulArgs, QuantizedEmbeddingLookupArgs, UnifiedSamplingArgs,

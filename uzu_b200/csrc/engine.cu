@@ -434,6 +434,7 @@ struct uzu_engine {
         uint32_t nstreams = 0;
         uint64_t stream_bytes = 0;
         uint64_t barrier_base = 0;       // arrivals the monotonic grid-barrier counter has seen before the next launch
+        std::map<uint64_t, uint64_t> stream_of;   // weight values pointer -> decode-stream copy (also feeds the per-kernel path's TMA GEMV)
     } mega;
 };
 
@@ -1149,6 +1150,12 @@ static uzu_matmul_args linear_args(const Linear& l, uint64_t a, uint32_t m, uint
     return ma;
 }
 
+// decode-stream copy of a linear's weights (built with the persistent kernel's program) or 0
+static uint64_t g_stream_lookup(const std::map<uint64_t, uint64_t>& m, const Linear& l) {
+    auto it = m.find(l.w.values.ptr());
+    return it == m.end() ? 0 : it->second;
+}
+
 static uzu_fused_linear_args fused_norm_args(const Linear& l, const Norm& n, uint64_t input, uint64_t sc_in, uint64_t sc_out, bool add, uint64_t d) {
     uzu_fused_linear_args f{};
     f.matmul = linear_args(l, 0, 1, d);
@@ -1206,6 +1213,21 @@ static bool fused_decode_supported(uzu_engine* e) {
     return true;
 }
 
+// a plain m = 1 GEMV of the decode step: through the TMA-fed stream variant when the linear has a decode-stream copy
+static void encode_decode_gemv(uzu_engine* e, uzu_command_buffer* cmd, const Linear& lin, uint64_t x, uint64_t d) {
+    const uint64_t stream = e->tp_sharded ? 0 : g_stream_lookup(e->mega.stream_of, lin);
+    if (stream) {
+        uzu_fused_linear_args f{};
+        f.matmul = linear_args(lin, x, 1, d);
+        f.decode_stream = stream;
+        if (uzu_fused_linear_supported(e->ctx, &f)) {
+            uzu_fused_linear_encode(cmd, &f);
+            return;
+        }
+    }
+    encode_row_parallel(e, cmd, lin, x, 1, d);
+}
+
 static void encode_decoder_fused(uzu_engine* e, uzu_command_buffer* cmd, const PassCtx& pc) {
     const uint32_t H = e->model_dim;
     const uint32_t mask = fuse_mask();
@@ -1237,6 +1259,7 @@ static void encode_decoder_fused(uzu_engine* e, uzu_command_buffer* cmd, const P
         auto mixer_in_linear = [&](const Linear& lin, uint64_t d) {
             if (fuse_norm) {
                 auto f = fused_norm_args(lin, L.pre_mixer, e->hidden_a.ptr(), S[cur], wrote ? 0 : S[cur ^ 1], add, d);
+                f.decode_stream = g_stream_lookup(e->mega.stream_of, lin);
                 uzu_fused_linear_encode(cmd, &f);
                 wrote = true;
             } else {
@@ -1296,10 +1319,11 @@ static void encode_decoder_fused(uzu_engine* e, uzu_command_buffer* cmd, const P
                 uzu_fused_linear_args g{};
                 g.matmul = linear_args(A.out, 0, 1, e->mixer_out.ptr());
                 g.prologue = 3; g.sg_attn = e->attn_out.ptr(); g.sg_gate = e->gate.ptr();
+                g.decode_stream = g_stream_lookup(e->mega.stream_of, A.out);
                 uzu_fused_linear_encode(cmd, &g);
             } else {
                 if (A.has_gate) uzu_sigmoid_gate_encode(cmd, e->gate.ptr(), e->attn_out.ptr(), Hq * D);
-                encode_row_parallel(e, cmd, A.out, e->attn_out.ptr(), 1, e->mixer_out.ptr());
+                encode_decode_gemv(e, cmd, A.out, e->attn_out.ptr(), e->mixer_out.ptr());
             }
         } else {
             const DeltaNetLayer& Dn = L.dn;
@@ -1319,13 +1343,14 @@ static void encode_decoder_fused(uzu_engine* e, uzu_command_buffer* cmd, const P
                 uzu_delta_net_conv_update_encode(cmd, &ca);
                 uzu_delta_net_update_encode(cmd, &ua);
             }
-            encode_linear(cmd, Dn.out_proj, e->delta_out.ptr(), 1, e->mixer_out.ptr());
+            encode_decode_gemv(e, cmd, Dn.out_proj, e->delta_out.ptr(), e->mixer_out.ptr());
         }
         if (fuse_norm) cur ^= 1;
         // pre_mlp_norm + DenseMlp (mlp/dense.rs:32-48)
         if (!fuse_norm) encode_norm(cmd, L.pre_mlp, e->mixer_out.ptr(), e->hidden_b.ptr(), S[cur], ShortcutAdd, 1);
         if (fuse_norm || fuse_gated) {
             auto fu = fused_up_args(e, L, fuse_norm, S[cur], S[cur ^ 1]);
+            fu.decode_stream = g_stream_lookup(e->mega.stream_of, L.up);
             uzu_fused_linear_encode(cmd, &fu);
         } else {
             encode_linear(cmd, L.up, e->hidden_b.ptr(), 1, e->fused_up.ptr());
@@ -1337,11 +1362,12 @@ static void encode_decoder_fused(uzu_engine* e, uzu_command_buffer* cmd, const P
             ga.act_type = L.act; ga.interleaved = 1;
             uzu_gated_act_mul_encode(cmd, &ga);
         }
-        encode_row_parallel(e, cmd, L.down, e->gated.ptr(), 1, e->hidden_a.ptr());
+        encode_decode_gemv(e, cmd, L.down, e->gated.ptr(), e->hidden_a.ptr());
     }
     // output norm with the residual add in place on the current residual buffer (transformer.rs:317-323), readout, logit transform
     encode_norm(cmd, e->out_norm, e->hidden_a.ptr(), e->normed_out.ptr(), S[cur], ShortcutAdd, 1);
-    encode_readout(e, cmd, e->normed_out.ptr(), 1);
+    if (!e->tp_sharded && g_stream_lookup(e->mega.stream_of, e->out_emb)) encode_decode_gemv(e, cmd, e->out_emb, e->normed_out.ptr(), e->logits.ptr());
+    else encode_readout(e, cmd, e->normed_out.ptr(), 1);
     if (e->has_logit_scale || e->has_logit_soft_cap)
         uzu_logit_transform_encode(cmd, e->logits.ptr(), e->vocab, e->has_logit_scale ? e->logit_scale : 1.0f, e->logit_soft_cap, e->has_logit_soft_cap);
     (void)pc;
@@ -1392,6 +1418,7 @@ struct MegaBuilder {
             mega_repack(e->ctx, (const uint8_t*)l.w.values.ptr(), (const __nv_bfloat16*)l.w.scales.ptr(), (const uint8_t*)l.w.zero_points.ptr(),
                         (const __nv_bfloat16*)l.w.biases.ptr(), l.out_dim, l.in_dim, bits, group_size, method, (uint8_t*)b.ptr());
             mg.stream_bytes += bytes;
+            mg.stream_of[key] = b.ptr();
             it = streams.emplace(key, b).first;
         }
         return (const uint8_t*)it->second.ptr();

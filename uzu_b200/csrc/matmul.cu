@@ -69,6 +69,10 @@ struct QmvParams {
     uint32_t d_is_f32;
     uint32_t accumulate, has_soft_cap;
     float ab_scale, soft_cap;
+    // decode-stream copy of the matrix (decode_mega.cu mega_repack: unit-major 4608-byte units = 16 rows x 512 nibbles + coefficients), or null.
+    // With it the decode kernel (METHOD == QMV_TMA) feeds its rings with ONE TMA bulk copy per stage instead of 12 cp.async per lane.
+    const uint8_t* stream;
+    uint32_t stream_C, pad_stream;
 };
 
 __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
@@ -781,9 +785,24 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_stream_kernel(const QmvPara
 #ifndef UZU_QA_ACCS
 #define UZU_QA_ACCS 2
 #endif
+constexpr int QMV_TMA = 3;             // pseudo quantisation method: zero-point form read from the decode-stream layout through TMA bulk copies
 constexpr int QA_STAGES = 2;         // base ring depth used for shared-memory sizing; the launch may deepen it (pick_stages)
 constexpr uint32_t QA_STAGE_BYTES = 4096 + 512;
 
+// TMA bulk copy + mbarrier helpers of the decode-stream variant (METHOD == QMV_TMA)
+__device__ __forceinline__ void qa_mbar_init(uint32_t addr) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(addr) : "memory"); }
+__device__ __forceinline__ void qa_mbar_expect_tx(uint32_t addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool qa_mbar_try_wait(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    return ok != 0;
+}
+// (weights are read once per token: L2 evict-first keeps the small hot rows -- activations, residual, norm scales -- resident)
+__device__ __forceinline__ void qa_bulk_copy(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_addr), "l"(gptr) : "memory");
 }
@@ -800,8 +819,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // PRO: 0 none, 1 RMSNorm (+ residual add), 3 sigmoid gate (prologue 2, gated act, moved to the producer's epilogue); EPI: GatedActMul
 template <int NPG, int STAGES, int METHOD, int BITS, int PRO, bool EPI>
 __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const QmvParams p) {
-    constexpr uint32_t method = METHOD, bits = BITS;
+    constexpr bool TMA = METHOD == QMV_TMA;
+    constexpr uint32_t method = TMA ? (uint32_t)UZU_QMETHOD_SCALE_ZERO_POINT : (uint32_t)METHOD, bits = BITS;
     static_assert(NPG == 64 || NPG == 128, "decode kernel covers int4 gs64 / gs128 and int8 gs64");
+    __shared__ uint64_t tma_bars[QS_WARPS * 4];      // TMA mode: one mbarrier per (warp, ring stage)
     constexpr int CPM = NPG >= 128 ? 1 : 2;
     constexpr int GPS = 512 / NPG;    // groups per super-chunk: 8 or 4
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -820,6 +841,14 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
     __nv_bfloat16* xrow = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(red + 2 * QS_WARPS * 16) + (size_t)QS_WARPS * STAGES * QA_STAGE_BYTES);
     uint32_t magic;
     asm volatile("mov.b32 %0, 0x43004300;" : "=r"(magic));
+    const uint32_t bars_s = (uint32_t)__cvta_generic_to_shared(tma_bars) + (uint32_t)warp * STAGES * 8u;
+    uint64_t l2_policy = 0;
+    if (TMA) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_policy));
+    if (TMA) {
+        if (tid < QS_WARPS * STAGES) qa_mbar_init((uint32_t)__cvta_generic_to_shared(tma_bars) + (uint32_t)tid * 8u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
 
     struct Item {
         uint32_t tile, slice, cb, ce;
@@ -840,6 +869,7 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
         it.slice = item % p.kslices;
         it.cb = it.slice * p.chunks_per_slice;
         it.ce = min(p.chunks_total, it.cb + p.chunks_per_slice);
+        if (TMA) return;                 // the stream is addressed by (tile, super-chunk) alone
         const uint32_t row_a = min(it.tile * 16u + (uint32_t)g, p.n - 1), row_b = min(it.tile * 16u + (uint32_t)g + 8u, p.n - 1);
         it.wa_base = p.w + (size_t)row_a * p.row_bytes + (size_t)t * 16;
         it.wb_base = p.w + (size_t)row_b * p.row_bytes + (size_t)t * 16;
@@ -861,6 +891,14 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
     // one stage = one super-chunk of this warp: 8 x 16 B of packed weights per lane + its scale / zero-point words,
     // copied global -> shared with cp.async (no registers held while in flight)
     auto issue_stage = [&](const Item& it, uint32_t c0, uint32_t slot) {
+        if (TMA) {
+            // one 4608-byte unit of the decode stream = exactly this stage (codes in lane order + scale / zero-point words)
+            if (lane == 0) {
+                qa_mbar_expect_tx(bars_s + slot * 8u, QA_STAGE_BYTES);
+                qa_bulk_copy(ring_s + slot * QA_STAGE_BYTES, p.stream + ((size_t)it.tile * p.stream_C + c0 / 4u) * QA_STAGE_BYTES, QA_STAGE_BYTES, bars_s + slot * 8u, l2_policy);
+            }
+            return;
+        }
         const uint32_t sbase = ring_s + slot * QA_STAGE_BYTES + (uint32_t)lane * 16u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -930,7 +968,7 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
             issue_stage(ic.it, ic.c0, issued % STAGES);
             ic.c0 += 4u * WPT;
         }
-        cp_async_commit();       // always commit (possibly empty) so wait_group<STAGES-1> means "oldest stage landed"
+        if (!TMA) cp_async_commit();       // always commit (possibly empty) so wait_group<STAGES-1> means "oldest stage landed"
         ++issued;
     };
 #pragma unroll
@@ -1176,7 +1214,7 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
                 const float2 sxv = *reinterpret_cast<const float2*>(sx + gi);
                 const uint32_t bsa = swd[0], bsb = swd[32];
                 uint32_t bca = swd[64], bcb = swd[96];
-                if (method == UZU_QMETHOD_SCALE_ZERO_POINT) {
+                if (method == UZU_QMETHOD_SCALE_ZERO_POINT && !TMA) {
                     const uint32_t goff = bits == 4 ? ((c0 * 128u) / NPG) / 2 : (c0 * 128u) / NPG;
                     bca >>= ((cur.za_off + goff) & 3u) * 8u;
                     bcb >>= ((cur.zb_off + goff) & 3u) * 8u;
@@ -1185,7 +1223,10 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
                 const float sb0 = __uint_as_float(bsb << 16), sb1 = __uint_as_float(bsb & 0xffff0000u);
                 if (method == UZU_QMETHOD_SCALE_ZERO_POINT) {
                     float ka0, ka1, kb0, kb1;   // value = s * (d + k * Sx)
-                    if (bits == 4) {
+                    if (TMA) {              // the stream carries the zero points as exact bf16 pairs
+                        ka0 = -(__uint_as_float(bca << 16) + mult128); ka1 = -(__uint_as_float(bca & 0xffff0000u) + mult128);
+                        kb0 = -(__uint_as_float(bcb << 16) + mult128); kb1 = -(__uint_as_float(bcb & 0xffff0000u) + mult128);
+                    } else if (bits == 4) {
                         ka0 = -((float)(bca & 15u) + mult128); ka1 = -((float)((bca >> 4) & 15u) + mult128);
                         kb0 = -((float)(bcb & 15u) + mult128); kb1 = -((float)((bcb >> 4) & 15u) + mult128);
                     } else {
@@ -1217,8 +1258,19 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
             for (uint32_t c0 = first_sc(cur); c0 < ce; c0 += step) {
                 // refill the slot consumed last iteration first (each lane only ever reads back its own cp.async bytes, so
                 // there is no cross-lane hazard), then wait until the oldest of the STAGES outstanding stages has landed
-                issue_next();
-                cp_async_wait<STAGES - 1>();
+                if (TMA) {
+                    // every lane is done with the slot about to be refilled (generic-proxy reads before the async-proxy write)
+                    __syncwarp();
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue_next();
+                    const uint32_t bar = bars_s + (consumed % STAGES) * 8u, parity = (consumed / STAGES) & 1u;
+                    uint32_t spins = 0;
+                    while (!qa_mbar_try_wait(bar, parity))
+                        if (++spins > (1u << 24)) __trap();          // a protocol bug must fail the launch, not hang the GPU
+                } else {
+                    issue_next();
+                    cp_async_wait<STAGES - 1>();
+                }
                 compute(consumed % STAGES, c0);
                 ++consumed;
             }
@@ -1466,6 +1518,7 @@ template <int NPG, int PRO, bool EPI>
 static void launch_qmv_decode_async_f(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
     if (p.bits == 4) {
         switch (p.method) {
+            case QMV_TMA: launch_qmv_decode_async_i<NPG, QMV_TMA, 4, PRO, EPI>(cmd, p, grid, smem); break;
             case UZU_QMETHOD_SCALE_ZERO_POINT: launch_qmv_decode_async_i<NPG, UZU_QMETHOD_SCALE_ZERO_POINT, 4, PRO, EPI>(cmd, p, grid, smem); break;
             case UZU_QMETHOD_SCALE_BIAS: launch_qmv_decode_async_i<NPG, UZU_QMETHOD_SCALE_BIAS, 4, PRO, EPI>(cmd, p, grid, smem); break;
             default: launch_qmv_decode_async_i<NPG, UZU_QMETHOD_SCALE_SYMMETRIC, 4, PRO, EPI>(cmd, p, grid, smem); break;
@@ -1670,6 +1723,13 @@ static bool encode_matmul(uzu_command_buffer* cmd, uzu_context* ctx_for_query, c
                 const size_t fsmem = asmem + (fused && fused->prologue ? (size_t)a.k * 2 + 64 : 0);
                 if (fused) {
                     if (fsmem > 200u * 1024u || (a.k % 8) != 0 || bits != 4) return false;
+                    // decode-stream copy available: one TMA bulk copy per ring stage (zero-point / symmetric weights, unsigned codes)
+                    static const bool tma_off = [] { const char* v = getenv("UZU_QMV_TMA"); return v && atoi(v) == 0; }();
+                    if (fused->decode_stream && !tma_off && p.xor_mask == 0 && p.method != UZU_QMETHOD_SCALE_BIAS && (npg == 64 || npg == 128)) {
+                        p.stream = (const uint8_t*)fused->decode_stream;
+                        p.stream_C = (np + 511u) / 512u;
+                        p.method = uzu::QMV_TMA;
+                    }
                     uint32_t pair_groups = 0;
                     if (fused->epilogue == 1) {
                         // gated-act epilogue: rows [0,F) up, [F,2F) gate; every CTA owns whole pairs, so no global k split
@@ -1822,7 +1882,8 @@ int uzu_fused_linear_supported(uzu_context* ctx, const uzu_fused_linear_args* ar
         if (!m.a) m.a = m.d;
         if (uzu::validate(&m)) return 0;
     }
-    if (args->prologue > 3 || args->prologue == 2 || args->epilogue > 1 || (args->prologue == 0 && args->epilogue == 0)) return 0;
+    // prologue 0 + epilogue 0 = a plain GEMV: only meaningful through this entry point when it brings a decode stream (TMA-fed rings)
+    if (args->prologue > 3 || args->prologue == 2 || args->epilogue > 1 || (args->prologue == 0 && args->epilogue == 0 && !args->decode_stream)) return 0;
     if (args->prologue == 3 && args->epilogue) return 0;
     if (args->prologue == 0 && !args->matmul.a) return 0;
     if (args->prologue == 1 && (!args->norm_input || !args->norm_scales || (args->norm_residual_add && !args->norm_shortcut_in) ||
