@@ -438,7 +438,7 @@ def roofline_of(eng, workload: str, prefill: int, K: int, seconds: float):
         per_tok = lin_s / iters
         achieved = info.weight_bytes_per_token / per_tok / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "qmv_decode_async_kernel (fused dequant + GEMV, all linears + readout of one token replayed back to back)",
+                "kernel": "qmv_decode_async_kernel (fused dequant + GEMV with TMA-bulk-fed rings from the decode-stream layout; all linears + readout of one token replayed back to back)",
                 "algorithmic_bytes_per_launch": int(info.weight_bytes_per_token // max(1, lin_launches // iters)), "peak_source": peak_src}
         extra = {"gemv_launches_per_token": lin_launches // iters, "gemv_ms_per_token": 1000.0 * per_tok}
     extra["whole_step_hbm_frac"] = step_bytes * (K / seconds) / 1e9 / peak

@@ -2597,24 +2597,26 @@ uzu_status uzu_engine_time_linears_select(uzu_engine* e, uint32_t iters, uint32_
             for (auto& L : e->layers) {
                 if (select & 1u) {
                     if (L.is_attention) {
-                        if (L.attn.has_gate) encode_linear(g.c, L.attn.gate, e->hidden_b.ptr(), 1, e->gate.ptr());
-                        encode_linear(g.c, L.attn.qkv, e->hidden_b.ptr(), 1, e->qkv.ptr());
+                        if (L.attn.has_gate) encode_decode_gemv(e, g.c, L.attn.gate, e->hidden_b.ptr(), e->gate.ptr());
+                        encode_decode_gemv(e, g.c, L.attn.qkv, e->hidden_b.ptr(), e->qkv.ptr());
                     } else {
-                        encode_linear(g.c, L.dn.in_proj, e->hidden_b.ptr(), 1, e->in_proj.ptr());
+                        encode_decode_gemv(e, g.c, L.dn.in_proj, e->hidden_b.ptr(), e->in_proj.ptr());
                     }
                 }
                 if (select & 2u) {
-                    if (L.is_attention) encode_linear(g.c, L.attn.out, e->attn_out.ptr(), 1, e->mixer_out.ptr());
-                    else encode_linear(g.c, L.dn.out_proj, e->delta_out.ptr(), 1, e->mixer_out.ptr());
+                    if (L.is_attention) encode_decode_gemv(e, g.c, L.attn.out, e->attn_out.ptr(), e->mixer_out.ptr());
+                    else encode_decode_gemv(e, g.c, L.dn.out_proj, e->delta_out.ptr(), e->mixer_out.ptr());
                 }
-                if (select & 4u) encode_linear(g.c, L.up, e->hidden_b.ptr(), 1, e->fused_up.ptr());
+                if (select & 4u) encode_decode_gemv(e, g.c, L.up, e->hidden_b.ptr(), e->fused_up.ptr());
                 if (select & 32u) {
                     uzu_fused_linear_args f{};
                     f.matmul = linear_args(L.up, e->hidden_b.ptr(), 1, e->gated.ptr());
                     f.epilogue = 1; f.act_type = L.act;
+                    f.decode_stream = g_stream_lookup(e->mega.stream_of, L.up);
+                    f.decode_stream = g_stream_lookup(e->mega.stream_of, L.up);
                     uzu_fused_linear_encode(g.c, &f);
                 }
-                if (select & 8u) encode_linear(g.c, L.down, e->gated.ptr(), 1, e->hidden_a.ptr());
+                if (select & 8u) encode_decode_gemv(e, g.c, L.down, e->gated.ptr(), e->hidden_a.ptr());
                 if ((select & 64u) && L.is_attention) {     // attention mix at the current context (rewrites the same KV row each time)
                     PassCtx pc{};
                     pc.m = 1;
@@ -2635,7 +2637,7 @@ uzu_status uzu_engine_time_linears_select(uzu_engine* e, uint32_t iters, uint32_
                     uzu_delta_net_update_encode(g.c, &ua);
                 }
             }
-            if (select & 16u) encode_linear(g.c, e->out_emb, e->normed_out.ptr(), 1, e->logits.ptr());
+            if (select & 16u) encode_decode_gemv(e, g.c, e->out_emb, e->normed_out.ptr(), e->logits.ptr());
         };
         once();   // warm-up
         cudaStreamSynchronize(s);
