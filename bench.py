@@ -540,7 +540,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # ---- tensor-parallel sub-measurement (N >= 2): the same model sharded over the N ranks ----
     if world > 1 and tp == 1 and not args.no_tp_sub:
         sub = {}
-        for mode in ("nccl", "p2p"):
+        # the one-kernel peer-memory exchange has run on hardware at 2 ranks only: larger groups need UZU_BENCH_TP_P2P=1
+        modes = ("nccl", "p2p") if (world == 2 or os.environ.get("UZU_BENCH_TP_P2P")) else ("nccl",)
+        for mode in modes:
             try:
                 sub[mode] = tp_line(B, dist, args, rank, world, local_rank, full_dir, workload, prefill, max_ctx, mode == "p2p")
             except Exception as ex:
