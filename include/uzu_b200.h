@@ -161,13 +161,15 @@ typedef struct uzu_matmul_args {
     uint64_t d;                    /* [m,n] output_dt */
     uint64_t bias;                 /* MatmulDOps::bias [n] weights_dt, 0 = none */
     uint64_t gather_indices;       /* optional u32 [m,n]: output column c of row r reads B row gather[r*n+c] */
+    uint64_t rht_factors;          /* MatmulDOps::rht_factors, i32 [n] of +-1 (UZU_D_RHT): D is output-RHT-transformed in place after the
+                                    * epilogue and `bias` is added AFTER the transform (cpu/kernel/matmul/kernel.rs:162,285,297-303) */
     uint32_t b_prologue;           /* uzu_gemm_b_prologue_kind */
     uint32_t b_mode;               /* uzu_quantization_mode */
     uint32_t b_group_size;
     uint32_t b_signed_codes;       /* XOR the top code bit (weight_matrix.rs:226-241) */
     uint32_t b_leading_dimension;  /* 0 = default (k if transposed else n) */
     uint32_t b_transpose;          /* quantized B requires 1 (linear/matmul.rs:136) */
-    uint32_t d_transform;          /* UZU_D_* mask; RHT is unsupported */
+    uint32_t d_transform;          /* UZU_D_* mask */
     float ab_scale;
     float soft_cap;
     uint32_t m, n, k;
@@ -335,6 +337,32 @@ typedef struct uzu_kv_cache_update_args {
     uint32_t copy_count, element_dim;
 } uzu_kv_cache_update_args;
 UZU_API void uzu_kv_cache_update_encode(uzu_command_buffer* cmd, const uzu_kv_cache_update_args* args);
+
+/* ActivationTransformKernel (Mirai RHT): backends/cpu/kernel/activation_transform/activation_transform.rs:44-63 (declaration
+ * order), semantics :64-136 and mod.rs:9-44; ops = gpu_types ActivationTransformOp. InputRht: out = H32 (s o x) per 32-wide stripe,
+ * OutputRht: out = s o (H32 x), H32 = Sylvester Walsh-Hadamard / sqrt(32), s = rht_factors (i32 +-1, [element_count]). Quantize ops run
+ * the InputRht transform and emit symmetric int8 codes per activation group (divisor = max|t| / 127), the f32 divisors and -- with
+ * group sums -- the integer code sums per sum group. Callers: RHTLinearWrapper::encode_input (encodable_block/linear/rht_wrapper.rs:
+ * 214-297) and the matmul's output-RHT epilogue. */
+typedef enum uzu_activation_transform_op {
+    UZU_ACTIVATION_TRANSFORM_INPUT_RHT = 0, UZU_ACTIVATION_TRANSFORM_OUTPUT_RHT = 1,
+    UZU_ACTIVATION_TRANSFORM_QUANTIZE = 2, UZU_ACTIVATION_TRANSFORM_QUANTIZE_WITH_GROUP_SUMS = 3
+} uzu_activation_transform_op;
+typedef struct uzu_activation_transform_args {
+    uint64_t input;                /* optional(!in_place): [batch, element_count] T */
+    uint64_t fp_out;               /* optional(InputRht | OutputRht): [batch, element_count] T (the operand itself when in_place) */
+    uint64_t q_out;                /* optional(Quantize*): i8 [batch, element_count] */
+    uint64_t scales_out;           /* optional(Quantize*): f32 [batch, element_count / activation_scale_group_size] */
+    uint64_t group_sums_out;       /* optional(QuantizeWithGroupSums): i32 [batch, element_count / sum_group_size] */
+    uint64_t rht_factors;          /* i32 [element_count] */
+    uint32_t batch_size, element_count;
+    uint32_t ops;                  /* specialize: uzu_activation_transform_op */
+    uint32_t in_place;             /* specialize */
+    uint32_t activation_scale_group_size, sum_group_size;   /* specialize (multiples of 32, <= 256, nested) */
+    uint32_t data_type;            /* T: UZU_DT_BF16 | UZU_DT_F32 */
+} uzu_activation_transform_args;
+UZU_API void uzu_activation_transform_encode(uzu_command_buffer* cmd, const uzu_activation_transform_args* args);
+UZU_API uzu_status uzu_activation_transform_validate(const uzu_activation_transform_args* args);
 
 /* SigmoidGateKernel: backends/cpu/kernel/attention/sigmoid_gate.rs:7-13 */
 UZU_API void uzu_sigmoid_gate_encode(uzu_command_buffer* cmd, uint64_t gate, uint64_t output, uint32_t total_elements);
@@ -511,6 +539,26 @@ UZU_API int uzu_engine_decode_mode(const uzu_engine* e);
 UZU_API const char* uzu_engine_decode_mode_reason(const uzu_engine* e);
 UZU_API uzu_status uzu_engine_set_decode_mode(uzu_engine* e, int persistent);
 UZU_API uzu_status uzu_engine_last_logits(uzu_engine* e, uint16_t* out_logits);
+
+/* Speculative (trie) decode, the verify half. Replaces what LanguageModelStream::generate does between "propose a trie" and
+ * "accept a path" (engine/language_model/stream/stream.rs:550-657 and :436-520): the host (trie.rs, unchanged) linearizes the proposal into
+ * `count` <= 16 nodes -- token ids, gpu_types::trie::TrieNode {trie_start, trie_end, height} from FlatTrie::token_subtrie_ranges
+ * (trie.rs:211-222) and per-node seeds (token_seeds, :224-226; NULL = PRng::derive(context + height)) -- and
+ *  trie_pass:   runs Decoder::encode over the nodes from the current state (BatchTopology::new(nodes, full_accept = false)): RoPE position =
+ *               context + height (transformer.rs:248), K/V of node i appended at row context + i, attention masked by subtrie range
+ *               (mask.rs:21-29), logits and one sampled token for EVERY node (stream.rs:640). out_tokens[count] (HOST) receives the sampled
+ *               ids, out_logits (HOST, optional) the bf16 logits [count, vocab]. Nothing is accepted: the context length does not move and
+ *               every other engine call fails until trie_accept.
+ *  trie_accept: TransformerState::encode_accept(accepted_indices) (transformer.rs:56-75 -> mixer/attention/state.rs:174-237): indices
+ *               strictly increasing (FlatTrie::accept, trie.rs:262-296, yields them that way); KV row context + accepted[i] moves to
+ *               context + i through KVCacheUpdateKernel, context grows by `count`; `next_token` (the last verified node's sampled token)
+ *               becomes the device-chained input of the next pass (ForwardPassChaining::Constant).
+ *  speculation_supported: Mixer::speculation_supported (mixer/mod.rs, delta_net.rs:442-444): 0 for hybrid (DeltaNet) models -- the tree-
+ *               verify core of the DeltaNet mixer is not built -- 1 for attention-only models. */
+UZU_API int uzu_engine_speculation_supported(const uzu_engine* e);
+UZU_API uzu_status uzu_engine_trie_pass(uzu_engine* e, const uint32_t* tokens, const uzu_trie_node* nodes, const uint64_t* seeds, uint32_t count,
+                                        const uzu_sampling_method* sampling, uint32_t* out_tokens, uint16_t* out_logits);
+UZU_API uzu_status uzu_engine_trie_accept(uzu_engine* e, const uint32_t* accepted_indices, uint32_t count, uint32_t next_token);
 /* measurement helper: run ONE persistent decode step and return, for CTA `cta`, eight SM-clock stamps per phase ([0] phase start, [1] activation
  * row staged / attention prepared, [2..5] phase-specific, [6] phase body done, [7] grid barrier passed; 0 = not stamped) and the phase kinds (1 GEMV, 2 prepare, 3 attention, 4 act, 5/6 DeltaNet, 7 logits, 8 finish) */
 UZU_API uzu_status uzu_engine_debug_decode_trace(uzu_engine* e, uint32_t cta, uint32_t capacity, uint32_t* out_kinds, uint64_t* out_cycles, uint32_t* out_nops);

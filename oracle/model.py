@@ -44,6 +44,17 @@ class _Linear:
     def __init__(self, tensors, meta, prefix, out_dim, in_dim, threads):
         spec = json.loads(meta[prefix + ".spec"])
         self.out_dim, self.in_dim, self.threads = out_dim, in_dim, threads
+        self.rht = None
+        if spec["type"] == "HybridSpec":
+            # RHTLinearWrapper (encodable_block/linear/{mod.rs:128-143, rht_wrapper.rs:58-176}): 32-wide input/output randomized Hadamard
+            # around an inner quantized LinearMatmul stored under `quantized`, signs under `incoherence_signs`
+            assert spec["adapter_spec"] is None and spec["incoherence_block_size"] == O.HADAMARD_TRANSFORM_BLOCK_SIZE \
+                and spec["incoherence_processing_mode"] == "input_output", f"unsupported HybridSpec {spec}"
+            self.rht = (tensors[prefix + ".incoherence_signs.input_signs"], tensors[prefix + ".incoherence_signs.output_signs"])
+            assert self.rht[0].shape == (in_dim,) and self.rht[1].shape == (out_dim,) and self.rht[0].dtype == np.int32
+            prefix = prefix + ".quantized"
+            spec = json.loads(meta[prefix + ".spec"])
+            assert spec["type"] in ("IntSpec", "MLXSpec"), "fused output-hadamard factors require quantized weights (linear/matmul.rs:88-91)"
         self.w = tensors[prefix + ".weights"]
         self.kw = {}
         t = spec["type"]
@@ -61,6 +72,11 @@ class _Linear:
 
     def __call__(self, x, d_f32=False):
         m = x.shape[0]
+        if self.rht is not None:
+            # encode_input (rht_wrapper.rs:286-296): InputRht over the activation, inner matmul with the output factors as its epilogue
+            assert not d_f32
+            x = O.activation_transform(x, self.rht[0], op=O.RHT_INPUT)
+            return O.matmul(x, self.w, m=m, n=self.out_dim, k=self.in_dim, threads=self.threads, rht_factors=self.rht[1], **self.kw)
         return O.matmul(x, self.w, m=m, n=self.out_dim, k=self.in_dim, d_f32=d_f32, threads=self.threads, **self.kw)
 
     def lookup(self, token_ids, vocab, input_scale):
@@ -132,6 +148,7 @@ class OracleModel:
     # ---- state (LanguageModelState / TransformerState) ----
     def reset(self):
         self.context_length = 0
+        self._pending = None
         self.state = []
         for L in self.layers:
             mc = L["mixer"]
@@ -151,7 +168,7 @@ class OracleModel:
                                epsilon=ncfg["epsilon"], scale_offset=ncfg["scale_offset"] or 0.0,
                                full_layer=ncfg["upcast_mode"] == "full_layer", subtract_mean=ncfg["subtract_mean"])
 
-    def _attention(self, L, st, hidden, positions):
+    def _attention(self, L, st, hidden, positions, trie=None):
         mc = L["mixer"]
         m = hidden.shape[0]
         D, Hq, Hkv = mc["head_dim"], mc["num_heads"], mc["num_groups"]
@@ -179,6 +196,8 @@ class OracleModel:
         kw = dict(head_dim=D, gqa_factor=Hq // Hkv, sequence_length=prefix + m, k_head_stride=D, k_seq_stride=Hkv * D,
                   v_head_stride=D, v_seq_stride=Hkv * D, scale=scale, num_heads=Hq, suffix_length=m,
                   is_causal=mc["is_causal"])
+        if trie is not None:   # run_core picks trie_core + uploads the nodes when the topology is not flat (mode.rs:178-184)
+            kw["trie"] = trie
         if prefix + m > 1024:  # core/mod.rs:88-92
             out = O.attention_two_pass(queries, st["k"], st["v"], **kw)
         else:
@@ -186,7 +205,8 @@ class OracleModel:
         out = out.reshape(m, Hq * D)
         if gate is not None:
             O.sigmoid_gate(gate, out)
-        st["len"] = prefix + m  # encode_accept(0..m): flat path, no copies (state.rs:174-237)
+        if trie is None:
+            st["len"] = prefix + m  # encode_accept(0..m): flat path, no copies (state.rs:174-237)
         return self._row_parallel(L["out"], out)
 
     def _row_parallel(self, linear, x):
@@ -211,23 +231,35 @@ class OracleModel:
                                  norm_epsilon=mc["norm_config"]["epsilon"])
         return L["out_proj"](out.reshape(1, vd))
 
-    def forward(self, token_ids, output_rows=None, return_hidden=False):
-        """One Decoder::encode over `token_ids` (m rows, flat topology). Returns bf16 logits (bits)
-        for `output_rows` (default: last row only, like the stream does)."""
+    def forward(self, token_ids, output_rows=None, return_hidden=False, trie=None):
+        """One Decoder::encode over `token_ids` (m rows). Returns bf16 logits (bits) for `output_rows` (default: last row only,
+        like the stream does). `trie` = u32 [m, 3] rows of (trie_start, trie_end, height) from FlatTrie::token_subtrie_ranges
+        (trie.rs:211-222) for a speculation pass: positions are context + height (transformer.rs:248), attention masks suffix keys
+        by subtrie range (mask.rs:21-29), and NOTHING is accepted -- call accept() with the indices the stream kept."""
         token_ids = np.ascontiguousarray(token_ids, dtype=np.uint32)
         m = len(token_ids)
+        if trie is not None:
+            trie = np.ascontiguousarray(trie, dtype=np.uint32).reshape(m, 3)
+            assert self._pending is None, "a speculation pass is already pending: accept() first"
+            assert all(L["mixer"]["type"] == "AttentionConfig" for L in self.layers), \
+                "DeltaNet tree verification is not restated (Mixer::speculation_supported is false without it, delta_net.rs:442-444)"
+            if output_rows is None:
+                output_rows = (0, m)          # stream.rs:640: Some(0..batch_dim.size())
         if output_rows is None:
             output_rows = (m - 1, m)
         input_scale = self.emb_cfg["input_scale"] if self.emb_cfg["input_scale"] is not None else 1.0
         hidden = self.in_emb.lookup(token_ids, self.V, input_scale)
         shortcut = np.zeros_like(hidden)
-        positions = np.arange(self.context_length, self.context_length + m, dtype=np.uint32)
+        if trie is not None:
+            positions = (self.context_length + trie[:, 2]).astype(np.uint32)
+        else:
+            positions = np.arange(self.context_length, self.context_length + m, dtype=np.uint32)
         for i, L in enumerate(self.layers):
             lc = L["cfg"]
             hidden = self._norm(hidden, L["prefix"] + "pre_mixer_norm", lc["pre_mixer_norm_config"], shortcut=shortcut,
                                 residual_add=i > 0)
             if L["mixer"]["type"] == "AttentionConfig":
-                hidden = self._attention(L, self.state[i], hidden, positions)
+                hidden = self._attention(L, self.state[i], hidden, positions, trie)
             else:
                 hidden = self._delta_net(L, self.state[i], hidden)
             hidden = self._norm(hidden, L["prefix"] + "pre_mlp_norm", lc["pre_mlp_norm_config"], shortcut=shortcut,
@@ -247,10 +279,27 @@ class OracleModel:
             logits = self.tp_gather(logits)          # [rows, V/P] per rank -> [rows, V]
         if self.emb_cfg["logit_scale"] is not None or self.emb_cfg["logit_soft_cap"] is not None:
             O.logit_transform(logits, self.emb_cfg["logit_scale"] or 1.0, self.emb_cfg["logit_soft_cap"])
-        self.context_length += m
+        if trie is None:
+            self.context_length += m
+        else:
+            self._pending = m
         if return_hidden:
             return logits, normed
         return logits
+
+    def accept(self, accepted_indices):
+        """TransformerState::encode_accept after a speculation pass (transformer.rs:56-75 -> mixer/attention/state.rs:174-237, Full
+        state): row `length + accepted[i]` of every layer's K/V moves to row `length + i`; the context grows by len(accepted)."""
+        idx = [int(i) for i in accepted_indices]
+        assert self._pending is not None, "no speculation pass to accept"
+        assert idx and all(a < b for a, b in zip(idx, idx[1:])) and idx[-1] < self._pending, "invalid accepted indices"
+        for L, st in zip(self.layers, self.state):
+            copies = [(st["len"] + a, st["len"] + i) for i, a in enumerate(idx) if a != i]
+            if copies:
+                O.kv_cache_update(st["k"], st["v"], copies, L["mixer"]["num_groups"] * L["mixer"]["head_dim"])
+            st["len"] += len(idx)
+        self.context_length += len(idx)
+        self._pending = None
 
     def prefill(self, prompt):
         """Chunks of <= 1024 (stream.rs:194-195); hybrid (DeltaNet) models step token by token

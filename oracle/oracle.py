@@ -96,8 +96,19 @@ class _MatmulArgs(C.Structure):
 
 def matmul(a, w, *, m, n, k, scales=None, zero_points=None, biases=None, method=QM_NONE, bits=4, group_size=64,
            signed_codes=False, b_transpose=True, ld=0, d=None, d_f32=False, gather=None, ab_scale=1.0,
-           accumulate=False, bias=None, soft_cap=None, w_f32=False, a_f32=False, threads=1):
-    """D = epilogue(A @ dequant(W)^T); returns D ([m,n] uint16 bf16 bits, or float32 if d_f32)."""
+           accumulate=False, bias=None, soft_cap=None, w_f32=False, a_f32=False, threads=1, rht_factors=None):
+    """D = epilogue(A @ dequant(W)^T); returns D ([m,n] uint16 bf16 bits, or float32 if d_f32).
+    rht_factors (MatmulDOps::rht_factors, i32 [n]): the matmul runs WITHOUT its bias, then OutputRht in place over D, then the bias
+    (cpu/kernel/matmul/kernel.rs:64,162,285,297-303: bias_after_rht)."""
+    if rht_factors is not None:
+        assert not d_f32 and gather is None
+        out = matmul(a, w, m=m, n=n, k=k, scales=scales, zero_points=zero_points, biases=biases, method=method, bits=bits,
+                     group_size=group_size, signed_codes=signed_codes, b_transpose=b_transpose, ld=ld, d=d, ab_scale=ab_scale,
+                     accumulate=accumulate, bias=None, soft_cap=soft_cap, w_f32=w_f32, a_f32=a_f32, threads=threads)
+        activation_transform(out, rht_factors, op=RHT_OUTPUT, in_place=True)
+        if bias is not None:
+            out[...] = tensor_add_bias(out, bias, n)
+        return out
     if d is None:
         d = np.zeros((m, n), dtype=np.float32 if d_f32 else np.uint16)
     args = _MatmulArgs(
@@ -290,6 +301,33 @@ def tensor_add_bias(inp, bias, num_cols):
     out = np.zeros_like(inp)
     lib().oracle_tensor_add_bias(_p(inp), _p(bias), _p(out), C.c_int(num_cols), C.c_int(inp.size))
     return out
+
+
+RHT_INPUT, RHT_OUTPUT, RHT_QUANTIZE, RHT_QUANTIZE_WITH_GROUP_SUMS = 0, 1, 2, 3   # gpu_types ActivationTransformOp
+HADAMARD_TRANSFORM_BLOCK_SIZE = 32
+
+
+def activation_transform(x, factors, *, op=RHT_INPUT, in_place=False, activation_group_size=0, sum_group_size=0):
+    """ActivationTransformKernel (cpu/kernel/activation_transform/activation_transform.rs:44-136). x: [rows, cols] bf16 bits (uint16) or
+    float32. InputRht / OutputRht return the transformed array (x itself when in_place); the quantize ops return (codes i8, scales f32
+    [rows, cols/activation_group_size], group sums i32 [rows, cols/sum_group_size] or None)."""
+    x = np.ascontiguousarray(x) if not in_place else x
+    rows, cols = x.shape
+    assert cols % HADAMARD_TRANSFORM_BLOCK_SIZE == 0
+    factors = np.ascontiguousarray(factors, dtype=np.int32)
+    assert factors.shape == (cols,)
+    is_f32 = int(x.dtype == np.float32)
+    if op in (RHT_INPUT, RHT_OUTPUT):
+        out = x if in_place else np.zeros_like(x)
+        lib().oracle_activation_transform(_p(x), C.c_int(is_f32), _p(out), None, None, None, _p(factors), C.c_int(rows), C.c_int(cols),
+                                          C.c_int(op), C.c_int(0), C.c_int(0))
+        return out
+    q = np.zeros((rows, cols), dtype=np.int8)
+    sc = np.zeros((rows, cols // activation_group_size), dtype=np.float32)
+    gs = np.zeros((rows, cols // sum_group_size), dtype=np.int32) if op == RHT_QUANTIZE_WITH_GROUP_SUMS else None
+    lib().oracle_activation_transform(_p(x), C.c_int(is_f32), None, _p(q), _p(sc), _p(gs) if gs is not None else None, _p(factors),
+                                      C.c_int(rows), C.c_int(cols), C.c_int(op), C.c_int(activation_group_size), C.c_int(sum_group_size))
+    return q, sc, gs
 
 
 def tensor_add_swap(skip, main):

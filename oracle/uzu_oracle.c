@@ -694,6 +694,76 @@ ORACLE_API void oracle_tensor_add_swap(bf16_t* skip, bf16_t* main_, int length) 
 }
 
 /* ------------------------------------------------------------------------------------------
+ * ActivationTransform (Mirai RHT): backends/cpu/kernel/activation_transform/
+ * {activation_transform.rs:44-136, mod.rs:31-44}. 32-point Walsh-Hadamard per stripe in f32
+ * (butterflies stride 1,2,4,8,16: lower = a+b, upper = a-b; then * 1/sqrt(32)); InputRht multiplies
+ * by the +-1 factors before the transform, OutputRht after. Quantize ops: symmetric int8 per
+ * activation group on the InputRht-transformed row (mod.rs:9-29, activation_transform.rs:11-42).
+ * op: 0 InputRht, 1 OutputRht, 2 Quantize, 3 QuantizeWithGroupSums (gpu_types ActivationTransformOp).
+ * `input` may alias `fp_out` (in_place): the row is transformed into a scratch row first, like the
+ * reference's `transformed` vector.
+ * ---------------------------------------------------------------------------------------- */
+static void hadamard32(float* v) {
+    for (int stride = 1; stride < 32; stride <<= 1)
+        for (int lane = 0; lane < 32; ++lane)
+            if ((lane & stride) == 0) {
+                float a = v[lane], b = v[lane | stride];
+                v[lane] = a + b;
+                v[lane | stride] = a - b;
+            }
+    const float scale = 1.0f / sqrtf(32.0f);
+    for (int i = 0; i < 32; ++i) v[i] *= scale;
+}
+
+static float min_max_symmetric_divisor(const float* v, int n) {
+    float mn = INFINITY, mx = -INFINITY;
+    for (int i = 0; i < n; ++i) { mn = fminf(mn, v[i]); mx = fmaxf(mx, v[i]); }
+    float mag = fmaxf(fabsf(mn), fabsf(mx));
+    return (isfinite(mag) && mag > 0.0f) ? mag / 127.0f : 1.0f;
+}
+
+ORACLE_API void oracle_activation_transform(const void* input, int is_f32, void* fp_out, int8_t* q_out, float* scales_out,
+                                            int32_t* group_sums_out, const int32_t* factors, int rows, int cols, int op,
+                                            int activation_group_size, int sum_group_size) {
+    const int input_rht = op != 1;
+    float* t = (float*)malloc((size_t)cols * sizeof(float));
+    for (int r = 0; r < rows; ++r) {
+        const size_t off = (size_t)r * cols;
+        for (int s0 = 0; s0 < cols; s0 += 32) {
+            float stripe[32];
+            for (int l = 0; l < 32; ++l) {
+                float v = is_f32 ? ((const float*)input)[off + s0 + l] : bf2f(((const bf16_t*)input)[off + s0 + l]);
+                stripe[l] = input_rht ? v * (float)factors[s0 + l] : v;
+            }
+            hadamard32(stripe);
+            for (int l = 0; l < 32; ++l) t[s0 + l] = input_rht ? stripe[l] : stripe[l] * (float)factors[s0 + l];
+        }
+        if (op >= 2) {
+            const int groups = cols / activation_group_size;
+            if (op == 3) for (int g = 0; g < cols / sum_group_size; ++g) group_sums_out[(size_t)r * (cols / sum_group_size) + g] = 0;
+            for (int g = 0; g < groups; ++g) {
+                const float* src = t + (size_t)g * activation_group_size;
+                const float scale = min_max_symmetric_divisor(src, activation_group_size);
+                scales_out[(size_t)r * groups + g] = scale;
+                for (int i = 0; i < activation_group_size; ++i) {
+                    float q = roundf(src[i] / scale);           /* f32::round: half away from zero */
+                    q = fminf(fmaxf(q, -127.0f), 127.0f);
+                    const int idx = g * activation_group_size + i;
+                    q_out[off + idx] = (int8_t)q;
+                    if (op == 3) group_sums_out[(size_t)r * (cols / sum_group_size) + idx / sum_group_size] += (int)q;
+                }
+            }
+        } else {
+            for (int i = 0; i < cols; ++i) {
+                if (is_f32) ((float*)fp_out)[off + i] = t[i];
+                else ((bf16_t*)fp_out)[off + i] = f2bf(t[i]);
+            }
+        }
+    }
+    free(t);
+}
+
+/* ------------------------------------------------------------------------------------------
  * Sampling RNG: encodable_block/sampling/gumbel.rs:1-81 (Philox4x32-10, key = 64-bit seed,
  * counter = [offset,0,0,0]); prng.rs:12-23.
  * ---------------------------------------------------------------------------------------- */

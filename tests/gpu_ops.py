@@ -19,12 +19,14 @@ def _ptr(b):
 
 def matmul(ctx, a, w, *, m, n, k, scales=None, zero_points=None, biases=None, method=0, bits=4, group_size=64,
            signed_codes=False, b_transpose=True, ld=0, d=None, d_f32=False, gather=None, ab_scale=1.0, accumulate=False,
-           bias=None, soft_cap=None, a_f32=False, w_f32=False, return_launches=False):
+           bias=None, soft_cap=None, a_f32=False, w_f32=False, return_launches=False, rht_factors=None):
     if d is None:
         d = np.zeros((m, n), np.float32 if d_f32 else np.uint16)
-    bufs = [_up(ctx, x) for x in (a, w, scales, zero_points, biases, d, bias, gather)]
-    ba, bw, bs, bz, bb, bd, bbias, bg = bufs
-    mask = 0
+    if rht_factors is not None:
+        rht_factors = np.ascontiguousarray(rht_factors, dtype=np.int32)
+    bufs = [_up(ctx, x) for x in (a, w, scales, zero_points, biases, d, bias, gather, rht_factors)]
+    ba, bw, bs, bz, bb, bd, bbias, bg, brht = bufs
+    mask = B.D_RHT if rht_factors is not None else 0
     if ab_scale != 1.0:
         mask |= B.D_SCALE
     if accumulate:
@@ -34,7 +36,7 @@ def matmul(ctx, a, w, *, m, n, k, scales=None, zero_points=None, biases=None, me
     if soft_cap is not None:
         mask |= B.D_SOFT_CAP
     args = B.MatmulArgs(a=_ptr(ba), b=_ptr(bw), b_scales=_ptr(bs), b_zero_points=_ptr(bz), b_biases=_ptr(bb), d=_ptr(bd),
-                        bias=_ptr(bbias), gather_indices=_ptr(bg), b_prologue=PROLOGUE[method],
+                        bias=_ptr(bbias), gather_indices=_ptr(bg), rht_factors=_ptr(brht), b_prologue=PROLOGUE[method],
                         b_mode=B.QMODE_U4 if bits == 4 else B.QMODE_U8, b_group_size=group_size,
                         b_signed_codes=int(signed_codes), b_leading_dimension=ld, b_transpose=int(b_transpose),
                         d_transform=mask, ab_scale=ab_scale, soft_cap=soft_cap or 0.0, m=m, n=n, k=k,
@@ -49,6 +51,31 @@ def matmul(ctx, a, w, *, m, n, k, scales=None, zero_points=None, biases=None, me
     if return_launches:
         return out, cmd.launches
     return out
+
+
+def activation_transform(ctx, x, factors, *, op=0, in_place=False, activation_group_size=0, sum_group_size=0):
+    """uzu_activation_transform_encode; same returns as oracle.activation_transform."""
+    rows, cols = x.shape
+    factors = np.ascontiguousarray(factors, dtype=np.int32)
+    bx, bf = ctx.upload(np.ascontiguousarray(x)), ctx.upload(factors)
+    dt = B.DT_F32 if x.dtype == np.float32 else B.DT_BF16
+    if op in (0, 1):
+        bo = bx if in_place else ctx.upload(np.zeros_like(x))
+        args = B.ActivationTransformArgs(input=0 if in_place else bx.ptr, fp_out=bo.ptr, rht_factors=bf.ptr, batch_size=rows,
+                                         element_count=cols, ops=op, in_place=int(in_place), data_type=dt)
+        with ctx.command_buffer("rht") as cmd:
+            cmd.encode("uzu_activation_transform_encode", C.byref(args))
+        return bo.numpy(x.dtype, x.shape)
+    bq = ctx.upload(np.zeros((rows, cols), np.int8))
+    bs = ctx.upload(np.zeros((rows, cols // activation_group_size), np.float32))
+    bg = ctx.upload(np.zeros((rows, cols // sum_group_size), np.int32)) if op == 3 else None
+    args = B.ActivationTransformArgs(input=bx.ptr, q_out=bq.ptr, scales_out=bs.ptr, group_sums_out=_ptr(bg), rht_factors=bf.ptr,
+                                     batch_size=rows, element_count=cols, ops=op, in_place=0,
+                                     activation_scale_group_size=activation_group_size, sum_group_size=sum_group_size, data_type=dt)
+    with ctx.command_buffer("rht-quantize") as cmd:
+        cmd.encode("uzu_activation_transform_encode", C.byref(args))
+    return (bq.numpy(np.int8, (rows, cols)), bs.numpy(np.float32, (rows, cols // activation_group_size)),
+            bg.numpy(np.int32, (rows, cols // sum_group_size)) if bg is not None else None)
 
 
 def normalization(ctx, inp, scales, *, shortcut=None, residual_add=False, epsilon=1e-5, scale_offset=0.0, full_layer=False,

@@ -447,3 +447,96 @@ def test_sigmoid_gate_and_kv_cache_update_closed_forms():
         ek[d_] = ek[s_]; ev[d_] = ev[s_]
     O.kv_cache_update(keys, values, copies, E)
     assert (keys == ek).all() and (values == ev).all()
+
+
+# ---- Mirai RHT: ActivationTransform + the matmul's output-RHT epilogue ------------------------------------------
+
+def _rht_case(batch, channels):
+    # the reference's own test inputs (tests/unit/backends/common/kernel/activation_transform_test.rs:64-76)
+    data = (np.sin(np.arange(batch * channels, dtype=np.float64) * 0.1) * 2.0).reshape(batch, channels)
+    factors = np.where(np.arange(channels) % 3 == 0, -1, 1).astype(np.int32)
+    return data, factors
+
+
+def _hadamard_f64(n=32):
+    h = np.array([[1.0]])
+    while h.shape[0] < n:
+        h = np.block([[h, h], [h, -h]])
+    return h / np.sqrt(n)
+
+
+@pytest.mark.parametrize("batch,channels", [(1, 32), (1, 64), (1, 128), (4, 32), (4, 256), (2, 2048)])
+def test_activation_transform_against_float64_hadamard(batch, channels):
+    """activation_transform.rs:73-99 + mod.rs:31-44: the butterfly network IS the Sylvester-ordered Walsh-Hadamard matrix / sqrt(32)
+    applied per 32-wide stripe; InputRht = H (s o x), OutputRht = s o (H x). Shapes and inputs of the reference's test."""
+    data, factors = _rht_case(batch, channels)
+    H = _hadamard_f64()
+    blocks = data.reshape(batch, channels // 32, 32)
+    fb = factors.reshape(channels // 32, 32).astype(np.float64)
+    want_in = np.einsum("ij,bsj->bsi", H, blocks * fb).reshape(batch, channels)
+    want_out = (np.einsum("ij,bsj->bsi", H, blocks) * fb).reshape(batch, channels)
+    x32 = data.astype(np.float32)
+    for op, want in ((O.RHT_INPUT, want_in), (O.RHT_OUTPUT, want_out)):
+        got = O.activation_transform(x32, factors, op=op)
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)             # reference tolerance for f32: 1e-4
+        inplace = x32.copy()
+        assert O.activation_transform(inplace, factors, op=op, in_place=True) is inplace and (inplace == got).all()
+        xb = f32_to_bf16(x32)
+        gb = O.activation_transform(xb, factors, op=op)
+        # bf16: exact f32 transform of the bf16 inputs, rounded once
+        blocks_b = bf16_to_f32(xb).astype(np.float64).reshape(batch, channels // 32, 32)
+        wb = (np.einsum("ij,bsj->bsi", H, blocks_b * fb) if op == O.RHT_INPUT else np.einsum("ij,bsj->bsi", H, blocks_b) * fb).reshape(batch, channels)
+        np.testing.assert_allclose(bf16_to_f32(gb), wb, rtol=2 ** -8, atol=1e-6)
+    # H is orthogonal and symmetric: OutputRht undoes InputRht
+    back = O.activation_transform(O.activation_transform(x32, factors, op=O.RHT_INPUT), factors, op=O.RHT_OUTPUT)
+    np.testing.assert_allclose(back, x32, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("group,sum_group", [(32, None), (64, 32), (128, 128)])
+def test_activation_quantize_closed_form(group, sum_group):
+    """activation_transform.rs:11-42, mod.rs:9-29: per activation group, divisor = max|t| / 127 (1 if the group is all zero), code =
+    round-half-away(t / divisor) clamped to +-127, group sums = integer sums of the codes."""
+    rng = np.random.default_rng(0x5EED)
+    rows, cols = 3, 256
+    x = rng.uniform(-1, 1, (rows, cols)).astype(np.float32)
+    x[1, 64:128] = 0.0
+    factors = np.where(np.arange(cols) % 3 == 0, -1, 1).astype(np.int32)
+    t = O.activation_transform(x, factors, op=O.RHT_INPUT)
+    op = O.RHT_QUANTIZE if sum_group is None else O.RHT_QUANTIZE_WITH_GROUP_SUMS
+    q, sc, gs = O.activation_transform(x, factors, op=op, activation_group_size=group, sum_group_size=sum_group or 0)
+    tg = t.reshape(rows, cols // group, group)
+    mag = np.abs(tg).max(axis=2)
+    want_sc = np.where(mag > 0, mag / np.float32(127.0), np.float32(1.0)).astype(np.float32)
+    assert (sc == want_sc).all()
+    r = tg / want_sc[:, :, None]
+    want_q = np.clip(np.sign(r) * np.floor(np.abs(r) + np.float32(0.5)), -127, 127).astype(np.int8).reshape(rows, cols)
+    assert (q == want_q).all()
+    assert np.abs(q.reshape(rows, cols // group, group)).max(axis=2)[mag > 0].min() == 127
+    if sum_group is not None:
+        assert (gs == q.astype(np.int32).reshape(rows, cols // sum_group, sum_group).sum(axis=2)).all()
+    else:
+        assert gs is None
+
+
+def test_matmul_output_rht_runs_bias_after_the_transform():
+    """cpu/kernel/matmul/kernel.rs:64,162,285,297-303: with rht_factors the in-loop bias is skipped, D is output-transformed in place
+    (rounded to bf16 first, as stored), and the bias is added afterwards by TensorAddBias."""
+    rng = np.random.default_rng(31)
+    m, n, k = 3, 64, 128
+    w = rng.integers(0, 256, (n, k // 2), dtype=np.uint8)
+    scales = f32_to_bf16(rng.uniform(0.01, 0.3, (n, k // 64)).astype(np.float32))
+    zp = rng.integers(0, 256, (n, 1), dtype=np.uint8)
+    x = f32_to_bf16(rng.uniform(-0.3, 0.3, (m, k)).astype(np.float32))
+    bias = f32_to_bf16(rng.uniform(-0.03, 0.03, n).astype(np.float32))
+    factors = rng.choice(np.array([-1, 1], np.int32), n)
+    kw = dict(m=m, n=n, k=k, scales=scales, zero_points=zp, method=O.QM_ZERO_POINT, bits=4, group_size=64)
+    plain = O.matmul(x, w, **kw)
+    got = O.matmul(x, w, bias=bias, rht_factors=factors, **kw)
+    H = _hadamard_f64()
+    t = (np.einsum("ij,bsj->bsi", H, bf16_to_f32(plain).astype(np.float64).reshape(m, n // 32, 32)) * factors.reshape(n // 32, 32)).reshape(m, n)
+    t = bf16_to_f32(f32_to_bf16(t.astype(np.float32)))
+    want = t.astype(np.float64) + bf16_to_f32(bias)
+    np.testing.assert_allclose(bf16_to_f32(got), want, rtol=2 ** -7, atol=2e-3)
+    # and it is NOT the bias-before-transform order
+    wrong = O.activation_transform(O.matmul(x, w, bias=bias, **kw), factors, op=O.RHT_OUTPUT)
+    assert (wrong != got).any()

@@ -41,9 +41,14 @@ KvCopy = _struct("uzu_kv_copy", [("source", u32), ("destination", u32)])
 
 MatmulArgs = _struct("uzu_matmul_args", [
     ("a", u64), ("b", u64), ("b_scales", u64), ("b_zero_points", u64), ("b_biases", u64), ("d", u64), ("bias", u64),
-    ("gather_indices", u64), ("b_prologue", u32), ("b_mode", u32), ("b_group_size", u32), ("b_signed_codes", u32),
+    ("gather_indices", u64), ("rht_factors", u64), ("b_prologue", u32), ("b_mode", u32), ("b_group_size", u32), ("b_signed_codes", u32),
     ("b_leading_dimension", u32), ("b_transpose", u32), ("d_transform", u32), ("ab_scale", f32), ("soft_cap", f32),
     ("m", u32), ("n", u32), ("k", u32), ("weights_dt", u32), ("input_dt", u32), ("output_dt", u32)])
+
+ActivationTransformArgs = _struct("uzu_activation_transform_args", [
+    ("input", u64), ("fp_out", u64), ("q_out", u64), ("scales_out", u64), ("group_sums_out", u64), ("rht_factors", u64),
+    ("batch_size", u32), ("element_count", u32), ("ops", u32), ("in_place", u32), ("activation_scale_group_size", u32),
+    ("sum_group_size", u32), ("data_type", u32)])
 
 NormalizationArgs = _struct("uzu_normalization_args", [
     ("input", u64), ("scales", u64), ("biases", u64), ("output", u64), ("shortcut", u64), ("hadamard_factors", u64),
@@ -150,7 +155,9 @@ uzu_engine_forward uzu_engine_batch_begin uzu_engine_batch_prefill uzu_engine_ba
 uzu_engine_batch_logits uzu_engine_batch_context_length uzu_engine_launch_count uzu_engine_decode_timed uzu_engine_step_host
 uzu_delta_net_fused_update_supported uzu_delta_net_fused_update_encode uzu_engine_time_linears uzu_engine_time_prefill_linears uzu_engine_time_linears_select uzu_debug_set_qmv_tuning uzu_debug_set_delta_prefill uzu_debug_set_prefill_attention uzu_debug_set_umma uzu_tp_get_unique_id uzu_context_tp_init uzu_context_tp_destroy uzu_context_tp_size
 uzu_context_tp_rank uzu_tp_p2p_export uzu_tp_p2p_import uzu_tp_all_reduce_encode uzu_tp_all_gather_encode uzu_fused_linear_supported uzu_fused_linear_encode
-uzu_engine_decode_mode uzu_engine_decode_mode_reason uzu_engine_set_decode_mode uzu_engine_last_logits uzu_engine_debug_decode_trace""".split()
+uzu_engine_decode_mode uzu_engine_decode_mode_reason uzu_engine_set_decode_mode uzu_engine_last_logits uzu_engine_debug_decode_trace
+uzu_engine_speculation_supported uzu_engine_trie_pass uzu_engine_trie_accept uzu_activation_transform_encode
+uzu_activation_transform_validate""".split()
 
 _lib = None
 
@@ -211,6 +218,8 @@ def load() -> C.CDLL:
         "uzu_command_buffer_launch_count": (u64, [vp]),
         "uzu_matmul_encode": (None, [vp, C.POINTER(MatmulArgs)]),
         "uzu_matmul_validate": (C.c_int, [C.POINTER(MatmulArgs)]),
+        "uzu_activation_transform_encode": (None, [vp, C.POINTER(ActivationTransformArgs)]),
+        "uzu_activation_transform_validate": (C.c_int, [C.POINTER(ActivationTransformArgs)]),
         "uzu_normalization_encode": (None, [vp, C.POINTER(NormalizationArgs)]),
         "uzu_qkv_norm_encode": (None, [vp, C.POINTER(QkvNormArgs)]),
         "uzu_attention_prepare_encode": (None, [vp, C.POINTER(AttentionPrepareArgs)]),
@@ -258,6 +267,9 @@ def load() -> C.CDLL:
         "uzu_engine_decode_mode_reason": (C.c_char_p, [vp]),
         "uzu_engine_set_decode_mode": (C.c_int, [vp, C.c_int]),
         "uzu_engine_last_logits": (C.c_int, [vp, C.POINTER(C.c_uint16)]),
+        "uzu_engine_speculation_supported": (C.c_int, [vp]),
+        "uzu_engine_trie_pass": (C.c_int, [vp, C.POINTER(u32), vp, C.POINTER(u64), u32, C.POINTER(SamplingMethod), C.POINTER(u32), C.POINTER(C.c_uint16)]),
+        "uzu_engine_trie_accept": (C.c_int, [vp, C.POINTER(u32), u32, u32]),
         "uzu_engine_debug_decode_trace": (C.c_int, [vp, u32, u32, C.POINTER(u32), C.POINTER(u64), C.POINTER(u32)]),
         "uzu_engine_time_linears": (C.c_int, [vp, u32, C.POINTER(C.c_double), C.POINTER(u64)]),
         "uzu_engine_time_prefill_linears": (C.c_int, [vp, u32, u32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -555,6 +567,62 @@ class Engine:
         out = np.zeros((1, self.info.vocab_size), dtype=np.uint16)
         _check(self.lib.uzu_engine_last_logits(self.h, out.ctypes.data_as(C.POINTER(C.c_uint16))))
         return out
+
+    # ---- speculative (trie) decode: the verify half of stream.rs:550-657 (host trie logic in uzu_b200/trie.py) ----
+    @property
+    def speculation_supported(self) -> bool:
+        return bool(self.lib.uzu_engine_speculation_supported(self.h))
+
+    def trie_pass(self, tokens, nodes, seeds=None, sampling: SamplingMethod | None = None, want_logits=False):
+        """One Decoder::encode over a linearized trie (<= 16 nodes) from the current state. Returns the token sampled at every node
+        (and the bf16 logits [count, vocab] when want_logits). Nothing is accepted until trie_accept()."""
+        tokens = np.ascontiguousarray(tokens, dtype=np.uint32)
+        nodes = np.ascontiguousarray(nodes, dtype=np.uint32).reshape(len(tokens), 3)
+        n = len(tokens)
+        out = np.zeros(n, dtype=np.uint32)
+        logits = np.zeros((n, self.info.vocab_size), dtype=np.uint16) if want_logits else None
+        sd = np.ascontiguousarray(seeds, dtype=np.uint64) if seeds is not None else None
+        _check(self.lib.uzu_engine_trie_pass(self.h, tokens.ctypes.data_as(C.POINTER(u32)), nodes.ctypes.data_as(C.c_void_p),
+                                             sd.ctypes.data_as(C.POINTER(u64)) if sd is not None else None, n,
+                                             C.byref(sampling) if sampling is not None else None, out.ctypes.data_as(C.POINTER(u32)),
+                                             logits.ctypes.data_as(C.POINTER(C.c_uint16)) if want_logits else None))
+        toks = [int(t) for t in out]
+        return (toks, logits) if want_logits else toks
+
+    def trie_accept(self, accepted_indices, next_token: int):
+        idx = np.ascontiguousarray(accepted_indices, dtype=np.uint32)
+        _check(self.lib.uzu_engine_trie_accept(self.h, idx.ctypes.data_as(C.POINTER(u32)), len(idx), int(next_token)))
+
+    def generate_speculative(self, prompt, steps, proposer, sampling: SamplingMethod | None = None, stats: dict | None = None):
+        """prefill + `steps` tokens through speculation passes, the way LanguageModelStream::generate drives a speculator
+        (stream.rs:550-657, 436-520): `proposer(history, root_token, budget)` returns a uzu_b200.trie.TrieNode tree rooted at `root_token`
+        (a draft model in the reference; any callable here); every pass verifies the whole tree with one sweep over the weights and keeps
+        the path the model itself would have sampled, so the output equals plain decode whatever the proposer suggests."""
+        from .trie import PRng, TrieNode
+        seed = sampling.seed if sampling is not None and sampling.kind == SAMPLING_STOCHASTIC else 0
+        prng = PRng(seed)
+        history = [int(t) for t in prompt]
+        root_token = self.prefill(prompt, sampling)
+        out = [root_token]
+        passes = 0
+        while len(out) < steps:
+            ctx = self.context_length
+            trie = proposer(history + out[:-1], root_token, 16) if proposer is not None else None
+            if trie is None:
+                trie = TrieNode(root_token, prng.derive(ctx))
+            assert trie.token == root_token, "the proposal must be rooted at the last sampled token"
+            trie.prune_to_budget(16)
+            flat = trie.linearize()
+            seeds = [prng.derive(ctx + h) for h in flat.heights()]          # dflash_tfm.rs:267,304
+            sampled = self.trie_pass(flat.token_ids(), flat.nodes(), seeds, sampling)
+            full = flat.accept(sampled)
+            root_token = full[-1][2]
+            self.trie_accept([i for i, _, _ in full], root_token)
+            out.extend(t for _, _, t in full)
+            passes += 1
+        if stats is not None:
+            stats.update(passes=passes, tokens=len(out) - 1, tokens_per_pass=(len(out) - 1) / max(passes, 1))
+        return out[:steps]
 
     # ---- multi-sequence batched decode (extension, see include/uzu_b200.h) ----
     def batch_begin(self, sequences: int):

@@ -32,6 +32,7 @@ SOURCES = {
     "attention_prefill.cu": [],
     "norm.cu": ["-fmad=false"],
     "elementwise.cu": ["-fmad=false"],
+    "activation_transform.cu": ["-fmad=false"],
     "sampling.cu": ["-fmad=false"],
     "deltanet.cu": ["-fmad=false"],
     "deltanet_prefill.cu": ["-fmad=false"],

@@ -270,6 +270,11 @@ struct WeightMatrix {
 struct Linear {
     WeightMatrix w;
     uint32_t in_dim = 0, out_dim = 0;
+    // RHTLinearWrapper (linear/rht_wrapper.rs): i32 +-1 signs of the 32-wide input / output randomized Hadamard; scratch = the engine's
+    // buffer for the transformed activation (the reference transforms its consumed input allocation in place, rht_wrapper.rs:294)
+    Buf in_signs, out_signs;
+    uint64_t rht_scratch = 0;
+    bool rht() const { return in_signs.b != nullptr; }
 };
 
 struct NormCfg {
@@ -345,6 +350,17 @@ struct DecodeState {      // device-resident per-stream scalars (one u32-aligned
 
 constexpr uint32_t MAX_ROWS = 1024;              // ATTENTION_SUFFIX_CAPACITY (mixer/attention/state.rs:14)
 constexpr uint32_t TOKEN_RING = 256;
+constexpr uint32_t MAX_TRIE = 16;                // nodes per speculation pass: the stream's full_batch_size (stream.rs:550) == logits_rows
+
+// RoPE rows of a speculation pass: node i sits at position context + height(i) (transformer.rs:248), so its cos/sin row is a gather
+__global__ void trie_rope_gather_kernel(const uzu_trie_node* nodes, uint32_t context_length, uint32_t dim, const float* cos_table,
+                                        const float* sin_table, float* cos_out, float* sin_out) {
+    const size_t row = (size_t)context_length + nodes[blockIdx.x].height;
+    for (uint32_t d = threadIdx.x; d < dim; d += blockDim.x) {
+        cos_out[(size_t)blockIdx.x * dim + d] = cos_table[row * dim + d];
+        sin_out[(size_t)blockIdx.x * dim + d] = sin_table[row * dim + d];
+    }
+}
 
 __global__ void decode_step_begin_kernel(const DecodeState* st, unsigned long long* seeds) {
     // PRng::derive(position) (encodable_block/sampling/prng.rs:12-23)
@@ -399,6 +415,11 @@ struct uzu_engine {
     Buf decode_state;     // device DecodeState
     Buf snapshot_token;   // next-input token at snapshot time
     uint32_t logits_rows = 16;
+    // speculation pass (trie): device nodes, per-rope gathered cos/sin rows, pinned staging; pending = nodes of an unaccepted pass
+    Buf rht_scratch;
+    Buf trie_nodes, host_trie;
+    std::vector<Buf> trie_cos, trie_sin;
+    uint32_t trie_pending = 0;
     // tensor parallelism (config.json "tensor_parallel" block written by uzu_b200/tp.py; tp.cu holds the collectives)
     uint32_t tp_rank = 0, tp_size = 1, vocab_local = 0;
     bool tp_sharded = false;       // the checkpoint is a shard: row-parallel partials in f32 + exchange, vocab-parallel readout
@@ -507,7 +528,26 @@ static Linear load_linear(uzu_engine* e, ParameterLoader& pl, const std::string&
     Linear l;
     l.in_dim = in_dim;
     l.out_dim = out_dim;
-    l.w = load_weight_matrix(e, pl, prefix + ".weights", "output_input", out_dim, in_dim);
+    const std::string wp = prefix + ".weights";
+    auto it = pl.metadata.find(wp + ".spec");
+    if (it != pl.metadata.end()) {
+        Json spec = parse_json(it->second);
+        if (spec.type_tag() == "HybridSpec") {
+            // Linear::new_mixed_precision (linear/mod.rs:128-143) -> RHTLinearWrapper::load_inner_with_output_rht (rht_wrapper.rs:141-176)
+            const Json* adapter = spec.get("adapter_spec");
+            const Json* block = spec.get("incoherence_block_size");
+            const Json* mode = spec.get("incoherence_processing_mode");
+            if ((adapter && !adapter->is_null()) || !block || block->is_null() || block->u32() != 32 || !mode || mode->str != "input_output")
+                throw std::runtime_error(wp + ": unsupported HybridSpec (only 32-wide input_output RHT without an adapter)");
+            if (in_dim % 32 || out_dim % 32) throw std::runtime_error(wp + ": RHT dimensions must be multiples of 32");
+            l.in_signs = load_tensor(e, pl, wp + ".incoherence_signs.input_signs", {in_dim}, "I32");
+            l.out_signs = load_tensor(e, pl, wp + ".incoherence_signs.output_signs", {out_dim}, "I32");
+            l.w = load_weight_matrix(e, pl, wp + ".quantized", "output_input", out_dim, in_dim);
+            if (l.w.prologue == UZU_B_FULL_PRECISION) throw std::runtime_error(wp + ": fused output-hadamard factors require quantized weights");
+            return l;
+        }
+    }
+    l.w = load_weight_matrix(e, pl, wp, "output_input", out_dim, in_dim);
     return l;
 }
 
@@ -825,6 +865,29 @@ static void create_state_and_scratch(uzu_engine* e) {
         e->rope_cos.push_back(c);
         e->rope_sin.push_back(s);
     }
+    {   // one scratch row block for the input-transformed activation of RHT linears
+        uint32_t max_in = 0;
+        auto visit = [&](Linear& l) { if (l.rht()) max_in = std::max(max_in, l.in_dim); };
+        auto each = [&](auto&& f) {
+            for (auto& L : e->layers) {
+                f(L.up); f(L.down);
+                if (L.is_attention) { f(L.attn.qkv); f(L.attn.out); if (L.attn.has_gate) f(L.attn.gate); }
+                else { f(L.dn.in_proj); f(L.dn.out_proj); }
+            }
+        };
+        each(visit);
+        if (max_in) {
+            if (e->tp_sharded) throw std::runtime_error("tensor-parallel shards of RHT (HybridSpec) linears are not supported");
+            e->rht_scratch = dev((size_t)MAX_ROWS * max_in * 2);
+            each([&](Linear& l) { if (l.rht()) l.rht_scratch = e->rht_scratch.ptr(); });
+        }
+    }
+    e->trie_nodes = dev(MAX_TRIE * sizeof(uzu_trie_node));
+    e->host_trie = make_buf(e, MAX_TRIE * (sizeof(uzu_trie_node) + 8 + 4 + 4), UZU_BUFFER_PINNED_HOST);
+    for (auto& rc : e->ropes) {
+        e->trie_cos.push_back(dev((size_t)MAX_TRIE * rc.head_dim * 4));
+        e->trie_sin.push_back(dev((size_t)MAX_TRIE * rc.head_dim * 4));
+    }
     cudaEventCreateWithFlags(&e->step_events[0], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->step_events[1], cudaEventDisableTiming);
 }
@@ -886,6 +949,7 @@ static void reset_state(uzu_engine* e) {
     cudaStreamSynchronize(e->ctx->stream);
     e->context_length = 0;
     e->snapshot_context = 0;
+    e->trie_pending = 0;
     for (auto& S : e->state) {
         S.length = 0;
         if (S.conv_state.b) {
@@ -917,6 +981,16 @@ static void encode_linear(uzu_command_buffer* cmd, const Linear& l, uint64_t a, 
     ma.ab_scale = 1.0f;
     ma.m = m; ma.n = l.out_dim; ma.k = l.in_dim;
     ma.weights_dt = ma.input_dt = ma.output_dt = UZU_DT_BF16;   // language_model/mod.rs:74
+    if (l.rht()) {   // RHTLinearWrapper::encode_input (rht_wrapper.rs:286-296): InputRht, then the inner matmul with the output factors
+        uzu_activation_transform_args t{};
+        t.input = a; t.fp_out = l.rht_scratch; t.rht_factors = l.in_signs.ptr();
+        t.batch_size = m; t.element_count = l.in_dim;
+        t.ops = UZU_ACTIVATION_TRANSFORM_INPUT_RHT; t.in_place = 0; t.data_type = UZU_DT_BF16;
+        uzu_activation_transform_encode(cmd, &t);
+        ma.a = l.rht_scratch;
+        ma.rht_factors = l.out_signs.ptr();
+        ma.d_transform |= UZU_D_RHT;
+    }
     uzu_matmul_encode(cmd, &ma);
 }
 
@@ -974,6 +1048,7 @@ static void encode_norm(uzu_command_buffer* cmd, const Norm& n, uint64_t input, 
 struct PassCtx {
     uint32_t m = 1;
     bool dynamic = false;   // decode-graph mode: positions come from the device DecodeState
+    uint64_t trie = 0;      // speculation pass: device uzu_trie_node[m] (BatchTopology not flat); RoPE rows come from e->trie_cos/sin
 };
 
 // q/k norms, RoPE + KV append, attention core, optional sigmoid gate: everything between the qkv and the out projections
@@ -1019,6 +1094,10 @@ static void encode_attention_mix(uzu_engine* e, uzu_command_buffer* cmd, const L
         const size_t row0 = pc.dynamic ? 0 : (size_t)e->context_length;   // token positions = context_length + i (transformer.rs:246-247)
         pa.cosines = e->rope_cos[A.rope_index].ptr() + row0 * rc.head_dim * 4;
         pa.sines = e->rope_sin[A.rope_index].ptr() + row0 * rc.head_dim * 4;
+        if (pc.trie) {   // positions = context_length + height (transformer.rs:248): rows gathered by trie_rope_gather_kernel
+            pa.cosines = e->trie_cos[A.rope_index].ptr();
+            pa.sines = e->trie_sin[A.rope_index].ptr();
+        }
     }
     pa.dynamic_position = dyn;
     uzu_attention_prepare_encode(cmd, &pa);
@@ -1031,12 +1110,13 @@ static void encode_attention_mix(uzu_engine* e, uzu_command_buffer* cmd, const L
     aa.scale = A.has_scale ? A.scale : 1.0f / sqrtf((float)D);
     aa.num_heads = Hq; aa.suffix_length = m; aa.head_dim = D; aa.is_causal = A.is_causal;
     aa.dynamic_position = dyn;
+    if (pc.trie) { aa.is_trie = 1; aa.trie = pc.trie; }   // run_core: trie_core + the nodes (mode.rs:178-184), mask.rs:21-29
     // AttentionCores::encode (core/mod.rs:81-93). This backend has no "gemm" core yet, so like the CPU backend long
     // suffixes go through the single/two-pass kernels. For suffix <= 8 with context > 1024 the reference uses the
     // two-pass core; the fused split-KV single-pass entry point computes the same function in one launch, so the
     // engine uses it for every decode step unless UZU_TWO_PASS=1 asks for the literal dispatch.
     static const bool literal_two_pass = getenv("UZU_TWO_PASS") != nullptr;
-    if (literal_two_pass && !pc.dynamic && m <= 8 && prefix + m > 1024) {
+    if (literal_two_pass && !pc.dynamic && !pc.trie && m <= 8 && prefix + m > 1024) {
         aa.out = e->tp_parts.ptr(); aa.sums = e->tp_sums.ptr(); aa.maxs = e->tp_maxs.ptr();
         uzu_attention_two_pass1_encode(cmd, &aa);
         uzu_attention_two_pass2_args a2{e->tp_parts.ptr(), e->tp_sums.ptr(), e->tp_maxs.ptr(), e->attn_out.ptr(), Hq, m, D};
@@ -1186,8 +1266,17 @@ static uzu_fused_linear_args fused_up_args(uzu_engine* e, const Layer& L, bool n
     return f;
 }
 
+static bool any_rht(const uzu_engine* e) {
+    for (auto& L : e->layers) {
+        if (L.up.rht() || L.down.rht()) return true;
+        if (L.is_attention ? (L.attn.qkv.rht() || L.attn.out.rht() || L.attn.gate.rht()) : (L.dn.in_proj.rht() || L.dn.out_proj.rht())) return true;
+    }
+    return e->out_emb.rht();
+}
+
 static bool fused_decode_supported(uzu_engine* e) {
     const uint32_t mask = fuse_mask();
+    if (any_rht(e)) return false;   // RHT linears take the unfused sequence (input transform, GEMV, output transform)
     for (auto& L : e->layers) {
         if (L.pre_mixer.cfg.subtract_mean || L.pre_mlp.cfg.subtract_mean || !L.pre_mixer.cfg.has_scale || !L.pre_mlp.cfg.has_scale) return false;
         std::vector<uzu_fused_linear_args> fs;
@@ -1400,6 +1489,7 @@ struct MegaBuilder {
     }
     void check_linear(const Linear& l) {
         const WeightMatrix& w = l.w;
+        need(!l.rht(), "RHT (HybridSpec) linear");
         need(w.prologue != UZU_B_FULL_PRECISION, "full-precision linear");
         need(w.mode == UZU_QMODE_U4 || w.mode == UZU_QMODE_U8, "signed codes");
         if (!bits) { bits = w.bits; group_size = w.group_size; }
@@ -1894,6 +1984,7 @@ static uint64_t prng_derive(uint64_t seed, uint64_t index) {
 // one non-graph pass over `count` host tokens; optionally samples the last row
 static void run_pass(uzu_engine* e, const uint32_t* tokens, uint32_t count, uint32_t row_begin, uint32_t row_end, bool sample_last) {
     if (count == 0 || count > MAX_ROWS) throw std::runtime_error("pass size must be in 1..1024");
+    if (e->trie_pending) throw std::runtime_error("a speculation pass is pending: uzu_engine_trie_accept first");
     if (e->context_length + count > e->max_context + MAX_ROWS || e->context_length + count > e->rope_positions)
         throw std::runtime_error("context overflow: raise max_context_length");
     state_prepare(e, e->context_length + count);
@@ -1970,6 +2061,7 @@ static bool graph_sampling_matches(const uzu_engine* e) {
 
 // enqueue one decode step (no host wait)
 static void issue_decode_step(uzu_engine* e, uint64_t dev_out, uint32_t dev_out_base_step) {
+    if (e->trie_pending) throw std::runtime_error("a speculation pass is pending: uzu_engine_trie_accept first");
     if (e->context_length + 1 > e->max_context + MAX_ROWS || e->context_length + 1 > e->rope_positions)
         throw std::runtime_error("context overflow: raise max_context_length");
     state_prepare(e, e->context_length + 1);
@@ -2118,6 +2210,7 @@ uzu_status uzu_engine_restore(uzu_engine* e) {
         cudaMemcpyAsync((void*)e->token_ids.ptr(), (void*)e->snapshot_token.ptr(), 4, cudaMemcpyDeviceToDevice, s);
         e->context_length = e->snapshot_context;
         e->steps_returned = e->steps_issued;
+        e->trie_pending = 0;
         cudaStreamSynchronize(s);
         upload_decode_state(e);
     });
@@ -2193,6 +2286,102 @@ uzu_status uzu_engine_forward(uzu_engine* e, const uint32_t* tokens, uint32_t co
         run_pass(e, tokens, count, row_begin, row_end, false);
         if (out_logits && row_end > row_begin)
             cudaMemcpy(out_logits, (void*)e->logits.ptr(), (size_t)(row_end - row_begin) * e->vocab * 2, cudaMemcpyDeviceToHost);
+    });
+}
+
+
+// ---- speculation pass over a trie: the verify half of the stream's speculative decode (stream.rs:550-657) ----
+// The proposer (a draft model / n-gram lookup) and the trie bookkeeping (trie.rs: linearize, accept) stay on the host side of the boundary;
+// the backend runs Decoder::encode over the linearized nodes (positions = context + height, attention masked by subtrie range, one sampled
+// token per node) and later compacts the KV rows of the accepted path (TransformerState::encode_accept).
+int uzu_engine_speculation_supported(const uzu_engine* e) {
+    // Mixer::speculation_supported: attention always, DeltaNet only with a tree-verify core (delta_net.rs:442-444) -- not built here
+    return e && !has_delta(e) ? 1 : 0;
+}
+
+uzu_status uzu_engine_trie_pass(uzu_engine* e, const uint32_t* tokens, const uzu_trie_node* nodes, const uint64_t* seeds, uint32_t count,
+                                const uzu_sampling_method* sampling, uint32_t* out_tokens, uint16_t* out_logits) {
+    UZU_ENGINE_TRY({
+        if (!tokens || !nodes || count == 0 || count > MAX_TRIE) throw std::runtime_error("trie_pass: 1..16 nodes");
+        if (has_delta(e)) throw std::runtime_error("trie_pass: DeltaNet tree verification is not supported (speculation_supported == 0)");
+        if (e->trie_pending) throw std::runtime_error("trie_pass: the previous speculation pass was not accepted");
+        if (e->steps_returned != e->steps_issued) throw std::runtime_error("trie_pass: flush() the in-flight decode steps first");
+        // a linearized trie: depth-first order, node i's subtree = [trie_start, trie_end] = [i, >= i], height = depth (trie.rs:158-178)
+        for (uint32_t i = 0; i < count; ++i) {
+            const uzu_trie_node& n = nodes[i];
+            const bool ok = n.trie_start == i && n.trie_end >= i && n.trie_end < count && n.height <= i && (i == 0 ? n.height == 0 : n.height >= 1 && n.height <= nodes[i - 1].height + 1);
+            if (!ok) throw std::runtime_error("trie_pass: nodes are not a linearized trie");
+        }
+        if (e->context_length + count > e->max_context + MAX_ROWS || e->context_length + count > e->rope_positions)
+            throw std::runtime_error("context overflow: raise max_context_length");
+        if (sampling) e->sampling = *sampling;
+        state_prepare(e, e->context_length + count);
+        cudaStream_t s = e->ctx->stream;
+        // pinned staging: tokens | nodes | seeds | sampled
+        uint8_t* host = (uint8_t*)uzu_buffer_cpu_ptr(e->host_trie.b);
+        uint64_t* h_seeds = (uint64_t*)host;
+        uzu_trie_node* h_nodes = (uzu_trie_node*)(host + MAX_TRIE * 8);
+        uint32_t* h_tokens = (uint32_t*)(host + MAX_TRIE * (8 + sizeof(uzu_trie_node)));
+        uint32_t* h_sampled = h_tokens + MAX_TRIE;
+        memcpy(h_tokens, tokens, count * 4);
+        memcpy(h_nodes, nodes, count * sizeof(uzu_trie_node));
+        for (uint32_t i = 0; i < count; ++i)   // speculator seeds = derive(root position + depth) (dflash_tfm.rs:267,304)
+            h_seeds[i] = seeds ? seeds[i] : prng_derive(e->sampling.seed, (uint64_t)e->context_length + nodes[i].height);
+        CmdGuard g(e->ctx, "trie pass");
+        check(uzu_command_buffer_start_encoding(g.c));
+        uzu_command_buffer_encode_copy(g.c, e->host_trie.ptr() + MAX_TRIE * (8 + sizeof(uzu_trie_node)), e->token_ids.ptr(), count * 4);
+        uzu_command_buffer_encode_copy(g.c, e->host_trie.ptr() + MAX_TRIE * 8, e->trie_nodes.ptr(), count * sizeof(uzu_trie_node));
+        uzu_command_buffer_encode_copy(g.c, e->host_trie.ptr(), e->seeds.ptr(), count * 8);
+        for (size_t r = 0; r < e->ropes.size(); ++r) {
+            trie_rope_gather_kernel<<<count, 64, 0, s>>>((const uzu_trie_node*)e->trie_nodes.ptr(), e->context_length, e->ropes[r].head_dim,
+                                                         (const float*)e->rope_cos[r].ptr(), (const float*)e->rope_sin[r].ptr(),
+                                                         (float*)e->trie_cos[r].ptr(), (float*)e->trie_sin[r].ptr());
+            g.c->launches++;
+        }
+        PassCtx pc;
+        pc.m = count;
+        pc.trie = e->trie_nodes.ptr();
+        encode_decoder(e, g.c, pc, 0, count);        // logits for every node (stream.rs:640: Some(0..batch_dim.size()))
+        encode_sampling(e, g.c, count);
+        uzu_command_buffer_encode_copy(g.c, e->sampled.ptr(), e->host_trie.ptr() + MAX_TRIE * (8 + sizeof(uzu_trie_node)) + MAX_TRIE * 4, count * 4);
+        run_cmd_to_completion(e, g.c);
+        if (out_tokens) memcpy(out_tokens, h_sampled, count * 4);
+        if (out_logits) cudaMemcpy(out_logits, (void*)e->logits.ptr(), (size_t)count * e->vocab * 2, cudaMemcpyDeviceToHost);
+        e->trie_pending = count;
+    });
+}
+
+uzu_status uzu_engine_trie_accept(uzu_engine* e, const uint32_t* accepted_indices, uint32_t count, uint32_t next_token) {
+    UZU_ENGINE_TRY({
+        if (!e->trie_pending) throw std::runtime_error("trie_accept: no speculation pass to accept");
+        if (!accepted_indices || count == 0 || count > e->trie_pending) throw std::runtime_error("trie_accept: 1..pending indices");
+        for (uint32_t i = 0; i < count; ++i)       // mixer/attention/state.rs:179: strictly increasing, inside the pass
+            if (accepted_indices[i] >= e->trie_pending || (i > 0 && accepted_indices[i] <= accepted_indices[i - 1]))
+                throw std::runtime_error("trie_accept: invalid accepted indices");
+        CmdGuard g(e->ctx, "trie accept");
+        check(uzu_command_buffer_start_encoding(g.c));
+        for (size_t l = 0; l < e->layers.size(); ++l) {
+            LayerState& S = e->state[l];
+            // AttentionStateType::Full (state.rs:182-199): accepted row `length + index` moves to `length + i`; already-compact rows stay
+            std::vector<uzu_kv_copy> copies;
+            for (uint32_t i = 0; i < count; ++i)
+                if (accepted_indices[i] != i) copies.push_back(uzu_kv_copy{S.length + accepted_indices[i], S.length + i});
+            if (!copies.empty()) {
+                uzu_kv_cache_update_args ka{};
+                ka.in_place_keys = S.keys; ka.in_place_values = S.values;
+                ka.copies = copies.data(); ka.copy_count = (uint32_t)copies.size();
+                ka.element_dim = e->layers[l].attn.num_groups * e->layers[l].attn.head_dim;
+                uzu_kv_cache_update_encode(g.c, &ka);
+            }
+        }
+        // the last verified node's sampled token is the next pass's root (ForwardPassChaining::Constant, stream.rs:508-513)
+        uint32_t* staging = (uint32_t*)uzu_buffer_cpu_ptr(e->host_tokens.b);
+        staging[0] = next_token;
+        uzu_command_buffer_encode_copy(g.c, e->host_tokens.ptr(), e->token_ids.ptr(), 4);
+        run_cmd_to_completion(e, g.c);
+        e->trie_pending = 0;
+        accept(e, count);
+        upload_decode_state(e);
     });
 }
 
@@ -2612,7 +2801,6 @@ uzu_status uzu_engine_time_linears_select(uzu_engine* e, uint32_t iters, uint32_
                     uzu_fused_linear_args f{};
                     f.matmul = linear_args(L.up, e->hidden_b.ptr(), 1, e->gated.ptr());
                     f.epilogue = 1; f.act_type = L.act;
-                    f.decode_stream = g_stream_lookup(e->mega.stream_of, L.up);
                     f.decode_stream = g_stream_lookup(e->mega.stream_of, L.up);
                     uzu_fused_linear_encode(g.c, &f);
                 }

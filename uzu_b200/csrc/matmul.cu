@@ -1466,7 +1466,11 @@ static const char* validate(const uzu_matmul_args* a) {
     if (!dt_ok(a->weights_dt) || !dt_ok(a->input_dt) || !dt_ok(a->output_dt)) return "unsupported data type (bf16 | f32 only)";
     if (a->m == 0 || a->n == 0 || a->k == 0) return "empty shape";
     if (!a->a || !a->b || !a->d) return "null operand";
-    if (a->d_transform & UZU_D_RHT) return "output RHT (Mirai HybridSpec) is not supported by this backend";
+    if (a->d_transform & UZU_D_RHT) {
+        if (!a->rht_factors) return "UZU_D_RHT without rht_factors";
+        if (a->n % 32 != 0) return "output RHT needs n to be a multiple of HADAMARD_TRANSFORM_BLOCK_SIZE (32)";
+        if (a->gather_indices) return "output RHT with gather_indices is undefined (the transform mixes 32 neighbouring columns)";
+    }
     if (a->b_prologue > UZU_B_SCALE_SYMMETRIC_DEQUANT) return "bad b_prologue";
     if (a->b_prologue != UZU_B_FULL_PRECISION) {
         if (!a->b_transpose) return "quantized B must be [n,k] (b_transpose)";
@@ -1867,6 +1871,28 @@ void uzu_matmul_encode(uzu_command_buffer* cmd, const uzu_matmul_args* args) {
         cmd->record_error(UZU_ERROR_INVALID_ARGUMENT, std::string("matmul: ") + err);
         return;
     }
+    if (args->d_transform & UZU_D_RHT) {
+        // MatmulDOps::rht_factors (cpu/kernel/matmul/kernel.rs:64,162,285,297-303): the product (scale / accumulate / soft-cap epilogue, NO
+        // bias) lands in D, ActivationTransform(OutputRht) runs over D in place, then TensorAddBias adds the bias (bias_after_rht).
+        uzu_matmul_args inner = *args;
+        inner.d_transform &= ~(uint32_t)(UZU_D_RHT | UZU_D_BIAS);
+        inner.bias = 0;
+        inner.rht_factors = 0;
+        uzu::encode_matmul(cmd, cmd->ctx, inner);
+        uzu_activation_transform_args t{};
+        t.fp_out = args->d; t.rht_factors = args->rht_factors;
+        t.batch_size = args->m; t.element_count = args->n;
+        t.ops = UZU_ACTIVATION_TRANSFORM_OUTPUT_RHT; t.in_place = 1; t.data_type = args->output_dt;
+        uzu_activation_transform_encode(cmd, &t);
+        if ((args->d_transform & UZU_D_BIAS) && args->bias) {
+            if (args->output_dt != UZU_DT_BF16 || args->weights_dt != UZU_DT_BF16) {
+                cmd->record_error(UZU_ERROR_UNSUPPORTED, "matmul: bias after output RHT is bf16-only (TensorAddBias)");
+                return;
+            }
+            uzu_tensor_add_bias_encode(cmd, 0, args->bias, args->d, args->n, args->m * args->n);
+        }
+        return;
+    }
     uzu::encode_matmul(cmd, cmd->ctx, *args);
 }
 
@@ -1883,6 +1909,7 @@ int uzu_fused_linear_supported(uzu_context* ctx, const uzu_fused_linear_args* ar
         if (uzu::validate(&m)) return 0;
     }
     // prologue 0 + epilogue 0 = a plain GEMV: only meaningful through this entry point when it brings a decode stream (TMA-fed rings)
+    if (args->matmul.d_transform & UZU_D_RHT) return 0;   // the output transform needs the whole row first: unfused sequence
     if (args->prologue > 3 || args->prologue == 2 || args->epilogue > 1 || (args->prologue == 0 && args->epilogue == 0 && !args->decode_stream)) return 0;
     if (args->prologue == 3 && args->epilogue) return 0;
     if (args->prologue == 0 && !args->matmul.a) return 0;

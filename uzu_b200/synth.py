@@ -33,8 +33,13 @@ class QuantSpec:
     bits: int = 4
     group_size: int = 64
     symmetric: bool = False    # IntSpec.is_symmetric
+    rht: bool = False          # HybridSpec: 32-wide input/output randomized Hadamard around this quantization (Mirai RHT)
 
     def spec_json(self, layout: str) -> dict:
+        if self.rht:
+            inner = QuantSpec(self.kind, self.bits, self.group_size, self.symmetric).spec_json(layout)
+            return {"type": "HybridSpec", "quantization_spec": inner, "adapter_spec": None, "incoherence_block_size": 32,
+                    "incoherence_processing_mode": "input_output"}
         if self.kind == "fp":
             return {"type": "FullPrecisionSpec", "layout": layout}
         if self.kind == "mlx":
@@ -174,6 +179,15 @@ def st_bits_to_f32(bits: np.ndarray) -> np.ndarray:
 
 
 def _add_matrix(tensors, meta, prefix, rng, rows, cols, q, layout, target_std):
+    if q.rht:
+        # RHTLinearWrapper::load_inner_with_output_rht (linear/rht_wrapper.rs:141-176): i32 +-1 signs + the inner matrix under `quantized`
+        assert layout == "output_input" and q.kind != "fp" and rows % 32 == 0 and cols % 32 == 0
+        inner = QuantSpec(q.kind, q.bits, q.group_size, q.symmetric)
+        tensors[f"{prefix}.incoherence_signs.input_signs"] = rng.choice(np.array([-1, 1], np.int32), cols)
+        tensors[f"{prefix}.incoherence_signs.output_signs"] = rng.choice(np.array([-1, 1], np.int32), rows)
+        _add_matrix(tensors, meta, prefix + ".quantized", rng, rows, cols, inner, layout, target_std)
+        meta[f"{prefix}.spec"] = json.dumps(q.spec_json(layout))
+        return
     for k, v in quantized_matrix(rng, rows, cols, q, target_std).items():
         tensors[f"{prefix}.{k}"] = v
     meta[f"{prefix}.spec"] = json.dumps(q.spec_json(layout))
@@ -184,6 +198,8 @@ def build_weights(spec: ModelSpec, seed: int = 0):
     T, M = {}, {}
     H, F, V = spec.model_dim, spec.hidden_dim, spec.vocab_size
     eq = spec.embedding_quant or spec.quant
+    if eq.rht:     # quantized embeddings with a Hadamard are unimplemented on the reference CPU backend (quant_embedding.rs:32-34)
+        eq = QuantSpec(eq.kind, eq.bits, eq.group_size, eq.symmetric)
     if spec.tied_embeddings:
         _add_matrix(T, M, "decoder.embedding.embedding", rng, V, H, eq, "input_output", 1.0 / np.sqrt(H) * 4.0)
     else:
