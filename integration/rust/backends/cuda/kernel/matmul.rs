@@ -59,9 +59,8 @@ impl MatmulKernel for CudaMatmul {
                 (args.b, args.b_scales) = (addr(b), addr(scales));
             }
         }
-        if a.d_transform.rht_factors.is_some() {
-            return Err(CudaError::NotSupported("output RHT (Mirai HybridSpec)"));
-        }
+        // MatmulDOps::rht_factors: the library runs OutputRht over D after the epilogue and adds the bias after it (kernel.rs:297-303)
+        args.rht_factors = a.d_transform.rht_factors.map(|f| addr(f)).unwrap_or(0);
         args.d_transform = a.d_transform.mask().bits();
         args.ab_scale = a.d_transform.ab_scale;
         args.soft_cap = a.d_transform.soft_cap.unwrap_or(0.0);

@@ -1,10 +1,9 @@
-//! `Backend::Kernels` for CUDA (backends/common/kernel/mod.rs:16-25): the hand-written slots + the generated traits.
+//! `Backend::Kernels` for CUDA (backends/common/kernel/mod.rs:16-25): the hand-written matmul slot + the 72 generated traits
+//! (generated.rs, emitted by tools/gen_rust_kernels.py -- the `build/cuda/compiler.rs` arm of build/cpu/compiler.rs:176-658).
+pub(crate) mod generated;
 mod matmul;
-mod normalization;
-// mod generated;   // emitted by build/cuda/compiler.rs from the same kernel table as build/cpu/compiler.rs (one impl per #[kernel])
 
 pub use matmul::CudaMatmul;
-pub use normalization::CudaNormalizationKernel;
 
 use std::convert::Infallible;
 
@@ -16,15 +15,16 @@ pub struct CudaKernels;
 
 impl Kernels for CudaKernels {
     type Backend = Cuda;
+
+    generated::autogen_cuda_kernels!();
     type MatmulKernel = CudaMatmul;
     // Optional cores this backend does not provide are `Infallible`, as in cpu/kernel/mod.rs:35-37: attention always goes through the
-    // single-pass / two-pass kernels (the library folds both into one split-KV kernel), DeltaNet prefill through the flat decode branch.
+    // single-pass / two-pass kernels (the library folds both into one split-KV kernel and picks its tensor-core prefill kernel itself),
+    // DeltaNet prefill through the flat decode branch, no DeltaNet tree verification (speculation_supported() == false for hybrids).
     type AttentionGemmCore = Infallible;
     type DeltaNetChunkedPrefill = Infallible;
     type DeltaNetTreeVerify = Infallible;
     type RadixTopKSmall = Infallible;
-    type NormalizationKernel = CudaNormalizationKernel;
-    // type QKVNormKernel = ..., type AttentionPrepareKernel = ..., ... (generated.rs)
 }
 
 /// `gpu_ptr + byte offset` of a kernel argument (BufferArg::into_parts, buffer/arg.rs:4-59)

@@ -5,6 +5,7 @@ mod command_buffer;
 mod context;
 mod error;
 pub mod ffi;
+pub mod ffi_generated;
 pub mod kernel;
 
 pub use backend::Cuda;

@@ -130,13 +130,23 @@ def generate() -> str:
     for name, fields in structs.items():
         size, _ = layout(fields, structs, opaque, enum_types)
         out.append(f"/// {size} bytes")
-        out.append("#[repr(C)] #[derive(Clone, Copy)]")
+        has_ptr = any(rust_type(ct, structs, opaque, enum_types).startswith("*") for _, ct, _ in fields)
+        nested = any(rust_type(ct, structs, opaque, enum_types) in structs and
+                     any(rust_type(c2, structs, opaque, enum_types).startswith("*") for _, c2, _ in structs[rust_type(ct, structs, opaque, enum_types)])
+                     for _, ct, _ in fields)
+        out.append("#[repr(C)] #[derive(Clone, Copy)]" if has_ptr or nested else "#[repr(C)] #[derive(Default, Clone, Copy)]")
         out.append(f"pub struct {name} {{")
         for f, ctype, n in fields:
             rt = rust_type(ctype, structs, opaque, enum_types)
             out.append(f"    pub {f}: " + (f"[{rt}; {n}]," if n else f"{rt},"))
         out.append("}")
         out.append("")
+    out.append("/// (C name, size_of) of every argument struct: ffi::abi_self_check() compares them with uzu_abi_struct_size() of the loaded library")
+    out.append("pub const STRUCT_SIZES: &[(&str, usize)] = &[")
+    for name in structs:
+        out.append(f"    (\"{name}\", std::mem::size_of::<{name}>()),")
+    out.append("];")
+    out.append("")
     out.append('#[link(name = "uzu_b200")]')
     out.append('extern "C" {')
     for name, ret, args in funcs:

@@ -92,7 +92,7 @@ size_t uzu_abi_struct_size(const char* name) {
     UZU_SZ(uzu_attention_args) UZU_SZ(uzu_attention_two_pass2_args) UZU_SZ(uzu_kv_cache_update_args) UZU_SZ(uzu_gated_act_mul_args)
     UZU_SZ(uzu_quantized_embedding_lookup_args) UZU_SZ(uzu_unified_sampling_args) UZU_SZ(uzu_delta_net_conv_update_args)
     UZU_SZ(uzu_delta_net_update_args) UZU_SZ(uzu_engine_options) UZU_SZ(uzu_sampling_method) UZU_SZ(uzu_model_info)
-    UZU_SZ(uzu_ring_params) UZU_SZ(uzu_trie_node) UZU_SZ(uzu_kv_copy) UZU_SZ(uzu_delta_net_fused_update_args) UZU_SZ(uzu_qk_norm_config) UZU_SZ(uzu_attention_prepare_norm_args) UZU_SZ(uzu_tp_all_gather_args)
+    UZU_SZ(uzu_ring_params) UZU_SZ(uzu_trie_node) UZU_SZ(uzu_kv_copy) UZU_SZ(uzu_delta_net_fused_update_args) UZU_SZ(uzu_qk_norm_config) UZU_SZ(uzu_attention_prepare_norm_args) UZU_SZ(uzu_tp_all_gather_args) UZU_SZ(uzu_activation_transform_args)
 #undef UZU_SZ
     return 0;
 }
