@@ -445,6 +445,39 @@ def roofline_of(eng, workload: str, prefill: int, K: int, seconds: float):
     return roof, extra
 
 
+def speculation_of(eng, step_ms: float, nodes: int = 16, passes: int = 6):
+    """Cost of one speculation pass (uzu_engine_trie_pass over a linearized trie of `nodes` nodes: one sweep over the weights, logits + a
+    sampled token for every node) next to the plain decode step of the timed run. Wall clock around the synchronous call,
+    which ends with the D2H read of the sampled ids like the stream's speculation loop. `break_even_tokens_per_pass` = pass / step: a
+    proposer has to get more than that many tokens accepted per pass for speculation to pay on this GPU."""
+    if not eng.speculation_supported:
+        return {"supported": False, "reason": "DeltaNet layers: no tree-verify core (Mixer::speculation_supported, delta_net.rs:442-444)"}
+    from uzu_b200.trie import PRng, TrieNode
+    rng = np.random.default_rng(1)
+    V = eng.info.vocab_size
+    eng.flush()
+    root = TrieNode(int(rng.integers(0, V)), 0)
+    node, made = root, 1
+    while made < nodes:                      # a bushy trie: siblings and chains, the shape a draft model proposes
+        child = TrieNode(int(rng.integers(0, V)), 0)
+        if node.get(child.token) is not None:
+            continue
+        node.add(child)
+        made += 1
+        if made % 3 == 0:
+            node = child
+    flat = root.linearize()
+    ms = []
+    for _ in range(passes):
+        t0 = time.perf_counter()
+        sampled = eng.trie_pass(flat.token_ids(), flat.nodes())
+        ms.append((time.perf_counter() - t0) * 1e3)
+        eng.trie_accept([0], sampled[0])
+    pass_ms = float(np.median(ms[1:]))
+    return {"supported": True, "nodes": nodes, "pass_ms": pass_ms, "plain_step_ms": step_ms, "break_even_tokens_per_pass": pass_ms / step_ms,
+            "note": "verify half only (no draft model in scope): the pass runs the unfused kernel sequence with the rows GEMV (2..16 rows per weight pass)"}
+
+
 def prefill_gemm_of(eng, prefill: int):
     try:
         pm = min(prefill, 1024)
@@ -525,6 +558,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "clocks": m["clocks"],
     }
     threads = effective_cpus()
+    if rank == 0 and tp == 1:
+        try:
+            line["config"]["speculation"] = speculation_of(eng, 1000.0 * m["seconds"] / K)
+        except Exception as ex:  # a side measurement must not take the line down
+            line["config"]["speculation"] = {"error": str(ex)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"], line["parity"] = cpu_leg(eng, full_dir, threads, budget_s=45.0)

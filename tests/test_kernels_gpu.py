@@ -70,6 +70,51 @@ def test_quantized_matmul_baseline_shapes(ctx, m, n, k, bits, gs, method):
     assert_f32_close(got[:, rows], ref, rtol=1e-3, atol=1e-4, what=f"matmul {m}x{n}x{k} int{bits} gs{gs} {method} (sampled rows)")
 
 
+# rows kernel (qmv_rows_kernel, 2..16 activation rows per weight pass: speculation passes, multi-sequence decode): every quantisation
+# method it instantiates, one and two MMA column blocks, k-slices through the split-k workspace, ragged n, several launches (m > 16)
+ROWS_CASES = [
+    (2, 64, 512, 4, 64, "zp"), (3, 4096, 4096, 4, 64, "zp"), (8, 6144, 4096, 4, 64, "zp"), (9, 4096, 4096, 4, 64, "zp"),
+    (16, 4096, 14336, 4, 64, "zp"), (16, 28672, 4096, 4, 64, "zp"), (5, 1000, 1024, 4, 64, "zp"), (16, 72, 2048, 4, 64, "mlx"),
+    (12, 512, 2048, 4, 128, "sym"), (7, 1024, 1536, 4, 128, "zp"), (8, 4096, 4096, 8, 64, "zp"), (16, 1024, 14336, 8, 64, "zp"),
+    (4, 256, 1024, 8, 64, "mlx"), (13, 320, 2048, 8, 64, "sym"), (40, 96, 512, 4, 64, "zp"), (33, 2048, 1024, 4, 64, "zp"),
+]
+
+
+@pytest.mark.parametrize("m,n,k,bits,gs,method", ROWS_CASES)
+def test_rows_kernel_matches_oracle(ctx, m, n, k, bits, gs, method):
+    x, w, kw = _quant_case(500 + n + k + m, m, n, k, bits, gs, METHODS[method])
+    cap = 1536                                    # oracle on a row sample for the big shapes (same function on those rows)
+    rows = np.arange(n) if n <= cap else np.sort(np.random.default_rng(n + m).choice(n, size=cap, replace=False))
+    sub = dict(kw)
+    sub["scales"] = np.ascontiguousarray(kw["scales"][rows])
+    for key in ("zero_points", "biases"):
+        if kw.get(key) is not None:
+            sub[key] = np.ascontiguousarray(kw[key][rows])
+    got, launches = G.matmul(ctx, x, w, m=m, n=n, k=k, d_f32=True, return_launches=True, **kw)
+    assert launches == (m + 15) // 16, "one launch per 16 activation rows"
+    ref = O.matmul(x, np.ascontiguousarray(w[rows]), m=m, n=len(rows), k=k, d_f32=True, threads=8, **sub)
+    assert_f32_close(got[:, rows], ref, rtol=1e-3, atol=1e-4, what=f"rows kernel {m}x{n}x{k} int{bits} gs{gs} {method}")
+    # every row of the batch is what the m = 1 decode kernel computes for it
+    one = G.matmul(ctx, x[m - 1:m], w, m=1, n=n, k=k, d_f32=True, **kw)
+    assert_f32_close(got[m - 1:m], one, rtol=1e-3, atol=1e-4, what="rows kernel vs decode kernel")
+
+
+def test_rows_kernel_epilogue_variants(ctx):
+    m, n, k = 11, 1024, 2048
+    x, w, kw = _quant_case(77, m, n, k, 4, 64, METHODS["zp"])
+    rng = np.random.default_rng(5)
+    bias = f32_to_bf16(rng.uniform(-0.5, 0.5, n).astype(np.float32))
+    d0 = f32_to_bf16(rng.uniform(-1, 1, (m, n)).astype(np.float32))
+    for extra in (dict(bias=bias), dict(ab_scale=0.37), dict(soft_cap=20.0), dict(accumulate=True, d=d0.copy()), dict(bias=bias, ab_scale=1.7, soft_cap=30.0)):
+        ref = O.matmul(x, w, m=m, n=n, k=k, threads=8, **kw, **{k_: (v.copy() if isinstance(v, np.ndarray) else v) for k_, v in extra.items()})
+        got = G.matmul(ctx, x, w, m=m, n=n, k=k, **kw, **{k_: (v.copy() if isinstance(v, np.ndarray) else v) for k_, v in extra.items()})
+        assert_bf16_close(got, ref, what=f"rows kernel epilogue {sorted(extra)}")
+    sx, sw, skw = _quant_case(78, 6, 512, 1024, 4, 64, METHODS["zp"])
+    ref = O.matmul(sx, sw, m=6, n=512, k=1024, signed_codes=True, threads=4, **skw)
+    got = G.matmul(ctx, sx, sw, m=6, n=512, k=1024, signed_codes=True, **skw)
+    assert_bf16_close(got, ref, what="rows kernel signed codes")
+
+
 @pytest.mark.parametrize("m,n,k,bits,gs,method", QUANT_CASES[:9])
 def test_quantized_matmul_bf16_out(ctx, m, n, k, bits, gs, method):
     x, w, kw = _quant_case(200 + n + k, m, n, k, bits, gs, METHODS[method])

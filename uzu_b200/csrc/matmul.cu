@@ -806,6 +806,9 @@ __device__ __forceinline__ void qa_bulk_copy(uint32_t dst_smem, const void* src,
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_addr), "l"(gptr) : "memory");
 }
+__device__ __forceinline__ void cp_async8(uint32_t smem_addr, const void* gptr) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_addr), "l"(gptr) : "memory");
+}
 __device__ __forceinline__ void cp_async4(uint32_t smem_addr, const void* gptr) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_addr), "l"(gptr) : "memory");
 }
@@ -1382,6 +1385,405 @@ __global__ void __launch_bounds__(QS_WARPS * 32) qmv_decode_async_kernel(const Q
 }
 
 // -------------------------------------------------------------------------------------------------
+// Rows kernel: 2..16 activation rows share ONE pass over the weights (speculation passes over a trie, multi-sequence batched decode,
+// the tail rows of a prefill chunk). Same weight stream and dot engine as the decode kernel (per-warp cp.async rings, mma.sync
+// m16n8k16 over (128 + code) bf16 pairs, hoisted per-group affine), but the 8 MMA columns carry 8 ACTIVATION ROWS instead of being
+// steered to quantisation groups. For that the groups must be separable without spending columns: a lane copies bytes [8t, 8t+8) and
+// [32 + 8t, 32 + 8t + 8) of every 64-byte chunk of a weight row (two 8-byte cp.async instead of one 16-byte one), so words 0-1 of
+// every lane lie in the first 64 nibbles of the chunk and words 2-3 in the second: with 64-nibble groups the MMAs of words 0-1
+// accumulate group 2j and those of words 2-3 group 2j+1 of chunk j (128-nibble groups: the whole chunk is one group). Per super-chunk
+// a warp issues 32 x MB MMAs (MB = 1 for <= 8 rows, 2 for <= 16) where the older streaming kernel needed 32 x 4 for 16 rows.
+// A CTA (8 warps, one per SM) is pinned to one k-slice (grid is a multiple of kslices), stages the m x slice activations once
+// (bf16 B-fragment layout + per-group sums, row stride padded to an odd number of 16-byte items so the 8 rows of a fragment load hit
+// 8 different bank groups) and walks tile groups; the WPT warps of a tile meet in shared memory, k-slices in the split-k workspace.
+// -------------------------------------------------------------------------------------------------
+#ifndef UZU_QMV_ROWS_DEFAULT_WARPS
+#define UZU_QMV_ROWS_DEFAULT_WARPS 16
+#endif
+constexpr int RW_WARPS = 8;      // warps per CTA of the default variant (the host sizes rings / reduction buffers with the launch's own count)
+
+template <int NPG, int STAGES, int METHOD, int BITS, int MB, int WARPS, int FEED>
+__global__ void __launch_bounds__(WARPS * 32, 1) qmv_rows_kernel(const QmvParams p) {
+    constexpr uint32_t method = (uint32_t)METHOD, bits = BITS;
+    static_assert(NPG == 64 || NPG == 128, "rows kernel covers int4 gs64 / gs128 and int8 gs64");
+    constexpr int GPS = 512 / NPG;          // groups per super-chunk: 8 or 4
+    constexpr int MROWS = MB * 8;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t ngroups = p.groups_per_row;
+    const uint32_t kslices = p.kslices, cps = p.chunks_per_slice;
+    const uint32_t slice = blockIdx.x % kslices;                 // constant over this CTA's items (host: gridDim.x % kslices == 0)
+    const uint32_t cb = slice * cps, ce = min(p.chunks_total, cb + cps);
+    const uint32_t slice_items = cps * 16u;                      // 16-byte B-fragment items per activation row and slice
+    const uint32_t xstride = slice_items + 1u;                   // odd: rows g and g+1 of a fragment load fall on different bank groups
+    const uint32_t sgroups = (cps * 128u) / NPG;                 // groups per slice
+    uint4* xs = reinterpret_cast<uint4*>(smem_raw);                                              // [MROWS][xstride]
+    float* sx = reinterpret_cast<float*>(smem_raw + (size_t)MROWS * xstride * 16);               // [MROWS][sgroups]
+    const uint32_t sxs = sgroups | 1u;                           // odd row stride: the four activation-row pairs of a quad read different banks
+    float* red = sx + (size_t)MROWS * sxs;                                                   // [WARPS][MROWS][16]
+    uint8_t* ring_base = reinterpret_cast<uint8_t*>(red + WARPS * MROWS * 16) + (size_t)warp * STAGES * QA_STAGE_BYTES;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring_base);
+    uint32_t magic;
+    asm volatile("mov.b32 %0, 0x43004300;" : "=r"(magic));
+
+    const float mult128 = bits == 4 ? 128.0f : 128.0f * 17.0f;
+    const float sym_mid = bits == 4 ? 8.0f : 128.0f;
+    const bool lane_has_groups = 2 * t < GPS;
+
+    const uint32_t WPT = p.warps_per_tile, TPC = WARPS / WPT;
+    const uint32_t tile_local = warp / WPT, kpart = warp % WPT;
+    const uint32_t tiles = (p.n + 15u) / 16u;
+    const uint32_t tile_groups = (tiles + TPC - 1) / TPC;
+    const uint32_t items_cta = tile_groups * kslices;
+
+    struct Item {
+        uint32_t tile;
+        const uint8_t *wa_base, *wb_base;
+        const __nv_bfloat16 *sa_base, *sb_base;
+        const uint8_t *za_base, *zb_base;
+        uint32_t za_row, zb_row;               // byte offset of the row's first zero-point byte
+    };
+    auto setup = [&](Item& it, uint32_t item) {
+        it.tile = (item / kslices) * TPC + tile_local;
+        const uint32_t tl = min(it.tile, tiles - 1u);
+        const uint32_t row_a = min(tl * 16u + (uint32_t)g, p.n - 1), row_b = min(tl * 16u + (uint32_t)g + 8u, p.n - 1);
+        it.wa_base = p.w + (size_t)row_a * p.row_bytes + (size_t)t * (FEED ? 16 : 8);
+        it.wb_base = p.w + (size_t)row_b * p.row_bytes + (size_t)t * (FEED ? 16 : 8);
+        it.sa_base = p.scales + (size_t)row_a * ngroups + 2 * t;
+        it.sb_base = p.scales + (size_t)row_b * ngroups + 2 * t;
+        if (method == UZU_QMETHOD_SCALE_BIAS) {
+            it.za_base = reinterpret_cast<const uint8_t*>(p.biases + (size_t)row_a * ngroups + 2 * t);
+            it.zb_base = reinterpret_cast<const uint8_t*>(p.biases + (size_t)row_b * ngroups + 2 * t);
+        } else {
+            it.za_base = it.zb_base = nullptr;
+        }
+        it.za_row = row_a * p.zp_stride;
+        it.zb_row = row_b * p.zp_stride;
+    };
+    // one stage = one super-chunk of this warp's tile: per lane 4 chunks x 2 rows x (8 + 8) bytes of codes, then the coefficient words
+    auto issue_stage = [&](const Item& it, uint32_t c0, uint32_t slot) {
+        const uint32_t sbase = ring_s + slot * QA_STAGE_BYTES + (uint32_t)lane * 16u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint8_t* sa_ = it.wa_base + (size_t)(c0 + j) * 64;
+            const uint8_t* sb_ = it.wb_base + (size_t)(c0 + j) * 64;
+            if (FEED) {      // 16 contiguous bytes per lane (L2-only cp.async.cg); the consumer regroups the halves with one quad exchange
+                cp_async16(sbase + (uint32_t)j * 512u, sa_);
+                cp_async16(sbase + (uint32_t)(4 + j) * 512u, sb_);
+            } else {
+                cp_async8(sbase + (uint32_t)j * 512u, sa_);
+                cp_async8(sbase + (uint32_t)j * 512u + 8u, sa_ + 32);
+                cp_async8(sbase + (uint32_t)(4 + j) * 512u, sb_);
+                cp_async8(sbase + (uint32_t)(4 + j) * 512u + 8u, sb_ + 32);
+            }
+        }
+        if (lane_has_groups) {
+            const uint32_t wbase = ring_s + slot * QA_STAGE_BYTES + 4096u + (uint32_t)lane * 4u;
+            const uint32_t gi = (c0 * 128u) / NPG;
+            cp_async4(wbase, it.sa_base + gi);
+            cp_async4(wbase + 128u, it.sb_base + gi);
+            if (method == UZU_QMETHOD_SCALE_ZERO_POINT) {
+                const uint32_t goff = (bits == 4 ? gi / 2 + (uint32_t)t : gi + 2u * (uint32_t)t);
+                cp_async4(wbase + 256u, p.zero_points + ((it.za_row + goff) & ~3u));
+                cp_async4(wbase + 384u, p.zero_points + ((it.zb_row + goff) & ~3u));
+            } else if (method == UZU_QMETHOD_SCALE_BIAS) {
+                cp_async4(wbase + 256u, it.za_base + (size_t)gi * 2);
+                cp_async4(wbase + 384u, it.zb_base + (size_t)gi * 2);
+            }
+        }
+    };
+    auto first_sc = [&]() { return cb + kpart * 4u; };
+
+    struct Cursor { uint32_t item, c0; Item it; };
+    auto cursor_begin = [&](Cursor& c, uint32_t item) {
+        c.item = item;
+        if (item < items_cta) { setup(c.it, item); c.c0 = first_sc(); }
+    };
+    auto cursor_has = [&](const Cursor& c) { return c.item < items_cta && c.it.tile < tiles && c.c0 < ce; };
+    Cursor ic;
+    cursor_begin(ic, blockIdx.x);
+    uint32_t issued = 0;
+    auto issue_next = [&]() {
+        while (ic.item < items_cta && !cursor_has(ic)) cursor_begin(ic, ic.item + gridDim.x);
+        if (ic.item < items_cta) {
+            issue_stage(ic.it, ic.c0, issued % STAGES);
+            ic.c0 += 4u * WPT;
+        }
+        cp_async_commit();
+        ++issued;
+    };
+#pragma unroll
+    for (int s_ = 0; s_ < STAGES - 1; ++s_) issue_next();      // weights do not depend on the producer of the activations
+    pdl_launch_dependents();
+    pdl_wait();
+
+    {   // ---- one-time staging of this CTA's k-slice of the m activation rows (rows >= m: zeros). All global loads of a batch are
+        // issued before any is consumed: the loop is L2-latency-bound otherwise (one dependent round trip per item) ----------------
+        constexpr uint32_t IPG = NPG / 8;
+        constexpr int BATCH = 8;
+        const uint32_t total = MROWS * slice_items;
+        for (uint32_t base = tid; base < total; base += blockDim.x * BATCH) {
+            uint4 v[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                const uint32_t it = base + u * blockDim.x;
+                v[u] = make_uint4(0, 0, 0, 0);
+                if (it < total) {
+                    const uint32_t r = it / slice_items, li = it % slice_items;
+                    const uint32_t pos = (cb * 16u + li) * 8u;          // nibble position in the row
+                    if (r < p.m && pos < p.np) {
+                        if (bits == 4) v[u] = *reinterpret_cast<const uint4*>(p.x + (size_t)r * p.k + pos);
+                        else {
+                            const uint2 h = *reinterpret_cast<const uint2*>(p.x + (size_t)r * p.k + pos / 2);
+                            v[u].x = h.x; v[u].y = h.y;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                const uint32_t it = base + u * blockDim.x;
+                if (it >= total) break;                  // warp-uniform: total and blockDim.x are multiples of 32
+                const uint32_t r = it / slice_items, li = it % slice_items;
+                uint4 out;
+                float part = 0.0f;
+                if (bits == 4) {
+                    out.x = __byte_perm(v[u].x, v[u].z, 0x5410);
+                    out.y = __byte_perm(v[u].x, v[u].z, 0x7632);
+                    out.z = __byte_perm(v[u].y, v[u].w, 0x5410);
+                    out.w = __byte_perm(v[u].y, v[u].w, 0x7632);
+                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { part += __low2float(h2[e]); part += __high2float(h2[e]); }
+                } else {
+                    __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v[u].x);
+                    __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&v[u].y);
+                    const float x0 = __low2float(a), x1 = __high2float(a), x2 = __low2float(b), x3 = __high2float(b);
+                    __nv_bfloat162 o0 = __floats2bfloat162_rn(x0, x2);
+                    __nv_bfloat162 o1 = __floats2bfloat162_rn(16.0f * x0, 16.0f * x2);
+                    __nv_bfloat162 o2 = __floats2bfloat162_rn(x1, x3);
+                    __nv_bfloat162 o3 = __floats2bfloat162_rn(16.0f * x1, 16.0f * x3);
+                    out.x = *reinterpret_cast<uint32_t*>(&o0);
+                    out.y = *reinterpret_cast<uint32_t*>(&o1);
+                    out.z = *reinterpret_cast<uint32_t*>(&o2);
+                    out.w = *reinterpret_cast<uint32_t*>(&o3);
+                    part = ((x0 + x1) + x2) + x3;
+                }
+                xs[(size_t)r * xstride + li] = out;
+#pragma unroll
+                for (uint32_t o = 1; o < IPG; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                if ((li & (IPG - 1)) == 0) sx[(size_t)r * sxs + li / IPG] = part;
+            }
+        }
+    }
+    __syncthreads();
+
+    uint32_t consumed = 0;
+    for (uint32_t item = blockIdx.x; item < items_cta; item += gridDim.x) {
+        Item cur;
+        setup(cur, item);
+        const uint32_t tile = cur.tile;
+        float acc[MB][4];
+#pragma unroll
+        for (int c = 0; c < MB; ++c) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0f; }
+
+        if (tile < tiles) {
+            for (uint32_t c0 = first_sc(); c0 < ce; c0 += 4u * WPT) {
+                // the coefficient words of a stage are read by all four lanes of a quad: nobody refills the slot consumed last iteration
+                // before every lane is done with it, and nobody reads the new stage before every lane's copies have landed
+                __syncwarp();
+                issue_next();
+                cp_async_wait<STAGES - 1>();
+                __syncwarp();
+                const uint32_t slot = consumed % STAGES;
+                ++consumed;
+                const uint4* sw = reinterpret_cast<const uint4*>(ring_base + (size_t)slot * QA_STAGE_BYTES) + lane;
+                const uint4* swc = reinterpret_cast<const uint4*>(ring_base + (size_t)slot * QA_STAGE_BYTES + 4096);
+                // coefficient words of rows g / g+8 for all groups of the super-chunk: the four lanes of this quad hold them (word [w][g*4 + t'])
+                const uint4 sa4 = swc[g], sb4 = swc[8 + g];
+                uint4 za4 = make_uint4(0, 0, 0, 0), zb4 = make_uint4(0, 0, 0, 0);
+                if (method != UZU_QMETHOD_SCALE_SYMMETRIC) { za4 = swc[16 + g]; zb4 = swc[24 + g]; }
+                const uint32_t sav[4] = {sa4.x, sa4.y, sa4.z, sa4.w}, sbv[4] = {sb4.x, sb4.y, sb4.z, sb4.w};
+                const uint32_t zav[4] = {za4.x, za4.y, za4.z, za4.w}, zbv[4] = {zb4.x, zb4.y, zb4.z, zb4.w};
+                const uint32_t gi0 = (c0 * 128u) / NPG;                     // first group of the super-chunk (row-global)
+                const uint32_t gl0 = gi0 - (cb * 128u) / NPG;               // ... and slice-local (index into sx)
+
+                // affine of one finished group fragment: out[wrow][arow] += s[wrow] * (d + k[wrow] * Sx[arow]); gl = group within the super-chunk
+                auto affine = [&](const float (&d)[MB][4], int gl) {
+                    const int tq = gl >> 1, hi = gl & 1;                    // quad lane t' holding the pair (2t', 2t'+1), which half
+                    const uint32_t bsa = sav[tq], bsb = sbv[tq];
+                    const float sa_ = hi ? __uint_as_float(bsa & 0xffff0000u) : __uint_as_float(bsa << 16);
+                    const float sb_ = hi ? __uint_as_float(bsb & 0xffff0000u) : __uint_as_float(bsb << 16);
+                    float ka, kb, ba = 0.0f, bb = 0.0f;
+                    if (method == UZU_QMETHOD_SCALE_ZERO_POINT) {
+                        const uint32_t goff = bits == 4 ? gi0 / 2 + (uint32_t)tq : gi0 + 2u * (uint32_t)tq;
+                        const uint32_t wa_ = zav[tq] >> (((cur.za_row + goff) & 3u) * 8u), wb_ = zbv[tq] >> (((cur.zb_row + goff) & 3u) * 8u);
+                        if (bits == 4) {
+                            ka = -((float)((wa_ >> (hi * 4)) & 15u) + mult128);
+                            kb = -((float)((wb_ >> (hi * 4)) & 15u) + mult128);
+                        } else {
+                            ka = -((float)((wa_ >> (hi * 8)) & 255u) + mult128);
+                            kb = -((float)((wb_ >> (hi * 8)) & 255u) + mult128);
+                        }
+                    } else if (method == UZU_QMETHOD_SCALE_BIAS) {
+                        ka = kb = -mult128;
+                        ba = hi ? __uint_as_float(zav[tq] & 0xffff0000u) : __uint_as_float(zav[tq] << 16);
+                        bb = hi ? __uint_as_float(zbv[tq] & 0xffff0000u) : __uint_as_float(zbv[tq] << 16);
+                    } else {
+                        ka = kb = -(sym_mid + mult128);
+                    }
+#pragma unroll
+                    for (int c = 0; c < MB; ++c) {
+                        const float s0 = sx[(size_t)(c * 8 + 2 * t) * sxs + gl0 + gl], s1 = sx[(size_t)(c * 8 + 2 * t + 1) * sxs + gl0 + gl];
+                        if (method == UZU_QMETHOD_SCALE_BIAS) {
+                            acc[c][0] += sa_ * (d[c][0] + ka * s0) + ba * s0;
+                            acc[c][1] += sa_ * (d[c][1] + ka * s1) + ba * s1;
+                            acc[c][2] += sb_ * (d[c][2] + kb * s0) + bb * s0;
+                            acc[c][3] += sb_ * (d[c][3] + kb * s1) + bb * s1;
+                        } else {
+                            acc[c][0] += sa_ * (d[c][0] + ka * s0);
+                            acc[c][1] += sa_ * (d[c][1] + ka * s1);
+                            acc[c][2] += sb_ * (d[c][2] + kb * s0);
+                            acc[c][3] += sb_ * (d[c][3] + kb * s1);
+                        }
+                    }
+                };
+
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 va = sw[j * 32], vb = sw[(4 + j) * 32];
+                    if (p.xor_mask) {
+                        va.x ^= p.xor_mask; va.y ^= p.xor_mask; va.z ^= p.xor_mask; va.w ^= p.xor_mask;
+                        vb.x ^= p.xor_mask; vb.y ^= p.xor_mask; vb.z ^= p.xor_mask; vb.w ^= p.xor_mask;
+                    }
+                    if (FEED) {
+                        // lane t holds nibbles [32t, 32t + 32) of the chunk: lanes t < 2 keep their first two words and take the first two of
+                        // lane t + 2, lanes t >= 2 keep their last two and take the last two of lane t - 2 -> words 0-1 lie in the first
+                        // 64 nibbles of the chunk for every lane, words 2-3 in the second
+                        const bool lo = t < 2;
+                        const uint32_t s0 = lo ? va.z : va.x, s1 = lo ? va.w : va.y, s2 = lo ? vb.z : vb.x, s3 = lo ? vb.w : vb.y;
+                        const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 2), r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+                        const uint32_t r2 = __shfl_xor_sync(0xffffffffu, s2, 2), r3 = __shfl_xor_sync(0xffffffffu, s3, 2);
+                        if (lo) { va.z = r0; va.w = r1; vb.z = r2; vb.w = r3; }
+                        else { va.x = r0; va.y = r1; vb.x = r2; vb.y = r3; }
+                    }
+                    const uint32_t wav[4] = {va.x, va.y, va.z, va.w};
+                    const uint32_t wbv[4] = {vb.x, vb.y, vb.z, vb.w};
+                    // four independent accumulator chains per group half (column block x {first, second} MMA of a word): asm volatile keeps
+                    // the issue order, so consecutive MMAs must not share an accumulator (the HMMA result latency is ~10 issue slots)
+                    float dA[MB][4], dB[MB][4], eA[MB][4], eB[MB][4];
+#pragma unroll
+                    for (int c = 0; c < MB; ++c) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { dA[c][i] = 0.0f; dB[c][i] = 0.0f; eA[c][i] = 0.0f; eB[c][i] = 0.0f; }
+                    }
+                    // B fragment of word w_: activation items of chunk (c0 + j): first half items [8 * half + 2t + (w_ & 1)]
+                    // (FEED: after the exchange lane t's words 0-1 are items 4 (t & 1) + 2 (t >> 1) + {0, 1} of the chunk's first half)
+                    const uint32_t xi = ((c0 + j) - cb) * 16u + (FEED ? 4u * (uint32_t)(t & 1) + 2u * (uint32_t)(t >> 1) : 2u * (uint32_t)t);
+#pragma unroll
+                    for (int w_ = 0; w_ < 4; ++w_) {
+                        const uint32_t a0 = nib_pair_fast(wav[w_], 0, magic), a1 = nib_pair_fast(wav[w_], 4, magic), a2 = nib_pair_fast(wav[w_], 8, magic), a3 = nib_pair_fast(wav[w_], 12, magic);
+                        const uint32_t b0 = nib_pair_fast(wbv[w_], 0, magic), b1 = nib_pair_fast(wbv[w_], 4, magic), b2 = nib_pair_fast(wbv[w_], 8, magic), b3 = nib_pair_fast(wbv[w_], 12, magic);
+                        const uint32_t li = xi + (uint32_t)(w_ >> 1) * 8u + (uint32_t)(w_ & 1);
+                        uint4 xb[MB];
+#pragma unroll
+                        for (int c = 0; c < MB; ++c) xb[c] = xs[(size_t)(c * 8 + g) * xstride + li];
+                        if (NPG == 64 && w_ >= 2) {
+#pragma unroll
+                            for (int c = 0; c < MB; ++c) mma_16816(dB[c], a0, b0, a1, b1, xb[c].x, xb[c].y);
+#pragma unroll
+                            for (int c = 0; c < MB; ++c) mma_16816(eB[c], a2, b2, a3, b3, xb[c].z, xb[c].w);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < MB; ++c) mma_16816(dA[c], a0, b0, a1, b1, xb[c].x, xb[c].y);
+#pragma unroll
+                            for (int c = 0; c < MB; ++c) mma_16816(eA[c], a2, b2, a3, b3, xb[c].z, xb[c].w);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < MB; ++c) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { dA[c][i] += eA[c][i]; dB[c][i] += eB[c][i]; }
+                    }
+                    if (NPG == 64) {
+                        affine(dA, 2 * j);
+                        affine(dB, 2 * j + 1);
+                    } else {
+                        affine(dA, j);
+                    }
+                }
+            }
+        }
+
+        // ---- the WPT warps of a tile meet in shared memory; k-slices meet in the split-k workspace ------------------------------
+        {
+            float* rw = red + (size_t)warp * (MROWS * 16);
+#pragma unroll
+            for (int c = 0; c < MB; ++c) {
+                rw[(c * 8 + 2 * t) * 16 + g] = acc[c][0];
+                rw[(c * 8 + 2 * t + 1) * 16 + g] = acc[c][1];
+                rw[(c * 8 + 2 * t) * 16 + g + 8] = acc[c][2];
+                rw[(c * 8 + 2 * t + 1) * 16 + g + 8] = acc[c][3];
+            }
+        }
+        // WPT == 1: a warp owns its tile outright -- the shared-memory round trip is only the fragment -> row-major transposition, and the
+        // warps of the CTA never wait for each other (no bubble at item boundaries); WPT > 1: CTA barrier, warp w < TPC finishes tile w
+        if (WPT == 1) __syncwarp(); else __syncthreads();
+        if ((uint32_t)warp < TPC) {
+            const uint32_t my_tile = (item / kslices) * TPC + (uint32_t)warp;
+            if (my_tile < tiles) {
+                constexpr int OUTS = MROWS * 16 / 32;      // outputs per lane: o = lane + 32 i -> activation row o / 16, weight row o % 16
+                float sum[OUTS];
+#pragma unroll
+                for (int i = 0; i < OUTS; ++i) {
+                    sum[i] = 0.0f;
+                    for (uint32_t kp = 0; kp < WPT; ++kp) sum[i] += red[(size_t)((uint32_t)warp * WPT + kp) * (MROWS * 16) + lane + 32 * i];
+                }
+                auto store = [&](int i, float v) {
+                    const uint32_t o = (uint32_t)lane + 32u * (uint32_t)i;
+                    const uint32_t arow = o / 16u, row = my_tile * 16u + (o % 16u);
+                    if (arow >= p.m || row >= p.n) return;
+                    const size_t idx = (size_t)arow * p.n + row;
+                    float value = p.ab_scale * v;
+                    if (p.accumulate) value += p.d_is_f32 ? reinterpret_cast<float*>(p.d)[idx] : __bfloat162float(reinterpret_cast<__nv_bfloat16*>(p.d)[idx]);
+                    if (p.bias) value += __bfloat162float(p.bias[row]);
+                    if (p.has_soft_cap) value = p.soft_cap * tanhf(value / p.soft_cap);
+                    if (p.d_is_f32) reinterpret_cast<float*>(p.d)[idx] = value;
+                    else reinterpret_cast<__nv_bfloat16*>(p.d)[idx] = __float2bfloat16_rn(value);
+                };
+                if (kslices == 1) {
+#pragma unroll
+                    for (int i = 0; i < OUTS; ++i) store(i, sum[i]);
+                } else {
+                    float* wst = p.ws + ((size_t)my_tile * kslices + slice) * (MROWS * 16);
+#pragma unroll
+                    for (int i = 0; i < OUTS; ++i) wst[lane + 32 * i] = sum[i];
+                    __threadfence();
+                    __syncwarp();
+                    unsigned int ticket = 0;
+                    if (lane == 0) ticket = atomicAdd(&p.counters[my_tile], 1u);
+                    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+                    if (ticket == kslices - 1) {
+                        __threadfence();
+                        const float* wt = p.ws + (size_t)my_tile * kslices * (MROWS * 16);
+#pragma unroll
+                        for (int i = 0; i < OUTS; ++i) {
+                            float total = 0.0f;
+                            for (uint32_t sl = 0; sl < kslices; ++sl) total += __ldcg(wt + (size_t)sl * (MROWS * 16) + lane + 32 * i);
+                            store(i, total);
+                        }
+                        __syncwarp();
+                        if (lane == 0) p.counters[my_tile] = 0;
+                    }
+                }
+            }
+        }
+        if (WPT == 1) __syncwarp(); else __syncthreads();       // `red` is single-buffered
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // Generic kernel: one warp per output element, the reference loop verbatim (any dtype / layout / gather).
 // -------------------------------------------------------------------------------------------------
 struct GenericParams {
@@ -1549,6 +1951,42 @@ static void launch_qmv_decode_async(uzu_command_buffer* cmd, const QmvParams& p,
     }
 }
 
+template <int NPG, int STAGES, int METHOD, int BITS, int MB, int WARPS, int FEED>
+static void launch_qmv_rows_f(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
+    static std::atomic<uint64_t> smem_opt_in{0};
+    opt_in_dynamic_smem(cmd, qmv_rows_kernel<NPG, STAGES, METHOD, BITS, MB, WARPS, FEED>, (int)(227 * 1024), smem_opt_in);
+    launch(cmd, "qmv_rows_kernel", qmv_rows_kernel<NPG, STAGES, METHOD, BITS, MB, WARPS, FEED>, dim3(grid), dim3(WARPS * 32), smem, p);
+}
+template <int NPG, int STAGES, int METHOD, int BITS, int MB, int WARPS>
+static void launch_qmv_rows_s(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem) {
+    // FEED 1 (16-byte cp.async.cg + one quad exchange) measured 7-8 % faster than FEED 0 (two 8-byte cp.async.ca per chunk and row) on the
+    // Llama-3-8B shapes (profiles/r2y_trie_probe_f{0,1}.json); only FEED 1 is instantiated
+    launch_qmv_rows_f<NPG, STAGES, METHOD, BITS, MB, WARPS, 1>(cmd, p, grid, smem);
+}
+// (warps, stages): 16 warps x 2 stages (more warps to hide the latency of the ~1000-instruction stage) or 8 warps x 3 / 4 stages
+template <int NPG, int METHOD, int BITS>
+static void launch_qmv_rows_m(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem, int mb, int warps) {
+    if (warps == 16) { if (mb == 1) launch_qmv_rows_s<NPG, 2, METHOD, BITS, 1, 16>(cmd, p, grid, smem); else launch_qmv_rows_s<NPG, 2, METHOD, BITS, 2, 16>(cmd, p, grid, smem); }
+    else if (p.stages >= 4) { if (mb == 1) launch_qmv_rows_s<NPG, 4, METHOD, BITS, 1, 8>(cmd, p, grid, smem); else launch_qmv_rows_s<NPG, 4, METHOD, BITS, 2, 8>(cmd, p, grid, smem); }
+    else { if (mb == 1) launch_qmv_rows_s<NPG, 3, METHOD, BITS, 1, 8>(cmd, p, grid, smem); else launch_qmv_rows_s<NPG, 3, METHOD, BITS, 2, 8>(cmd, p, grid, smem); }
+}
+template <int NPG>
+static void launch_qmv_rows(uzu_command_buffer* cmd, const QmvParams& p, uint32_t grid, size_t smem, int mb, int warps) {
+    if (p.bits == 4) {
+        switch (p.method) {
+            case UZU_QMETHOD_SCALE_ZERO_POINT: launch_qmv_rows_m<NPG, UZU_QMETHOD_SCALE_ZERO_POINT, 4>(cmd, p, grid, smem, mb, warps); break;
+            case UZU_QMETHOD_SCALE_BIAS: launch_qmv_rows_m<NPG, UZU_QMETHOD_SCALE_BIAS, 4>(cmd, p, grid, smem, mb, warps); break;
+            default: launch_qmv_rows_m<NPG, UZU_QMETHOD_SCALE_SYMMETRIC, 4>(cmd, p, grid, smem, mb, warps); break;
+        }
+    } else if constexpr (NPG == 128) {     // int8: 64-element groups = 128 nibbles (int8 gs32 would be NPG 64: streaming kernel)
+        switch (p.method) {
+            case UZU_QMETHOD_SCALE_ZERO_POINT: launch_qmv_rows_m<NPG, UZU_QMETHOD_SCALE_ZERO_POINT, 8>(cmd, p, grid, smem, mb, warps); break;
+            case UZU_QMETHOD_SCALE_BIAS: launch_qmv_rows_m<NPG, UZU_QMETHOD_SCALE_BIAS, 8>(cmd, p, grid, smem, mb, warps); break;
+            default: launch_qmv_rows_m<NPG, UZU_QMETHOD_SCALE_SYMMETRIC, 8>(cmd, p, grid, smem, mb, warps); break;
+        }
+    }
+}
+
 // Tuning overrides for sweeps (0 = heuristic). Not part of the reference-facing API; set through uzu_debug_set_qmv_tuning.
 struct QmvTuning { int wpt = 0, dks = 0, per_sm = 0, stages = 0; };   // stages: 2..4 forces the cp.async ring depth
 static QmvTuning g_tune;
@@ -1608,13 +2046,107 @@ static bool encode_matmul(uzu_command_buffer* cmd, uzu_context* ctx_for_query, c
     if (fused && (a.m != 1 || (npg != 64 && npg != 128) || a.output_dt != UZU_DT_BF16 && a.output_dt != UZU_DT_F32)) return false;
     const int cpm = npg >= 128 ? 1 : 128 / npg;
     const int mpm = 8 / cpm;
-    const uint32_t max_rows = 4 * mpm;  // MT = 4
     const uint32_t tiles = (a.n + 15) / 16;
     const uint32_t chunks_total = (np + 127) / 128;
     const uint32_t chunk_align = npg > 128 ? npg / 128 : 1;
+    // rows kernel (2..16 activation rows per weight pass): int4 gs64 / gs128 and int8 gs64, whole super-chunks, aligned operands
+    static const bool rows_off = [] { const char* v = getenv("UZU_QMV_ROWS"); return v && atoi(v) == 0; }();
+    const bool rows_ok = !fused && !rows_off && a.m >= 2 && (npg == 128 || (npg == 64 && bits == 4)) && np % 512 == 0 && a.k % a.b_group_size == 0 &&
+                         (a.k / a.b_group_size) % (512u / npg) == 0 && ((a.b_scales & 15) == 0) && ((a.b_zero_points & 15) == 0) &&
+                         ((a.b_biases & 15) == 0) && (a.k * 2) % 16 == 0 && (np / 2) % 8 == 0;
+    const uint32_t max_rows = rows_ok ? 16u : 4u * mpm;  // MT = 4
 
     for (uint32_t m0 = 0; m0 < a.m; m0 += max_rows) {
         const uint32_t mb = std::min(max_rows, a.m - m0);
+        if (rows_ok && mb >= 2) {
+            const int MBk = mb <= 8 ? 1 : 2;
+            const uint32_t mrows_k = 8u * MBk, gps_k = 512u / npg;
+            const uint32_t scs = chunks_total / QS_SC;                       // super-chunks per row
+            // CTA shape: 16 warps x 2 ring stages or 8 warps x 3 / 4 stages (UZU_QMV_ROWS_WARPS = 8 | 16 overrides the default)
+            static const int warps_env = [] { const char* v = getenv("UZU_QMV_ROWS_WARPS"); return v ? atoi(v) : 0; }();
+            const uint32_t nw = warps_env == 8 ? 8u : (warps_env == 16 ? 16u : (uint32_t)UZU_QMV_ROWS_DEFAULT_WARPS);
+            // shared memory: rings (warps x stages x 4608 B) + reduction buffer + the m x slice activations (B-fragment items + group sums)
+            const size_t fixed = (size_t)nw * mrows_k * 16 * 4 + 256 + mrows_k * 4;
+            const size_t per_sc = (size_t)mrows_k * (QS_SC * 16 * 16) + (size_t)mrows_k * gps_k * 4;     // per super-chunk of slice (+ one pad word per row, in `fixed`)
+            const size_t budget = 225u * 1024u;
+            uint32_t stages = nw == 16 ? 2u : 4u;
+            auto dsc_max_for = [&](uint32_t st) {
+                const size_t rings = (size_t)nw * st * QA_STAGE_BYTES;
+                if (rings + fixed + mrows_k * 16 >= budget) return 0u;
+                return (uint32_t)((budget - rings - fixed - mrows_k * 16) / per_sc);
+            };
+            uint32_t dsc_max = dsc_max_for(stages);
+            if (nw == 8 && dsc_max < std::min(scs, 4u)) { stages = 3; dsc_max = dsc_max_for(3); }
+            if (dsc_max >= 1) {
+                // (k-slices, warps per tile): a CTA item = (nw / wpt) row tiles x one k-slice, every warp walks dsc / wpt super-chunks ("stages",
+                // ~1000 instructions each) and then pays one epilogue. With so few stages per warp the launch is a handful of dependent
+                // stage times long, so the choice minimises   rounds x (stages per warp + split-k epilogue + CTA barrier)   in stage units
+                // (measured on B200: a split-k epilogue -- workspace write, fence, ticket -- ~0.6 stage, a CTA barrier + shared reduction ~0.5).
+                const uint32_t ks_min = (scs + dsc_max - 1) / dsc_max;
+                uint32_t ks = ks_min, dsc = (scs + ks_min - 1) / ks_min, wpt = 1;
+                float best = 1e30f;
+                for (uint32_t ks_c = ks_min; ks_c <= std::min(scs, ks_min * 4u); ++ks_c) {
+                    const uint32_t dsc_c = (scs + ks_c - 1) / ks_c;
+                    const uint32_t ks_r = (scs + dsc_c - 1) / dsc_c;
+                    if (ks_r != ks_c) continue;                                   // same slice length as a smaller count
+                    if (ks_c > 1 && ((size_t)tiles * ks_c * mrows_k * 16 * 4 > ctx->splitk_ws_bytes || tiles > ctx->splitk_counter_count)) break;
+                    for (uint32_t w = 1; w <= 4u && w <= dsc_c; w *= 2) {
+                        const uint32_t tpc_c = nw / w;
+                        const uint32_t items_c = ((tiles + tpc_c - 1) / tpc_c) * ks_c;
+                        const uint32_t amax_c = std::max(ks_c, ((uint32_t)ctx->sm_count / ks_c) * ks_c);
+                        const uint32_t rounds_c = (items_c + amax_c - 1) / amax_c;
+                        const float est = (float)rounds_c * ((float)((dsc_c + w - 1) / w) + (ks_c > 1 ? 0.6f : 0.1f) + (w > 1 ? 0.5f : 0.0f));
+                        if (est < best) { best = est; ks = ks_c; dsc = dsc_c; wpt = w; }
+                    }
+                }
+                const uint32_t tpc = nw / wpt;
+                const uint32_t tgroups = (tiles + tpc - 1) / tpc;
+                const size_t ws_need = (size_t)tiles * ks * mrows_k * 16 * 4;
+                if ((ks == 1 || (ws_need <= ctx->splitk_ws_bytes && tiles <= ctx->splitk_counter_count))) {
+                    QmvParams p{};
+                    p.w = (const uint8_t*)a.b;
+                    p.scales = (const __nv_bfloat16*)a.b_scales;
+                    p.zero_points = (const uint8_t*)a.b_zero_points;
+                    p.biases = (const __nv_bfloat16*)a.b_biases;
+                    p.x = (const __nv_bfloat16*)a.a + (size_t)m0 * a.k;
+                    p.d = (void*)(a.d + (size_t)m0 * a.n * (a.output_dt == UZU_DT_F32 ? 4 : 2));
+                    p.bias = (a.d_transform & UZU_D_BIAS) ? (const __nv_bfloat16*)a.bias : nullptr;
+                    p.ws = ctx->splitk_ws;
+                    p.counters = ctx->splitk_counters;
+                    p.m = mb; p.n = a.n; p.k = a.k;
+                    p.np = np;
+                    p.row_bytes = np / 2;
+                    p.groups_per_row = a.k / a.b_group_size;
+                    p.zp_stride = bits == 4 ? (p.groups_per_row + 1) / 2 : p.groups_per_row;
+                    p.group_size = a.b_group_size;
+                    p.chunks_total = chunks_total; p.chunks_per_slice = dsc * QS_SC; p.kslices = ks;
+                    p.warps_per_tile = wpt;
+                    p.stages = stages;
+                    p.method = a.b_prologue == UZU_B_SCALE_BIAS_DEQUANT ? UZU_QMETHOD_SCALE_BIAS
+                               : a.b_prologue == UZU_B_SCALE_ZERO_POINT_DEQUANT ? UZU_QMETHOD_SCALE_ZERO_POINT : UZU_QMETHOD_SCALE_SYMMETRIC;
+                    p.bits = bits;
+                    p.xor_mask = a.b_signed_codes ? (bits == 4 ? 0x88888888u : 0x80808080u) : 0u;
+                    p.d_is_f32 = a.output_dt == UZU_DT_F32;
+                    p.accumulate = (a.d_transform & UZU_D_ACCUMULATE) != 0;
+                    p.has_soft_cap = (a.d_transform & UZU_D_SOFT_CAP) != 0;
+                    p.ab_scale = (a.d_transform & UZU_D_SCALE) ? a.ab_scale : 1.0f;
+                    p.soft_cap = a.soft_cap;
+                    const uint32_t items = tgroups * ks;
+                    // one CTA per SM; every CTA keeps one k-slice (grid multiple of ks) and gets (almost) the same number of items
+                    const uint32_t amax = std::max(ks, ((uint32_t)ctx->sm_count / ks) * ks);
+                    const uint32_t rounds = (items + amax - 1) / amax;
+                    uint32_t grid = (items + rounds - 1) / rounds;
+                    grid = std::min(amax, ((grid + ks - 1) / ks) * ks);
+                    const size_t xs_bytes = (size_t)mrows_k * ((size_t)dsc * QS_SC * 16 + 1) * 16;
+                    const size_t smem = xs_bytes + (size_t)mrows_k * ((dsc * gps_k) | 1u) * 4 + (size_t)nw * mrows_k * 16 * 4 + (size_t)nw * stages * QA_STAGE_BYTES;
+                    if (smem <= 227u * 1024u) {
+                        if (npg == 64) launch_qmv_rows<64>(cmd, p, grid, smem, MBk, (int)nw);
+                        else launch_qmv_rows<128>(cmd, p, grid, smem, MBk, (int)nw);
+                        continue;
+                    }
+                }
+            }
+        }
         int mt = (int)((mb + mpm - 1) / mpm);
         mt = mt <= 1 ? 1 : (mt == 2 ? 2 : 4);
         const uint32_t mrows = mt * mpm;
