@@ -80,9 +80,17 @@ def test_persistent_decode_device_chained_generation(ctx, tmp_path):
         eng.reset()
         eng.set_persistent_decode(False)
         c = eng.generate(prompt, 24)
-        # identical unless a near-tie flips one argmax: require a long common prefix
+        # identical unless a near-tie flips one argmax: at the first difference both candidates must be (near-)tied in the per-kernel
+        # path's own logits under teacher forcing with the common prefix
         common = next((i for i, (x, y) in enumerate(zip(a, c)) if x != y), len(a))
-        assert common >= 8, (a, c)
+        assert common >= 1, (a, c)
+        if common < len(a):
+            eng.reset()
+            eng.prefill(prompt)
+            for j in range(common):
+                eng.step_host(a[j])                     # feeding a[common - 1] produces output index `common`
+            lg = bf16_to_f32(eng.last_logits()[0])
+            assert abs(float(lg[a[common]]) - float(lg[c[common]])) <= 0.02 * float(np.abs(lg).max()) + 1e-3, (common, a, c)
         eng.set_persistent_decode(True)
         eng.reset()
         eng.prefill(prompt)
