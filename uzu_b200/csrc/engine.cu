@@ -2676,14 +2676,29 @@ uzu_status uzu_engine_batch_begin(uzu_engine* e, uint32_t sequences) {
         if (e->sampling.kind == UZU_SAMPLING_STOCHASTIC) throw std::runtime_error("batch decode samples greedily (per-row seeds are not wired yet)");
         if (e->logits_rows < sequences) throw std::runtime_error("batch_begin: logits scratch too small");
         cudaStreamSynchronize(e->ctx->stream);
+        if (e->seqs.size() != sequences && e->batch_graph) {
+            // the captured batched step holds the addresses of every sequence's state: a different set of sequences needs a new capture
+            cudaGraphExecDestroy(e->batch_graph);
+            e->batch_graph = nullptr;
+            e->batch_graph_B = 0;
+        }
         while (e->seqs.size() < sequences) {
             e->seqs.emplace_back();
             alloc_sequence_state(e, e->seqs.back().layers);
         }
+        auto release = [&](Buf& b) {          // buffers of a dropped sequence leave the engine's ownership list with it
+            if (!b.b) return;
+            auto it = std::find(e->owned.begin(), e->owned.end(), b.b);
+            if (it != e->owned.end()) e->owned.erase(it);
+            uzu_buffer_destroy(b.b);
+            b = Buf{};
+        };
         while (e->seqs.size() > sequences) {
             for (auto& S : e->seqs.back().layers) {
                 if (S.k_sparse) uzu_sparse_buffer_destroy(S.k_sparse);
                 if (S.v_sparse) uzu_sparse_buffer_destroy(S.v_sparse);
+                release(S.k_dense); release(S.v_dense);
+                release(S.conv_state); release(S.ssm_state); release(S.conv_snapshot); release(S.ssm_snapshot);
             }
             e->seqs.pop_back();
         }
