@@ -228,6 +228,64 @@ def test_attention_mask_ring_and_window():
     assert not (ring == full).all()
 
 
+def test_attention_trie_mask_is_ancestor_or_self_visibility():
+    """mask.rs:21-29: suffix key i is visible to query q iff trie_start(i) <= q <= trie_end(i), i.e. q lies in the subtree of node i -- key i is
+    an ancestor of the query's node or the node itself; every prefix key is visible. Float64 softmax over exactly that set, for a trie
+    with siblings at two depths, single-pass and two-pass cores."""
+    from uzu_b200.trie import TrieNode
+    root = TrieNode(0, 0)
+    a = TrieNode(1, 0); a.add(TrieNode(2, 0)); a.add(TrieNode(3, 0))
+    b = TrieNode(4, 0); c = TrieNode(5, 0); c.add(TrieNode(6, 0)); b.add(c)
+    root.add(a); root.add(b); root.add(TrieNode(7, 0))
+    flat = root.linearize()
+    nodes, parents = flat.nodes(), flat.parents()
+    H, Hkv, D, prefix, suffix = 4, 2, 64, 21, len(flat)
+    seq = prefix + suffix
+    q, k, v = attention_inputs(H, Hkv, seq, suffix, D)
+    kw = dict(head_dim=D, gqa_factor=H // Hkv, sequence_length=seq, k_head_stride=seq * D, k_seq_stride=D, v_head_stride=seq * D,
+              v_seq_stride=D, scale=float(np.float32(1.0) / np.sqrt(np.float32(D))), num_heads=H, suffix_length=suffix, is_causal=True)
+    sp = bf16_to_f32(O.attention_single_pass(q, k, v, trie=nodes, **kw))
+    tp = O.attention_two_pass(q, k, v, trie=nodes, **kw)
+    qf = bf16_to_f32(q).astype(np.float64).reshape(H, suffix, D)
+    kf = bf16_to_f32(k).astype(np.float64).reshape(Hkv, seq, D)
+    vf = bf16_to_f32(v).astype(np.float64).reshape(Hkv, seq, D)
+    for node in range(suffix):
+        anc, pnode = [], node
+        while pnode >= 0:
+            anc.append(pnode); pnode = parents[pnode]
+        visible = list(range(prefix)) + [prefix + i for i in sorted(anc)]
+        assert sorted(anc) == [i for i in range(suffix) if nodes[i, 0] <= node <= nodes[i, 1]]
+        for h in range(H):
+            s_ = kf[h // (H // Hkv)][visible] @ qf[h, node] / np.sqrt(D)
+            p_ = np.exp(s_ - s_.max()); p_ /= p_.sum()
+            np.testing.assert_allclose(sp[node, h], p_ @ vf[h // (H // Hkv)][visible], rtol=1e-2, atol=4e-3)
+    assert_bf16_close(tp, f32_to_bf16(sp), max_ulp=1, min_exact=0.9, what="two-pass vs single-pass with a trie")
+    # a flat chain is the causal mask
+    chain = TrieNode.flat(0, range(suffix), __import__("uzu_b200.trie", fromlist=["PRng"]).PRng(0)).linearize().nodes()
+    assert (O.attention_single_pass(q, k, v, trie=chain, **kw) == O.attention_single_pass(q, k, v, **kw)).all()
+
+
+def test_qkv_norm_and_logit_transform_closed_forms():
+    """qkv_norm.rs:36-76: per-head RMS norm over head_dim on the selected heads only, in place; logit_transform: scale then soft cap
+    cap * tanh(x / cap)."""
+    rng = np.random.default_rng(41)
+    rows, heads, D = 3, 6, 64
+    qkv = f32_to_bf16(rng.standard_normal((rows, heads * D)).astype(np.float32))
+    scales = (1.0 + 0.1 * rng.standard_normal(D)).astype(np.float32)
+    got = O.qkv_norm(qkv.copy(), scales, total_heads=heads, head_dim=D, epsilon=1e-6, scale_offset=0.0, head_offset=1, head_count=3, full_layer=False)
+    x = bf16_to_f32(qkv).astype(np.float64).reshape(rows, heads, D)
+    want = x.copy()
+    sel = x[:, 1:4]
+    want[:, 1:4] = sel / np.sqrt((sel ** 2).mean(axis=2, keepdims=True) + 1e-6) * scales
+    g = bf16_to_f32(got).reshape(rows, heads, D)
+    np.testing.assert_allclose(g[:, 1:4], want[:, 1:4], rtol=2e-2, atol=2e-3)
+    assert (got.reshape(rows, heads, D)[:, [0, 4, 5]] == qkv.reshape(rows, heads, D)[:, [0, 4, 5]]).all()   # untouched heads: bit-identical
+    logits = f32_to_bf16((rng.standard_normal(500) * 40).astype(np.float32)).reshape(1, 500)
+    out = O.logit_transform(logits.copy(), 0.5, 30.0)
+    ref = 30.0 * np.tanh(bf16_to_f32(logits).astype(np.float64) * 0.5 / 30.0)
+    np.testing.assert_allclose(bf16_to_f32(out), ref, rtol=1e-2, atol=1e-2)
+
+
 # ---- normalization / rope / prepare ------------------------------------------------------------------------
 def test_normalization_closed_form():
     # tests/unit/backends/common/kernel/normalization_test.rs:87-92 input pattern 0.5 + i*0.01
