@@ -53,3 +53,35 @@ def test_batched_decode_matches_independent_oracles(ctx, tmp_path, kind, nseq, g
         for b in range(nseq):
             assert ctx.lib.uzu_engine_batch_context_length(eng.h, b) == len(prompts[b]) + 5
         assert eng.batch_decode_timed(toks, 4) > 0.0                                     # device-chained steps run
+
+
+def test_batch_resize_frees_sequences_and_recaptures_the_graph(ctx, tmp_path):
+    """batch_begin with a different sequence count: dropped sequences release their state, re-created ones get fresh buffers, and the captured
+    batched step (which holds every sequence's buffer addresses) is re-captured -- the logits after 4 -> 2 -> 4 sequences equal those of a
+    fresh 4-sequence engine bit for bit."""
+    spec = synth.tiny("qwen-hybrid-512")
+    path = synth.write_model(spec, tmp_path / "m", seed=43)
+    rng = np.random.default_rng(10)
+    prompts = [rng.integers(0, spec.vocab_size, 6 + 3 * b) for b in range(4)]
+
+    def run(eng, nseq, steps=3):
+        eng.batch_begin(nseq)
+        toks = [eng.batch_prefill(b, prompts[b]) for b in range(nseq)]
+        out = []
+        for _ in range(steps):
+            toks = eng.batch_step(toks)
+            out.append(eng.batch_logits()[:nseq].copy())
+        return out
+
+    with B.Engine(ctx, path, max_context_length=128, use_cuda_graph=True) as eng:
+        first = run(eng, 4)
+        two = run(eng, 2)
+        again = run(eng, 4)
+    with B.Engine(ctx, path, max_context_length=128, use_cuda_graph=True) as fresh:
+        want = run(fresh, 4)
+    for a, b, c in zip(first, again, want):
+        assert (a == c).all() and (b == c).all()
+    with B.Engine(ctx, path, max_context_length=128, use_cuda_graph=True) as fresh2:
+        want2 = run(fresh2, 2)
+    for a, c in zip(two, want2):
+        assert (a == c).all()
