@@ -77,3 +77,27 @@ def test_library_registers_every_struct_the_rust_start_up_check_asks_about(lib):
 def test_committed_kernel_table_is_what_the_reference_declares():
     ext = _load("extract_kernel_table")
     assert ext.extract(Path("/root/reference")) == TABLE, "run python tools/extract_kernel_table.py"
+
+
+def _strip_rust(text: str) -> str:
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    text = re.sub(r'"(\\.|[^"\\])*"', '""', text)
+    return re.sub(r"'(\\.|[^\\'])'", "' '", text)          # char literals; lifetimes ('a) have no closing quote and stay
+
+
+def test_every_rust_file_has_balanced_delimiters():
+    """No rustc in the image: at least the cheapest class of slip (an unbalanced brace / bracket / parenthesis in hand-written or generated
+    glue) is caught here."""
+    pairs = {")": "(", "]": "[", "}": "{"}
+    files = sorted((ROOT / "integration" / "rust").rglob("*.rs"))
+    assert len(files) >= 9
+    for f in files:
+        stack = []
+        for i, ch in enumerate(_strip_rust(f.read_text())):
+            if ch in "([{":
+                stack.append(ch)
+            elif ch in pairs:
+                assert stack and stack[-1] == pairs[ch], f"{f.name}: unbalanced {ch!r} at offset {i}"
+                stack.pop()
+        assert not stack, f"{f.name}: unclosed {stack[-1]!r}"

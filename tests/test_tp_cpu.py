@@ -115,6 +115,40 @@ def test_two_rank_oracle_matches_unsharded(tmp_path, kind, quant):
         assert int(np.argmax(bf16_to_f32(a[0]))) == int(np.argmax(bf16_to_f32(w[0])))
 
 
+def test_eight_rank_oracle_with_llama3_head_geometry(tmp_path):
+    """BASELINE config 5's split (TP = 8) on a small model with Llama-3's head geometry ratios: 8 kv heads -> one per rank, q heads 4 per
+    kv head, FFN columns and vocabulary in 8 slices, every K shard an even number of quantisation groups. The 8 rank oracles (threads,
+    lockstep exchange) must reproduce the unsharded logits."""
+    from uzu_b200.synth import LLAMA3_ROPE, ModelSpec
+    spec = ModelSpec(name="tiny-llama-8kv", model_dim=256, hidden_dim=1024, vocab_size=1024, layer_kinds=["attn"] * 2, num_heads=32, num_groups=8,
+                     head_dim=32, rope=dict(LLAMA3_ROPE, head_dim=32), quant=synth.QuantSpec("int", 4, 64, False))
+    full, shards = _write_shards(tmp_path, spec, 8)
+    cfg = json.loads((shards[5] / "config.json").read_text())
+    mc = cfg["decoder_config"]["transformer_config"]["layer_configs"][0]["mixer_config"]
+    assert (mc["num_heads"], mc["num_groups"]) == (4, 1) and cfg["tensor_parallel"]["vocab_size_local"] == 128
+    rng = np.random.default_rng(6)
+    prompt = rng.integers(0, spec.vocab_size, 7)
+    ref = OracleModel(full, max_context=64)
+    want = [ref.forward(prompt), ref.forward([11])]
+    ex = _LockstepExchange(8)
+    got = [None] * 8
+
+    def run(rank):
+        red, gat = ex.hooks(rank)
+        m = OracleModel(shards[rank], max_context=64, tp_reduce=red, tp_gather=gat)
+        got[rank] = [m.forward(prompt), m.forward([11])]
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(8)]
+    [t.start() for t in threads]
+    [t.join(timeout=180) for t in threads]
+    assert all(g is not None for g in got)
+    for step, w in enumerate(want):
+        for r in range(1, 8):
+            assert (got[r][step] == got[0][step]).all()
+        scale = float(np.abs(bf16_to_f32(w)).max())
+        assert float(np.abs(bf16_to_f32(got[0][step]) - bf16_to_f32(w)).max()) <= 0.02 * scale + 1e-3
+
+
 def test_two_rank_gloo_processes(tmp_path):
     spec = synth.tiny("llama")
     full, shards = _write_shards(tmp_path, spec, 2)
