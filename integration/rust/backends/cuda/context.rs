@@ -36,7 +36,7 @@ impl Context for CudaContext {
     /// DenseBuffer::cpu_ptr must work (the loader preads weights through it, parameters/loader.rs:162-179): managed memory with
     /// preferred location = device; `CudaBuffer::make_resident` migrates the pages to HBM once after the load.
     fn create_buffer(&self, size: usize) -> Result<CudaBuffer, CudaError> {
-        CudaBuffer::new(self, size, ffi::UZU_BUFFER_MANAGED)
+        CudaBuffer::new(self, size, ffi::UZU_BUFFER_MANAGED as i32)
     }
 
     fn create_allocation(&self, size: usize, allocation_type: AllocationType<Cuda>) -> Result<Allocation<Cuda>, CudaError> {
