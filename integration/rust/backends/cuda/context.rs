@@ -19,6 +19,7 @@ impl Context for CudaContext {
     type Backend = Cuda;
 
     fn new() -> Result<Arc<Self>, CudaError> {
+        ffi::abi_self_check();      // a glue layer compiled against another header revision must not run
         let mut raw = std::ptr::null_mut();
         // -1: CUDA current device or $UZU_DEVICE (one process per GPU for tensor parallel runs)
         check(unsafe { ffi::uzu_context_create(-1, &mut raw) })?;
