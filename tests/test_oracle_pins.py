@@ -598,3 +598,38 @@ def test_matmul_output_rht_runs_bias_after_the_transform():
     # and it is NOT the bias-before-transform order
     wrong = O.activation_transform(O.matmul(x, w, bias=bias, **kw), factors, op=O.RHT_OUTPUT)
     assert (wrong != got).any()
+
+
+def test_tensor_glue_fp_embedding_and_bitmask_sampling_closed_forms():
+    """The small kernels around the hot path: tensor_{add_scale,add_bias,add_swap,copy}/*.rs (one bf16 rounding of the f32 result),
+    full_precision_embedding.rs (row copy x input_scale, out-of-range id -> zeros), unified_sampling.rs:48-55 (a cleared grammar bit makes
+    the logit -inf before anything else)."""
+    rng = np.random.default_rng(51)
+    rows, n = 3, 40
+    x = f32_to_bf16(rng.standard_normal((rows, n)).astype(np.float32))
+    b = f32_to_bf16(rng.standard_normal(n).astype(np.float32))
+    xf, bf = bf16_to_f32(x).astype(np.float64), bf16_to_f32(b).astype(np.float64)
+    assert (O.tensor_add_bias(x, b, n) == f32_to_bf16((xf + bf).astype(np.float32))).all()
+    assert (O.tensor_add_scale(x, b, n, 0.25) == f32_to_bf16(((xf + bf) * 0.25).astype(np.float32))).all()
+    skip, main = x.copy(), f32_to_bf16(rng.standard_normal((rows, n)).astype(np.float32))
+    want = f32_to_bf16((bf16_to_f32(skip) + bf16_to_f32(main)).astype(np.float32))
+    O.tensor_add_swap(skip, main)
+    assert (skip == want).all() and (main == want).all()
+    V, H = 9, 16
+    w = f32_to_bf16(rng.standard_normal((V, H)).astype(np.float32))
+    out = O.fp_embedding_lookup(np.array([8, 0, 9], np.uint32), w, vocab_size=V, model_dim=H, input_scale=1.5)
+    np.testing.assert_allclose(bf16_to_f32(out[:2]), 1.5 * bf16_to_f32(w[[8, 0]]), rtol=2 ** -8)
+    assert (out[2] == 0).all()
+    # bitmask: only allowed ids can win, greedy and stochastic alike
+    Vv = 100
+    logits = f32_to_bf16(rng.standard_normal((2, Vv)).astype(np.float32))
+    allowed = [[3, 64, 65], [99]]
+    mask = np.zeros((2, (Vv + 31) // 32), np.uint32)
+    for r, ids in enumerate(allowed):
+        for i in ids:
+            mask[r, i // 32] |= np.uint32(1 << (i % 32))
+    g = O.unified_sampling(logits, bitmask=mask)
+    f = bf16_to_f32(logits)
+    assert int(g[0]) == max(allowed[0], key=lambda i: (f[0, i], -i)) and int(g[1]) == 99
+    s = O.unified_sampling(logits, bitmask=mask, seeds=np.array([7, 8], np.uint64), temperature=1.3)
+    assert int(s[0]) in allowed[0] and int(s[1]) == 99
